@@ -1,0 +1,165 @@
+/* opencloth.h — C-ABI of libopencloth_b200.so
+ *
+ * A B200-native (sm_100a) drop-in for ONE path of mmmovania/opencloth: the Verlet mass-spring
+ * cloth step  StepPhysics = ComputeForces -> IntegrateVerlet -> EllipsoidCollision  of
+ * OpenCloth_Verlet/OpenCloth_Verlet/main.cpp ("V:" below; StepPhysics is V:557-562).
+ *
+ * The reference has no library interface: the step is a free function over file-scope globals
+ * (V:76-80 X, X_last, F, springs; V:97-104 and V:123-130 parameters), initialised by InitGL
+ * (V:249-327) and driven by OnIdle (V:548-552).  Its own GPU back ends (5-mode demo "C:" =
+ * OpenCloth_Verlet_CUDA_GLSL_OPENCL_CPU/OpenCloth_Verlet_CUDA/main.cpp:145-154, verlet.cu "H:",
+ * verlet_cl.cpp "LH:") expose the de-facto operator interface Init / Upload / Verlet / ReadBuffer /
+ * Shutdown.  Each entry point below says which of those it replaces.
+ *
+ * Conventions: every function returns OC_OK (0) or a negative oc_status and never aborts
+ * (the reference's cutilSafeCall / oclCheckError abort, H:21, LH:30); oc_last_error() gives the text of
+ * the last failure on the calling thread.  A handle is not thread safe; distinct handles are
+ * independent.  The caller owns every host buffer.  oc_step is asynchronous; oc_sync / oc_download
+ * wait.  There is NO CPU fallback: without a CUDA device every compute call fails with
+ * OC_ERR_NO_DEVICE.
+ *
+ * Particle (i,j), i = column 0..nx-1 (x direction), j = row 0..ny-1 (z direction), linear index
+ * j*nx + i, exactly as V:254-259.  Host-side state is float[3] (stride 3, the reference's
+ * vector<glm::vec3>) or float[4] (stride 4, the float4 of the reference's GPU back ends, w = 1).
+ */
+#ifndef OPENCLOTH_H
+#define OPENCLOTH_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OC_ABI_VERSION 1
+
+typedef enum oc_status {
+    OC_OK = 0,
+    OC_ERR_INVALID = -1,     /* bad argument */
+    OC_ERR_NO_DEVICE = -2,   /* no CUDA device / driver: there is no CPU fallback */
+    OC_ERR_CUDA = -3,        /* a CUDA runtime call failed (text in oc_last_error) */
+    OC_ERR_NOMEM = -4,
+    OC_ERR_UNSUPPORTED = -5
+} oc_status;
+
+typedef enum oc_kernel {
+    OC_KERNEL_AUTO = 0,      /* marching stencil kernel where the grid allows, else gather */
+    OC_KERNEL_GATHER = 1,    /* one thread per particle, 12-neighbour gather from global memory */
+    OC_KERNEL_MARCH = 2      /* fused shared-memory marching stencil, k substeps per launch */
+} oc_kernel;
+
+typedef struct oc_cloth oc_cloth;      /* opaque; owns all device memory of one simulation */
+
+/* All defaults (oc_default_params) are the reference's values. */
+typedef struct oc_params {
+    /* ---- fixed at oc_create ------------------------------------------------------------- */
+    int   nx, ny;              /* particles per row / per column; reference 21 x 21 = (numX+1, numY+1), V:59 */
+    int   batch;               /* independent cloths stepped together (1 = the reference's single cloth)  */
+    int   row_begin, row_end;  /* row band [row_begin,row_end) of the ny rows this handle owns.
+                                  0,0 = whole cloth.  Used by the multi-process row-band driver:
+                                  one handle per GPU, see oc_halo_* below.                                  */
+    int   halo_rows;           /* band only: rows of neighbour state kept either side (multiple of 2)    */
+    int   device;              /* CUDA device ordinal, -1 = current                                        */
+    float fullsize;            /* 4.0f, V:61 (halfsize = fullsize/2, V:62); cloth spans x[-2,2] z[0,4] y=5 */
+    /* ---- changeable with oc_set_params ---------------------------------------------------- */
+    int   substeps_per_launch; /* k: temporal blocking, 1..8 (march kernel); 0 = library default        */
+    int   exact;               /* 1 = IEEE op-for-op order of the reference (bitwise equal to its CPU
+                                  path); 0 = fast (FMA contraction, MUFU rsqrt; within the stated tolerance) */
+    int   kernel;              /* oc_kernel                                                                */
+    float ks_struct, kd_struct;/* 50.75f, -0.25f  V:98  */
+    float ks_shear,  kd_shear; /* 50.75f, -0.25f  V:99  */
+    float ks_bend,   kd_bend;  /* 50.95f, -0.25f  V:100 */
+    float damping;             /* -0.0125f  V:97 DEFAULT_DAMPING */
+    float gravity[3];          /* 0, -0.00981f, 0  V:101 */
+    float mass;                /* 1.0f  V:102 */
+    float dt;                  /* 1/60.0f  V:104 timeStep */
+    float ellipsoid[16];       /* column-major; translate(0,2,0)*rotate(45deg,x)*scale(1,1,.5)  V:324-326 */
+    float inv_ellipsoid[16];   /* glm::inverse(ellipsoid)  V:327 */
+    float center[3];           /* 0,0,0  V:129 */
+    float radius;              /* 1.0f   V:130 */
+} oc_params;
+
+/* Fill *p with the reference's values for an nx x ny cloth (replaces the globals V:59-62, V:97-104,
+ * V:123-130 and the ellipsoid set-up V:324-327). */
+int oc_default_params(oc_params* p, int nx, int ny);
+
+/* Allocate device state and initialise X = X_last = the flat sheet of InitGL (V:249-260); the
+ * spring net of V:286-320 is implicit in (i,j), its rest lengths are derived from the same fp32
+ * expressions (V:141-142).  Replaces InitGL's physics part, InitCUDA (H:16-25) and the one-time
+ * upload in UploadCUDA (H:53-79). */
+int oc_create(oc_cloth** out, const oc_params* p);
+
+/* Change run-time scalars (spring constants, damping, gravity, mass, dt, collider, k, exact,
+ * kernel).  nx, ny, batch, band and fullsize are fixed at create and must match.  Replaces editing
+ * the globals V:97-104 / V:123-130 (and the per-call scalar arguments of VerletCUDA, H:81). */
+int oc_set_params(oc_cloth* c, const oc_params* p);
+int oc_get_params(const oc_cloth* c, oc_params* p);
+
+/* Overwrite the state with host arrays (stride_floats 3 or 4), batch*rows*nx particles of this
+ * handle's band, cloth-major then row-major.  Replaces UploadCUDA(positions, positions_old, size)
+ * (H:53) / UploadOpenCL (LH:155). */
+int oc_upload(oc_cloth* c, const float* X, const float* X_last, int stride_floats);
+
+/* n x StepPhysics(dt) (V:557-562; the body of the OnIdle step V:548-552 and of VerletCUDA H:81-100).
+ * Asynchronous on the handle's stream. */
+int oc_step(oc_cloth* c, int n);
+
+/* Wait for all queued work (the reference's cudaThreadSynchronize H:96 / clFinish LH:213). */
+int oc_sync(oc_cloth* c);
+
+/* Synchronise and copy the state to host arrays (either pointer may be NULL).  Replaces the mapped
+ * VBO read (C:603-605) / ReadBuffer (LH:219). */
+int oc_download(oc_cloth* c, float* X, float* X_last, int stride_floats);
+
+/* ShutdownCUDA (H:27) / OnShutdown (V:418-424). */
+void oc_destroy(oc_cloth* c);
+
+/* Text of the last error on this thread ("" if none). */
+const char* oc_last_error(void);
+
+/* ---- interaction write-back (mouse drag, V:203-208): X[idx] = X_last[idx] = xyz ---------------- */
+int oc_set_particle(oc_cloth* c, int cloth, int idx, const float xyz[3]);
+
+/* ---- stream / timing plumbing (the host side owns streams; torch passes its current stream) --- */
+int oc_set_stream(oc_cloth* c, void* cuda_stream);          /* cudaStream_t; NULL = handle's own stream */
+/* kernels launched by this handle since create (bench.py's gpu_launches) */
+long long oc_launch_count(const oc_cloth* c);
+/* time n substeps on the device with CUDA events on the handle's stream; returns milliseconds */
+int oc_step_timed(oc_cloth* c, int n, float* ms);
+
+/* ---- row-band halo plumbing (multi-GPU) ----------------------------------
+ * A band handle stores rows [row_begin-halo_rows, row_end+halo_rows) clipped to [0,ny).  After the
+ * neighbours' halo rows are current, oc_step(c, n) with n <= halo_rows/2 advances the band by n
+ * substeps, recomputing a shrinking part of the halo (communication-avoiding: one exchange per
+ * halo_rows/2 substeps).  The exchange itself is done by the host: device pointers of the rows to
+ * send and of the halo rows to fill are exposed here, each a contiguous run of
+ * rows*nx float4 (x,y,z,w).  Two buffers (X at t and X at t-1) are exchanged.
+ *   side: 0 = towards row 0 (upper neighbour), 1 = towards row ny-1 (lower neighbour)
+ *   which: 0 = X(t) buffer, 1 = X(t-1) buffer
+ * Returns the pointer in *dev_ptr and the element count (float4s) in *count (0 if that side is
+ * the cloth boundary). */
+int oc_halo_send_region(oc_cloth* c, int side, int which, void** dev_ptr, size_t* count);
+int oc_halo_recv_region(oc_cloth* c, int side, int which, void** dev_ptr, size_t* count);
+/* tell the handle that the halo rows are current again (resets the shrink counter) */
+int oc_halo_refreshed(oc_cloth* c);
+/* substeps that can still be taken before the next exchange is required */
+int oc_halo_budget(const oc_cloth* c);
+/* Single-process exchange: bands[0..n) are the bands of ONE cloth in row order (same process, same
+ * or different devices).  Copies every send region into the neighbour's halo (cudaMemcpyPeerAsync
+ * across devices, i.e. NVLink on an HGX box), ordered after each band's queued work and before its
+ * next step, without blocking the host, then marks all bands refreshed. */
+int oc_halo_exchange(oc_cloth* const* bands, int n);
+
+/* ---- diagnostics ----------------------------------------------------------------------------- */
+/* Spring energy  sum 1/2 Ks (|p1-p2| - rest)^2  over the reference's spring list (duplicated edge
+ * bend springs included), reduced in double on the device; whole-cloth handles only. */
+int oc_spring_energy(oc_cloth* c, int cloth, double* energy);
+/* sizeof(oc_params) as the library was compiled, so that FFI bindings can verify their mirror */
+size_t oc_sizeof_params(void);
+/* library / device info string: "opencloth_b200 abi=1 sm=100 device=NVIDIA B200 ..." */
+const char* oc_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OPENCLOTH_H */

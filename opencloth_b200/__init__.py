@@ -1,0 +1,12 @@
+"""opencloth_b200 — B200-native (sm_100a) Verlet mass-spring cloth step of mmmovania/opencloth.
+
+Only the hot path: StepPhysics = ComputeForces -> IntegrateVerlet -> EllipsoidCollision
+(/root/reference/OpenCloth_Verlet/OpenCloth_Verlet/main.cpp:557-562), behind the C-ABI of
+include/opencloth.h.  Importing the package does not need a GPU; creating a ``Cloth`` does, and
+fails loudly without one (there is no CPU fallback).
+"""
+from ._abi import (LIB_PATH, OcParams, OpenClothError, OC_KERNEL_AUTO, OC_KERNEL_GATHER, OC_KERNEL_MARCH)
+from .cloth import Cloth, default_params, version
+
+__all__ = ["Cloth", "default_params", "version", "OcParams", "OpenClothError", "LIB_PATH",
+           "OC_KERNEL_AUTO", "OC_KERNEL_GATHER", "OC_KERNEL_MARCH"]

@@ -1,0 +1,160 @@
+"""Host-side mirror of the reference's cloth step interface, over the C-ABI.
+
+The reference (mmmovania/opencloth, OpenCloth_Verlet/OpenCloth_Verlet/main.cpp, "V:") has no class:
+``InitGL`` (V:232-328) builds the state, ``StepPhysics(dt)`` (V:557-562) advances it, the render
+loop reads the global ``X`` (V:78).  Its own GPU back ends use Init / Upload / Verlet / ReadBuffer /
+Shutdown (…/OpenCloth_Verlet_CUDA/verlet.cu:16-100, verlet_cl.cpp:57-222).  ``Cloth`` keeps those
+names' meaning:
+
+    cloth = Cloth(nx=21, ny=21)        # InitGL + InitCUDA + UploadCUDA: flat sheet, springs, collider
+    cloth.step(1000)                   # 1000 x StepPhysics(timeStep)
+    X, X_last = cloth.download()       # ReadBuffer
+
+Everything runs in libopencloth_b200.so (CUDA, sm_100a).  numpy is only used for host buffers.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _abi
+from ._abi import OcParams, check
+
+
+def default_params(nx=21, ny=21, **overrides):
+    """``oc_params`` filled with the reference's values (V:59-62, V:97-104, V:123-130, V:324-327)."""
+    p = OcParams()
+    check(_abi.load().oc_default_params(ctypes.byref(p), nx, ny))
+    for k, v in overrides.items():
+        if not hasattr(p, k):
+            raise AttributeError(f"oc_params has no field {k!r}")
+        cur = getattr(p, k)
+        if hasattr(cur, "__len__"):
+            for i, x in enumerate(v):
+                cur[i] = x
+        else:
+            setattr(p, k, v)
+    return p
+
+
+class Cloth:
+    """One simulation (or a batch of independent ones, or one row band of a large one)."""
+
+    def __init__(self, nx=21, ny=21, params=None, **overrides):
+        self._lib = _abi.load()
+        self._h = ctypes.c_void_p()
+        self.params = params if params is not None else default_params(nx, ny, **overrides)
+        h = ctypes.c_void_p()
+        check(self._lib.oc_create(ctypes.byref(h), ctypes.byref(self.params)))
+        self._h = h
+        q = OcParams()
+        check(self._lib.oc_get_params(self._h, ctypes.byref(q)))
+        self.params = q
+        self.nx, self.ny, self.batch = q.nx, q.ny, q.batch
+        self.rows = q.row_end - q.row_begin
+        self.n_local = self.batch * self.rows * self.nx     # particles held by this handle
+
+    # ---- reference surface -------------------------------------------------------------------
+    def step(self, n=1):
+        """n x StepPhysics(dt) (V:557-562). Asynchronous."""
+        check(self._lib.oc_step(self._h, int(n)))
+
+    def step_timed(self, n=1):
+        """n substeps timed with CUDA events on the handle's stream; returns milliseconds."""
+        ms = ctypes.c_float()
+        check(self._lib.oc_step_timed(self._h, int(n), ctypes.byref(ms)))
+        return ms.value
+
+    def sync(self):
+        check(self._lib.oc_sync(self._h))
+
+    def download(self, stride=3, out=None):
+        """Returns (X, X_last) as float32 arrays of shape (n_local, stride)."""
+        if out is None:
+            x = np.empty((self.n_local, stride), np.float32)
+            xl = np.empty((self.n_local, stride), np.float32)
+        else:
+            x, xl = out
+        check(self._lib.oc_download(self._h, x.ctypes.data_as(ctypes.c_void_p),
+                                    xl.ctypes.data_as(ctypes.c_void_p), stride))
+        return x, xl
+
+    def download_into(self, x_ptr, xl_ptr, stride=3):
+        """Download into raw host pointers (ints), e.g. pinned torch tensors' data_ptr()."""
+        check(self._lib.oc_download(self._h, ctypes.c_void_p(x_ptr), ctypes.c_void_p(xl_ptr) if xl_ptr else None, stride))
+
+    def upload(self, x, x_last):
+        x = np.ascontiguousarray(x, np.float32)
+        xl = np.ascontiguousarray(x_last, np.float32)
+        stride = x.shape[-1]
+        if x.size != self.n_local * stride or xl.size != x.size:
+            raise ValueError(f"expected {self.n_local} x {stride} floats")
+        check(self._lib.oc_upload(self._h, x.ctypes.data_as(ctypes.c_void_p), xl.ctypes.data_as(ctypes.c_void_p), stride))
+
+    def upload_from(self, x_ptr, xl_ptr, stride=3):
+        check(self._lib.oc_upload(self._h, ctypes.c_void_p(x_ptr), ctypes.c_void_p(xl_ptr), stride))
+
+    def set_params(self, **overrides):
+        """Edit run-time scalars (V:97-104, V:123-130): spring constants, damping, gravity, dt, collider,
+        substeps_per_launch, exact, kernel."""
+        p = self.params
+        for k, v in overrides.items():
+            cur = getattr(p, k)
+            if hasattr(cur, "__len__"):
+                for i, x in enumerate(v):
+                    cur[i] = x
+            else:
+                setattr(p, k, v)
+        check(self._lib.oc_set_params(self._h, ctypes.byref(p)))
+
+    def set_particle(self, idx, xyz, cloth=0):
+        """Mouse-drag write-back of the reference (V:203-208): X[idx] = X_last[idx] = xyz."""
+        v = (ctypes.c_float * 3)(*[float(t) for t in xyz])
+        check(self._lib.oc_set_particle(self._h, int(cloth), int(idx), v))
+
+    def spring_energy(self, cloth=0):
+        e = ctypes.c_double()
+        check(self._lib.oc_spring_energy(self._h, int(cloth), ctypes.byref(e)))
+        return e.value
+
+    # ---- plumbing ----------------------------------------------------------------------------
+    def set_stream(self, cuda_stream_ptr):
+        check(self._lib.oc_set_stream(self._h, ctypes.c_void_p(cuda_stream_ptr) if cuda_stream_ptr else None))
+
+    @property
+    def launch_count(self):
+        return int(self._lib.oc_launch_count(self._h))
+
+    def halo_region(self, side, which, send):
+        ptr = ctypes.c_void_p()
+        cnt = ctypes.c_size_t()
+        fn = self._lib.oc_halo_send_region if send else self._lib.oc_halo_recv_region
+        check(fn(self._h, side, which, ctypes.byref(ptr), ctypes.byref(cnt)))
+        return (ptr.value or 0), cnt.value
+
+    def halo_refreshed(self):
+        check(self._lib.oc_halo_refreshed(self._h))
+
+    @property
+    def halo_budget(self):
+        return int(self._lib.oc_halo_budget(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.oc_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
+def version():
+    return _abi.load().oc_version().decode()

@@ -1,0 +1,564 @@
+// oc_api.cu — the C-ABI of include/opencloth.h: handle, device memory, launches.
+//
+// Host side of the hot path.  Replaces, for the Verlet demo of the reference
+// (/root/reference/OpenCloth_Verlet/OpenCloth_Verlet/main.cpp, "V:"), the physics part of InitGL
+// (V:249-327), the OnIdle step (V:548-552) and OnShutdown (V:418-424); and for the reference's own
+// GPU back end (…/OpenCloth_Verlet_CUDA/verlet.cu, "H:") InitCUDA/UploadCUDA/VerletCUDA/ShutdownCUDA
+// (H:16-100).  No torch types, no CPU fallback: every compute entry point needs a CUDA device.
+#include "../../include/opencloth.h"
+#include "oc_core.cuh"
+#include "oc_host.h"
+#include "oc_gather.cuh"
+#include "oc_march.cuh"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cstdarg>
+#include <vector>
+#include <new>
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int oc_fail(int code, const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define OC_CUDA(call)                                                                            \
+    do {                                                                                         \
+        cudaError_t e_ = (call);                                                                 \
+        if (e_ != cudaSuccess)                                                                   \
+            return oc_fail((e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver)        \
+                               ? OC_ERR_NO_DEVICE : (e_ == cudaErrorMemoryAllocation ? OC_ERR_NOMEM : OC_ERR_CUDA), \
+                           "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+extern "C" const char* oc_last_error(void) { return g_err; }
+
+// ------------------------------------------------------------------------------------------------
+// handle
+// ------------------------------------------------------------------------------------------------
+struct oc_cloth {
+    oc_params p;
+    OcConst   k;                 // kernel constants (device pointers inside)
+    int       dev;
+    int       sm_count;
+    float4*   buf[4];            // rotating position buffers
+    OcSeq     q;                 // buffer rotation + band shrink counter (oc_host.h)
+    float*    tables;            // device: xs[U] zs[V] rh1[U] rh2[U] dx2[U] rv1[V] rv2[V] dz2[V]
+    float*    d_xs; float* d_zs;
+    long long stored;            // float4 elements per buffer (batch * srows * U)
+    int       rows_own;          // row_end - row_begin
+    cudaStream_t own_stream, stream;
+    cudaEvent_t  ev0, ev1;
+    cudaEvent_t  ev_ready, ev_filled;   // band exchange: my rows are final / my halo has been written
+    long long launches;
+    float*    stage[2];          // device staging for upload/download
+    size_t    stage_bytes;
+    double*   d_energy;
+};
+
+static int free_handle(oc_cloth* c)
+{
+    if (!c) return OC_OK;
+    for (int i = 0; i < 4; ++i) if (c->buf[i]) cudaFree(c->buf[i]);
+    if (c->tables) cudaFree(c->tables);
+    if (c->stage[0]) cudaFree(c->stage[0]);
+    if (c->stage[1]) cudaFree(c->stage[1]);
+    if (c->d_energy) cudaFree(c->d_energy);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->ev_ready) cudaEventDestroy(c->ev_ready);
+    if (c->ev_filled) cudaEventDestroy(c->ev_filled);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+    return OC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// defaults: the reference's globals (oc_host.h)
+// ------------------------------------------------------------------------------------------------
+extern "C" int oc_default_params(oc_params* p, int nx, int ny)
+{
+    if (!p) return oc_fail(OC_ERR_INVALID, "oc_default_params: null");
+    oc_host_default_params(p, nx, ny);
+    return OC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// small kernels: initial sheet, pack / unpack, particle write-back, energy
+// ------------------------------------------------------------------------------------------------
+__global__ void oc_k_init(OcConst c, const float* __restrict__ xs, const float* __restrict__ zs, float y,
+                          float4* __restrict__ A, float4* __restrict__ B)
+{
+    long long per = (long long)c.srows * c.U;
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= per * c.batch) return;
+    long long r = t % per;
+    int j = (int)(r / c.U) + c.row_lo, i = (int)(r % c.U);
+    float4 v = make_float4(xs[i], y, zs[j], oc_u2f(OC_W_PLAIN));       // V:256-257
+    A[t] = v; B[t] = v;
+}
+
+// host layout (stride 3 or 4, owned rows only) -> float4 storage (owned rows inside the halo'd store)
+__global__ void oc_k_unpack(OcConst c, int row_begin, int rows, int stride,
+                            const float* __restrict__ X, const float* __restrict__ XL,
+                            float4* __restrict__ A, float4* __restrict__ B)
+{
+    long long per = (long long)rows * c.U;
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= per * c.batch) return;
+    int b = (int)(t / per); long long r = t % per;
+    int j = (int)(r / c.U) + row_begin, i = (int)(r % c.U);
+    long long o = oc_index(c, b, i, j);
+    const float* x = X + t * stride; const float* l = XL + t * stride;
+    A[o] = make_float4(x[0], x[1], x[2], oc_u2f(OC_W_PLAIN));
+    B[o] = make_float4(l[0], l[1], l[2], oc_u2f(OC_W_PLAIN));
+}
+
+__global__ void oc_k_pack(OcConst c, int row_begin, int rows, int stride,
+                          const float4* __restrict__ A, const float4* __restrict__ B,
+                          float* __restrict__ X, float* __restrict__ XL)
+{
+    long long per = (long long)rows * c.U;
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= per * c.batch) return;
+    int b = (int)(t / per); long long r = t % per;
+    int j = (int)(r / c.U) + row_begin, i = (int)(r % c.U);
+    long long o = oc_index(c, b, i, j);
+    float4 a = A[o];
+    if (X) {
+        float* x = X + t * stride;
+        x[0] = a.x; x[1] = a.y; x[2] = a.z; if (stride == 4) x[3] = 1.0f;
+    }
+    if (XL) {
+        float4 q = oc_hit(a.w) ? a : B[o];                              // V:530 vs V:438
+        float* l = XL + t * stride;
+        l[0] = q.x; l[1] = q.y; l[2] = q.z; if (stride == 4) l[3] = 1.0f;
+    }
+}
+
+__global__ void oc_k_set_particle(float4* A, float4* B, long long o, float x, float y, float z)
+{
+    float4 v = make_float4(x, y, z, oc_u2f(OC_W_PLAIN));                // V:203-208
+    A[o] = v; B[o] = v;
+}
+
+// sum over springs of 1/2 Ks (|p1-p2| - rest)^2 in double; every particle owns its forward springs
+__device__ double oc_e_term(const OcConst& c, const float4* A, int b, int i, int j, int ni, int nj, float rest, float ks)
+{
+    float4 p = A[oc_index(c, b, i, j)], q = A[oc_index(c, b, ni, nj)];
+    float dx = __fsub_rn(p.x, q.x), dy = __fsub_rn(p.y, q.y), dz = __fsub_rn(p.z, q.z);
+    double len = sqrt((double)dx * dx + (double)dy * dy + (double)dz * dz);
+    double ext = len - (double)rest;
+    return 0.5 * (double)ks * ext * ext;
+}
+__global__ void oc_k_energy(OcConst c, const float4* __restrict__ A, int b, float ks_struct, float ks_shear, float ks_bend,
+                            double* __restrict__ out)
+{
+    long long per = (long long)c.V * c.U;
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    double e = 0.0;
+    if (t < per) {
+        int j = (int)(t / c.U), i = (int)(t % c.U);
+        const int U = c.U, V = c.V;
+        if (i + 1 < U) e += oc_e_term(c, A, b, i, j, i + 1, j, c.rh1[i], ks_struct);
+        if (j + 1 < V) e += oc_e_term(c, A, b, i, j, i, j + 1, c.rv1[j], ks_struct);
+        if (i + 1 < U && j + 1 < V) {
+            float r = __fsqrt_rn(__fadd_rn(c.dx2[i], c.dz2[j]));
+            e += oc_e_term(c, A, b, i, j, i + 1, j + 1, r, ks_shear);
+            e += oc_e_term(c, A, b, i, j + 1, i + 1, j, r, ks_shear);
+        }
+        if (i + 2 < U) e += oc_e_term(c, A, b, i, j, i + 2, j, c.rh2[i], ks_bend) * (i == U - 3 ? 2.0 : 1.0);
+        if (j + 2 < V) e += oc_e_term(c, A, b, i, j, i, j + 2, c.rv2[j], ks_bend) * (j == V - 3 ? 2.0 : 1.0);
+    }
+    for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+    __shared__ double s[8];
+    int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) s[w] = e;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0.0;
+        for (int q = 0; q < (int)(blockDim.x >> 5); ++q) tot += s[q];
+        atomicAdd(out, tot);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// create / destroy
+// ------------------------------------------------------------------------------------------------
+static int validate(const oc_params* p)
+{
+    if (!p) return oc_fail(OC_ERR_INVALID, "null params");
+    if (p->nx < 3 || p->ny < 3) return oc_fail(OC_ERR_INVALID, "nx, ny must be >= 3 (bend springs reach 2; got %d x %d)", p->nx, p->ny);
+    if (p->batch < 1) return oc_fail(OC_ERR_INVALID, "batch must be >= 1");
+    if (p->row_begin != 0 || p->row_end != 0) {
+        if (p->row_begin < 0 || p->row_end > p->ny || p->row_end <= p->row_begin)
+            return oc_fail(OC_ERR_INVALID, "bad row band [%d,%d) of %d rows", p->row_begin, p->row_end, p->ny);
+        bool sub = p->row_begin > 0 || p->row_end < p->ny;
+        if (sub) {
+            if (p->batch != 1) return oc_fail(OC_ERR_UNSUPPORTED, "row bands need batch == 1");
+            if (p->halo_rows < 2 || (p->halo_rows & 1)) return oc_fail(OC_ERR_INVALID, "halo_rows must be an even number >= 2");
+            if (p->row_end - p->row_begin < p->halo_rows) return oc_fail(OC_ERR_INVALID, "band has fewer rows than halo_rows");
+        }
+    }
+    if (!(p->dt > 0.0f) || !(p->mass > 0.0f)) return oc_fail(OC_ERR_INVALID, "dt and mass must be positive");
+    if (p->substeps_per_launch < 0 || p->substeps_per_launch > OC_MARCH_MAX_STAGES)
+        return oc_fail(OC_ERR_INVALID, "substeps_per_launch must be 0..%d", OC_MARCH_MAX_STAGES);
+    if (p->kernel < OC_KERNEL_AUTO || p->kernel > OC_KERNEL_MARCH) return oc_fail(OC_ERR_INVALID, "bad kernel id");
+    return OC_OK;
+}
+
+extern "C" int oc_create(oc_cloth** out, const oc_params* p)
+{
+    if (!out) return oc_fail(OC_ERR_INVALID, "oc_create: null out");
+    *out = nullptr;
+    int rc = validate(p);
+    if (rc) return rc;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return oc_fail(OC_ERR_NO_DEVICE, "no CUDA device (%s); libopencloth_b200 has no CPU fallback",
+                       e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    oc_cloth* c = new (std::nothrow) oc_cloth();
+    if (!c) return oc_fail(OC_ERR_NOMEM, "host allocation failed");
+    memset(c, 0, sizeof(*c));
+    c->p = *p;
+    if (p->device >= 0) c->dev = p->device; else { OC_CUDA(cudaGetDevice(&c->dev)); }
+    if (c->dev >= ndev) { delete c; return oc_fail(OC_ERR_INVALID, "device %d of %d", p->device, ndev); }
+#define OC_CREATE_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { free_handle(c); \
+        return oc_fail(e_ == cudaErrorMemoryAllocation ? OC_ERR_NOMEM : OC_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); } } while (0)
+    OC_CREATE_CUDA(cudaSetDevice(c->dev));
+    OC_CREATE_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->dev));
+
+    const int U = p->nx, V = p->ny;
+    OcConst& k = c->k;
+    oc_host_geometry(c->p, k, c->q);
+    c->rows_own = c->p.row_end - c->p.row_begin;
+    c->stored = k.cloth_stride * p->batch;
+    oc_host_derive_scalars(c->p, k);
+
+    // rest-length tables from the initial sheet (V:254-260 positions, V:141-142 rest lengths)
+    OcHostTables T;
+    oc_host_build_tables(U, V, p->fullsize, T);
+    OC_CREATE_CUDA(cudaMalloc(&c->tables, T.t.size() * sizeof(float)));
+    OC_CREATE_CUDA(cudaMemcpy(c->tables, T.t.data(), T.t.size() * sizeof(float), cudaMemcpyHostToDevice));
+    c->d_xs = c->tables + T.xs; c->d_zs = c->tables + T.zs;
+    oc_host_bind_tables(k, c->tables, T);
+
+    for (int b = 0; b < 4; ++b) OC_CREATE_CUDA(cudaMalloc(&c->buf[b], (size_t)c->stored * sizeof(float4)));
+    OC_CREATE_CUDA(cudaMalloc(&c->d_energy, sizeof(double)));
+    OC_CREATE_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
+    OC_CREATE_CUDA(cudaEventCreate(&c->ev0));
+    OC_CREATE_CUDA(cudaEventCreate(&c->ev1));
+    OC_CREATE_CUDA(cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming));
+    OC_CREATE_CUDA(cudaEventCreateWithFlags(&c->ev_filled, cudaEventDisableTiming));
+    {
+        long long n = c->stored;
+        oc_k_init<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(k, c->d_xs, c->d_zs, p->fullsize + 1, c->buf[0], c->buf[1]);
+        c->launches++;
+        OC_CREATE_CUDA(cudaGetLastError());
+        // the two spare buffers start as copies so that never-computed halo rows hold finite values
+        OC_CREATE_CUDA(cudaMemcpyAsync(c->buf[2], c->buf[0], (size_t)n * sizeof(float4), cudaMemcpyDeviceToDevice, c->stream));
+        OC_CREATE_CUDA(cudaMemcpyAsync(c->buf[3], c->buf[0], (size_t)n * sizeof(float4), cudaMemcpyDeviceToDevice, c->stream));
+    }
+    rc = oc_march_configure(c->dev);
+    if (rc != 0) { free_handle(c); return oc_fail(OC_ERR_CUDA, "oc_march_configure failed: %s", cudaGetErrorString((cudaError_t)rc)); }
+#undef OC_CREATE_CUDA
+    *out = c;
+    return OC_OK;
+}
+
+extern "C" void oc_destroy(oc_cloth* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->dev);
+    cudaStreamSynchronize(c->stream);
+    free_handle(c);
+}
+
+extern "C" int oc_set_params(oc_cloth* c, const oc_params* p)
+{
+    if (!c || !p) return oc_fail(OC_ERR_INVALID, "oc_set_params: null");
+    oc_params q = *p;
+    if (q.row_begin == 0 && q.row_end == 0) q.row_end = q.ny;
+    if (q.nx != c->p.nx || q.ny != c->p.ny || q.batch != c->p.batch || q.fullsize != c->p.fullsize ||
+        q.row_begin != c->p.row_begin || q.row_end != c->p.row_end || (c->q.band && q.halo_rows != c->p.halo_rows))
+        return oc_fail(OC_ERR_INVALID, "oc_set_params: nx, ny, batch, row band, halo_rows and fullsize are fixed at oc_create");
+    int rc = validate(&q);
+    if (rc) return rc;
+    q.device = c->p.device; q.halo_rows = c->p.halo_rows;
+    c->p = q;
+    oc_host_derive_scalars(c->p, c->k);
+    return OC_OK;
+}
+
+extern "C" int oc_get_params(const oc_cloth* c, oc_params* p)
+{
+    if (!c || !p) return oc_fail(OC_ERR_INVALID, "oc_get_params: null");
+    *p = c->p;
+    return OC_OK;
+}
+
+extern "C" int oc_set_stream(oc_cloth* c, void* s)
+{
+    if (!c) return oc_fail(OC_ERR_INVALID, "oc_set_stream: null");
+    OC_CUDA(cudaSetDevice(c->dev));
+    OC_CUDA(cudaStreamSynchronize(c->stream));
+    c->stream = s ? (cudaStream_t)s : c->own_stream;
+    return OC_OK;
+}
+
+extern "C" long long oc_launch_count(const oc_cloth* c) { return c ? c->launches : 0; }
+
+extern "C" int oc_sync(oc_cloth* c)
+{
+    if (!c) return oc_fail(OC_ERR_INVALID, "oc_sync: null");
+    OC_CUDA(cudaSetDevice(c->dev));
+    OC_CUDA(cudaStreamSynchronize(c->stream));
+    return OC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// upload / download / set_particle
+// ------------------------------------------------------------------------------------------------
+static int ensure_stage(oc_cloth* c, size_t bytes)
+{
+    if (c->stage_bytes >= bytes) return OC_OK;
+    if (c->stage[0]) cudaFree(c->stage[0]);
+    if (c->stage[1]) cudaFree(c->stage[1]);
+    c->stage[0] = c->stage[1] = nullptr; c->stage_bytes = 0;
+    OC_CUDA(cudaMalloc(&c->stage[0], bytes));
+    OC_CUDA(cudaMalloc(&c->stage[1], bytes));
+    c->stage_bytes = bytes;
+    return OC_OK;
+}
+
+extern "C" int oc_upload(oc_cloth* c, const float* X, const float* X_last, int stride)
+{
+    if (!c || !X || !X_last) return oc_fail(OC_ERR_INVALID, "oc_upload: null");
+    if (stride != 3 && stride != 4) return oc_fail(OC_ERR_INVALID, "stride_floats must be 3 or 4");
+    OC_CUDA(cudaSetDevice(c->dev));
+    long long n = (long long)c->p.batch * c->rows_own * c->p.nx;
+    size_t bytes = (size_t)n * stride * sizeof(float);
+    int rc = ensure_stage(c, bytes);
+    if (rc) return rc;
+    OC_CUDA(cudaMemcpyAsync(c->stage[0], X, bytes, cudaMemcpyHostToDevice, c->stream));
+    OC_CUDA(cudaMemcpyAsync(c->stage[1], X_last, bytes, cudaMemcpyHostToDevice, c->stream));
+    oc_k_unpack<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->k, c->p.row_begin, c->rows_own, stride,
+                                                                    c->stage[0], c->stage[1], c->buf[c->q.ia], c->buf[c->q.ib]);
+    c->launches++;
+    OC_CUDA(cudaGetLastError());
+    if (c->q.band) c->q.fresh = c->q.kmax;     // halos are stale until the host exchanges them
+    return OC_OK;
+}
+
+extern "C" int oc_download(oc_cloth* c, float* X, float* X_last, int stride)
+{
+    if (!c) return oc_fail(OC_ERR_INVALID, "oc_download: null");
+    if (stride != 3 && stride != 4) return oc_fail(OC_ERR_INVALID, "stride_floats must be 3 or 4");
+    OC_CUDA(cudaSetDevice(c->dev));
+    long long n = (long long)c->p.batch * c->rows_own * c->p.nx;
+    size_t bytes = (size_t)n * stride * sizeof(float);
+    int rc = ensure_stage(c, bytes);
+    if (rc) return rc;
+    oc_k_pack<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->k, c->p.row_begin, c->rows_own, stride,
+                                                                  c->buf[c->q.ia], c->buf[c->q.ib],
+                                                                  X ? c->stage[0] : nullptr, X_last ? c->stage[1] : nullptr);
+    c->launches++;
+    OC_CUDA(cudaGetLastError());
+    if (X) OC_CUDA(cudaMemcpyAsync(X, c->stage[0], bytes, cudaMemcpyDeviceToHost, c->stream));
+    if (X_last) OC_CUDA(cudaMemcpyAsync(X_last, c->stage[1], bytes, cudaMemcpyDeviceToHost, c->stream));
+    OC_CUDA(cudaStreamSynchronize(c->stream));
+    return OC_OK;
+}
+
+extern "C" int oc_set_particle(oc_cloth* c, int cloth, int idx, const float xyz[3])
+{
+    if (!c || !xyz) return oc_fail(OC_ERR_INVALID, "oc_set_particle: null");
+    if (cloth < 0 || cloth >= c->p.batch || idx < 0 || idx >= c->p.nx * c->p.ny)
+        return oc_fail(OC_ERR_INVALID, "oc_set_particle: cloth %d / index %d out of range", cloth, idx);
+    int j = idx / c->p.nx, i = idx % c->p.nx;
+    if (j < c->k.row_lo || j >= c->k.row_lo + c->k.srows) return OC_OK;      // not stored by this band
+    OC_CUDA(cudaSetDevice(c->dev));
+    oc_k_set_particle<<<1, 1, 0, c->stream>>>(c->buf[c->q.ia], c->buf[c->q.ib], oc_index(c->k, cloth, i, j), xyz[0], xyz[1], xyz[2]);
+    c->launches++;
+    OC_CUDA(cudaGetLastError());
+    return OC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// step
+// ------------------------------------------------------------------------------------------------
+static int pick_kernel(const oc_cloth* c)
+{
+    if (c->p.kernel != OC_KERNEL_AUTO) return c->p.kernel;
+    return OC_KERNEL_MARCH;
+}
+
+extern "C" int oc_step(oc_cloth* c, int n)
+{
+    if (!c) return oc_fail(OC_ERR_INVALID, "oc_step: null");
+    if (n < 0) return oc_fail(OC_ERR_INVALID, "oc_step: n < 0");
+    if (c->q.band && c->q.fresh + n > c->q.kmax)
+        return oc_fail(OC_ERR_INVALID, "oc_step: %d substeps requested but only %d remain before the halo rows must be exchanged "
+                                       "(halo_rows=%d)", n, c->q.kmax - c->q.fresh, c->p.halo_rows);
+    OC_CUDA(cudaSetDevice(c->dev));
+    const int kern = pick_kernel(c);
+    const int kdef = c->p.substeps_per_launch > 0 ? c->p.substeps_per_launch : 1;
+    while (n > 0) {
+        const int kmaxS = (kern == OC_KERNEL_MARCH) ? oc_host_pick_stages(n < kdef ? n : kdef) : 1;
+        OcLaunch L;
+        oc_host_next_launch(c->q, n, kmaxS, L);
+        if (kern == OC_KERNEL_MARCH) {
+            int nl = 0;
+            cudaError_t e = oc_march_launch(c->k, c->p.exact != 0, L.S, L.ra, L.rb, c->sm_count,
+                                            c->buf[L.src_a], c->buf[L.src_b], c->buf[L.dst], c->buf[L.dst_prev], c->stream, &nl);
+            c->launches += nl;
+            if (e != cudaSuccess) return oc_fail(OC_ERR_CUDA, "march kernel launch failed: %s", cudaGetErrorString(e));
+        } else {
+            dim3 blk(128, 1, 1), grd((c->p.nx + 127) / 128, L.rb - L.ra, c->p.batch);
+            if (c->p.exact) oc_k_gather<MathExact><<<grd, blk, 0, c->stream>>>(c->k, c->buf[L.src_a], c->buf[L.src_b], c->buf[L.dst], L.ra);
+            else            oc_k_gather<MathFast><<<grd, blk, 0, c->stream>>>(c->k, c->buf[L.src_a], c->buf[L.src_b], c->buf[L.dst], L.ra);
+            c->launches++;
+            OC_CUDA(cudaGetLastError());
+        }
+    }
+    return OC_OK;
+}
+
+extern "C" int oc_step_timed(oc_cloth* c, int n, float* ms)
+{
+    if (!c || !ms) return oc_fail(OC_ERR_INVALID, "oc_step_timed: null");
+    OC_CUDA(cudaSetDevice(c->dev));
+    OC_CUDA(cudaStreamSynchronize(c->stream));
+    OC_CUDA(cudaEventRecord(c->ev0, c->stream));
+    int rc = oc_step(c, n);
+    if (rc) return rc;
+    OC_CUDA(cudaEventRecord(c->ev1, c->stream));
+    OC_CUDA(cudaEventSynchronize(c->ev1));
+    OC_CUDA(cudaEventElapsedTime(ms, c->ev0, c->ev1));
+    return OC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// row-band halo plumbing
+// ------------------------------------------------------------------------------------------------
+static int halo_region(oc_cloth* c, int side, int which, bool send, void** ptr, size_t* count)
+{
+    if (!c || !ptr || !count) return oc_fail(OC_ERR_INVALID, "oc_halo_*: null");
+    if ((side != 0 && side != 1) || (which != 0 && which != 1)) return oc_fail(OC_ERR_INVALID, "oc_halo_*: side/which must be 0 or 1");
+    *ptr = nullptr; *count = 0;
+    int r0, rows;
+    if (!oc_host_halo_rows(c->p, c->q.band, side, send, &r0, &rows)) return OC_OK;
+    const int U = c->p.nx;
+    float4* base = c->buf[which == 0 ? c->q.ia : c->q.ib];
+    *ptr = (void*)(base + (long long)(r0 - c->k.row_lo) * U);
+    *count = (size_t)rows * U;
+    return OC_OK;
+}
+extern "C" int oc_halo_send_region(oc_cloth* c, int side, int which, void** p, size_t* n) { return halo_region(c, side, which, true, p, n); }
+extern "C" int oc_halo_recv_region(oc_cloth* c, int side, int which, void** p, size_t* n) { return halo_region(c, side, which, false, p, n); }
+extern "C" int oc_halo_refreshed(oc_cloth* c)
+{
+    if (!c) return oc_fail(OC_ERR_INVALID, "oc_halo_refreshed: null");
+    c->q.fresh = 0;
+    return OC_OK;
+}
+extern "C" int oc_halo_budget(const oc_cloth* c)
+{
+    if (!c) return 0;
+    return c->q.band ? c->q.kmax - c->q.fresh : 0x7fffffff;
+}
+
+extern "C" int oc_halo_exchange(oc_cloth* const* bands, int n)
+{
+    if (!bands || n < 1) return oc_fail(OC_ERR_INVALID, "oc_halo_exchange: no bands");
+    for (int b = 0; b < n; ++b) {
+        if (!bands[b]) return oc_fail(OC_ERR_INVALID, "oc_halo_exchange: null band");
+        if (b > 0 && (bands[b]->p.row_begin != bands[b - 1]->p.row_end || bands[b]->p.nx != bands[0]->p.nx ||
+                      bands[b]->p.ny != bands[0]->p.ny || bands[b]->p.halo_rows != bands[0]->p.halo_rows))
+            return oc_fail(OC_ERR_INVALID, "oc_halo_exchange: bands must be consecutive row bands of one cloth with equal halo_rows");
+    }
+    // 1. every band announces that its owned rows are final
+    for (int b = 0; b < n; ++b) {
+        OC_CUDA(cudaSetDevice(bands[b]->dev));
+        OC_CUDA(cudaEventRecord(bands[b]->ev_ready, bands[b]->stream));
+    }
+    // 2. every band pulls its two halos on its own stream, after the producer is ready
+    for (int b = 0; b < n; ++b) {
+        oc_cloth* me = bands[b];
+        OC_CUDA(cudaSetDevice(me->dev));
+        for (int side = 0; side < 2; ++side) {
+            oc_cloth* nb = (side == 0) ? (b > 0 ? bands[b - 1] : nullptr) : (b + 1 < n ? bands[b + 1] : nullptr);
+            if (!nb) continue;
+            OC_CUDA(cudaStreamWaitEvent(me->stream, nb->ev_ready, 0));
+            for (int which = 0; which < 2; ++which) {
+                void *src, *dst; size_t ns, nd;
+                int rc = halo_region(nb, 1 - side, which, true, &src, &ns);
+                if (rc) return rc;
+                rc = halo_region(me, side, which, false, &dst, &nd);
+                if (rc) return rc;
+                if (ns != nd) return oc_fail(OC_ERR_INVALID, "oc_halo_exchange: halo size mismatch");
+                if (ns == 0) continue;
+                if (nb->dev == me->dev) OC_CUDA(cudaMemcpyAsync(dst, src, ns * sizeof(float4), cudaMemcpyDeviceToDevice, me->stream));
+                else                    OC_CUDA(cudaMemcpyPeerAsync(dst, me->dev, src, nb->dev, ns * sizeof(float4), me->stream));
+            }
+        }
+        OC_CUDA(cudaEventRecord(me->ev_filled, me->stream));
+    }
+    // 3. nobody overwrites rows a neighbour is still reading: wait for the neighbours' pulls
+    for (int b = 0; b < n; ++b) {
+        oc_cloth* me = bands[b];
+        OC_CUDA(cudaSetDevice(me->dev));
+        if (b > 0)     OC_CUDA(cudaStreamWaitEvent(me->stream, bands[b - 1]->ev_filled, 0));
+        if (b + 1 < n) OC_CUDA(cudaStreamWaitEvent(me->stream, bands[b + 1]->ev_filled, 0));
+        me->q.fresh = 0;
+    }
+    return OC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// diagnostics
+// ------------------------------------------------------------------------------------------------
+extern "C" size_t oc_sizeof_params(void) { return sizeof(oc_params); }
+
+extern "C" int oc_spring_energy(oc_cloth* c, int cloth, double* energy)
+{
+    if (!c || !energy) return oc_fail(OC_ERR_INVALID, "oc_spring_energy: null");
+    if (c->q.band) return oc_fail(OC_ERR_UNSUPPORTED, "oc_spring_energy: whole-cloth handles only");
+    if (cloth < 0 || cloth >= c->p.batch) return oc_fail(OC_ERR_INVALID, "oc_spring_energy: cloth out of range");
+    OC_CUDA(cudaSetDevice(c->dev));
+    OC_CUDA(cudaMemsetAsync(c->d_energy, 0, sizeof(double), c->stream));
+    long long n = (long long)c->p.nx * c->p.ny;
+    oc_k_energy<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->k, c->buf[c->q.ia], cloth, c->p.ks_struct, c->p.ks_shear, c->p.ks_bend, c->d_energy);
+    c->launches++;
+    OC_CUDA(cudaGetLastError());
+    OC_CUDA(cudaMemcpyAsync(energy, c->d_energy, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    OC_CUDA(cudaStreamSynchronize(c->stream));
+    return OC_OK;
+}
+
+extern "C" const char* oc_version(void)
+{
+    static thread_local char buf[256];
+    int ndev = 0, dev = 0;
+    char name[128] = "none";
+    if (cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0 && cudaGetDevice(&dev) == cudaSuccess) {
+        cudaDeviceProp pr;
+        if (cudaGetDeviceProperties(&pr, dev) == cudaSuccess) snprintf(name, sizeof(name), "%s sm_%d%d x%d", pr.name, pr.major, pr.minor, pr.multiProcessorCount);
+    } else {
+        cudaGetLastError();
+    }
+    snprintf(buf, sizeof(buf), "opencloth_b200 abi=%d built-for=sm_100a devices=%d device=%s", OC_ABI_VERSION, ndev, name);
+    return buf;
+}

@@ -1,0 +1,125 @@
+// oc_march.cu — host side of the marching kernel: variant table, launch geometry, launch.
+#include "oc_march.cuh"
+#include <cstdlib>
+#include <cstdio>
+
+extern "C" const void* oc_march_fn_exact_32(int S);
+extern "C" const void* oc_march_fn_exact_64(int S);
+extern "C" const void* oc_march_fn_exact_128(int S);
+extern "C" const void* oc_march_fn_fast_32(int S);
+extern "C" const void* oc_march_fn_fast_64(int S);
+extern "C" const void* oc_march_fn_fast_128(int S);
+
+static const void* march_fn(bool exact, int TW, int S)
+{
+    switch (TW) {
+    case 32:  return exact ? oc_march_fn_exact_32(S)  : oc_march_fn_fast_32(S);
+    case 64:  return exact ? oc_march_fn_exact_64(S)  : oc_march_fn_fast_64(S);
+    case 128: return exact ? oc_march_fn_exact_128(S) : oc_march_fn_fast_128(S);
+    default:  return nullptr;
+    }
+}
+
+static size_t stage_smem(int TW)
+{
+    switch (TW) {
+    case 32:  return sizeof(OcStageSmem<32>);
+    case 64:  return sizeof(OcStageSmem<64>);
+    case 128: return sizeof(OcStageSmem<128>);
+    default:  return 0;
+    }
+}
+
+// resident CTAs per SM for each variant, filled by oc_march_configure: [exact][tw_idx][S]
+static int g_occ[2][3][OC_MARCH_MAX_STAGES + 1];
+static int tw_index(int TW) { return TW == 32 ? 0 : (TW == 64 ? 1 : 2); }
+
+// width of the column window for a cloth of nx columns stepped S substeps per launch
+static int pick_tw(int nx, int S)
+{
+    if (nx <= 32) return 32;
+    if (nx <= 64) return 64;
+    if (S <= 4) return 128;
+    return 64;
+}
+
+int oc_march_configure(int device)
+{
+    (void)device;
+    const int tws[3] = { 32, 64, 128 };
+    for (int e = 0; e < 2; ++e)
+        for (int t = 0; t < 3; ++t)
+            for (int S = 1; S <= OC_MARCH_MAX_STAGES; ++S) {
+                const void* fn = march_fn(e != 0, tws[t], S);
+                g_occ[e][t][S] = 0;
+                if (!fn) continue;
+                size_t smem = stage_smem(tws[t]) * S;
+                cudaError_t err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (err != cudaSuccess) return (int)err;
+                int occ = 0;
+                err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, tws[t] * S, smem);
+                if (err != cudaSuccess) return (int)err;
+                g_occ[e][t][S] = occ;
+            }
+    return 0;
+}
+
+// Launch geometry.  Rows are cut into nseg segments of RS rows; every segment costs
+// RS + (pipeline fill) iterations, so few long segments are efficient but the grid must also fill
+// sm_count * occupancy CTA slots in whole waves.  Pick the RS that maximises
+//   useful row-iterations / (waves * slots * iterations per CTA).
+int oc_march_plan(const OcConst& c, int S, int ra, int rb, int sm_count, int occ_hint, OcMarchPlan* pl)
+{
+    const int U = c.U;
+    int TW = pick_tw(U, S);
+    int x_halo = (U <= TW) ? 0 : 2 * S;
+    int W_out = TW - 2 * x_halo;
+    if (W_out <= 0) return -1;
+    int nstrips = (U + W_out - 1) / W_out;
+    int rows = rb - ra;
+    if (rows <= 0) return -1;
+    int occ = occ_hint > 0 ? occ_hint : 1;
+    long long slots = (long long)sm_count * occ;
+    const int fill = OC_MARCH_LAG * S + 2 * (S - 1) + 2;      // iterations beyond RS per segment
+    int best_rs = rows; double best = -1.0;
+    const char* env = getenv("OC_MARCH_RS");
+    if (env && atoi(env) > 0) {
+        best_rs = atoi(env);
+        if (best_rs > rows) best_rs = rows;
+    } else {
+        for (int nseg = 1; nseg <= rows; ++nseg) {
+            int rs = (rows + nseg - 1) / nseg;
+            if (rs < 8 && nseg > 1) break;
+            int ns = (rows + rs - 1) / rs;
+            long long ctas = (long long)nstrips * ns * c.batch;
+            long long waves = (ctas + slots - 1) / slots;
+            double eff = (double)rows * nstrips * c.batch / ((double)waves * slots * (rs + fill));
+            if (eff > best * 1.0001) { best = eff; best_rs = rs; }
+        }
+    }
+    pl->TW = TW; pl->S = S; pl->x_halo = x_halo; pl->W_out = W_out; pl->nstrips = nstrips;
+    pl->RS = best_rs; pl->nseg = (rows + best_rs - 1) / best_rs; pl->threads = TW * S;
+    pl->smem = stage_smem(TW) * S;
+    return 0;
+}
+
+cudaError_t oc_march_launch(const OcConst& c, bool exact, int S, int ra, int rb, int sm_count,
+                            const float4* A, const float4* B, float4* C, float4* Dst,
+                            cudaStream_t stream, int* n_launches)
+{
+    *n_launches = 0;
+    OcMarchPlan pl;
+    int TW = pick_tw(c.U, S);
+    int occ = g_occ[exact ? 1 : 0][tw_index(TW)][S];
+    if (oc_march_plan(c, S, ra, rb, sm_count, occ, &pl) != 0) return cudaErrorInvalidValue;
+    const void* fn = march_fn(exact, pl.TW, S);
+    if (!fn) return cudaErrorInvalidDeviceFunction;
+    if (pl.nseg > 65535 || c.batch > 65535) return cudaErrorInvalidConfiguration;
+    dim3 grid(pl.nstrips, pl.nseg, c.batch), block(pl.threads, 1, 1);
+    OcConst cc = c;
+    int RS = pl.RS, xh = pl.x_halo;
+    void* args[] = { &cc, (void*)&A, (void*)&B, (void*)&C, (void*)&Dst, &ra, &rb, &RS, &xh };
+    cudaError_t e = cudaLaunchKernel(fn, grid, block, args, pl.smem, stream);
+    if (e == cudaSuccess) *n_launches = 1;
+    return e;
+}

@@ -1,0 +1,330 @@
+// tests/emu/oc_emu.cu — TEST INFRASTRUCTURE ONLY: runs the product's kernel BODIES on the CPU.
+//
+// The CUDA kernels of opencloth_b200/csrc are written as __host__ __device__ templates over an
+// execution context.  This file provides a CPU context — one ucontext fiber per CUDA thread, a
+// cooperative scheduler as __syncthreads, a malloc'd block as shared memory — and the same host
+// sequencing (oc_host.h) as the C-ABI, so that `pytest -m "not gpu"` can check the kernels' logic
+// (index arithmetic, pipeline hazards across barriers, accumulation order, band/halo protocol)
+// bit for bit against the oracle without a GPU.  It is never loaded by the opencloth_b200 package
+// and is not a CPU fallback: fibers make it thousands of times slower than the oracle.
+//
+// Host arithmetic is IEEE binary32 without contraction (-ffp-contract=off), which is exactly what
+// the device intrinsics of MathExact compute, so exact-mode results must equal the GPU's.
+#include "../../opencloth_b200/csrc/oc_core.cuh"
+#include "../../opencloth_b200/csrc/oc_host.h"
+#include "../../opencloth_b200/csrc/oc_gather.cuh"
+#include "../../opencloth_b200/csrc/oc_march.cuh"
+
+#include <ucontext.h>
+#include <cstdlib>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+#include <functional>
+
+// ------------------------------------------------------------------------------------------------
+// fiber CTA
+// ------------------------------------------------------------------------------------------------
+struct EmuCta;
+struct EmuCtx {
+    int tid_, bx_, by_, bz_;
+    unsigned char* smem_;
+    EmuCta* cta;
+    int tid() const { return tid_; }
+    int bx() const { return bx_; }
+    int by() const { return by_; }
+    int bz() const { return bz_; }
+    unsigned char* smem() const { return smem_; }
+    void sync();
+};
+
+struct EmuCta {
+    ucontext_t sched;
+    std::vector<ucontext_t> fib;
+    std::vector<char*> stacks;
+    std::vector<int> done;
+    std::vector<long> nsync;
+    std::function<void(EmuCtx&)> body;
+    std::vector<EmuCtx> ctx;
+    int cur;
+};
+
+static EmuCta* g_cta = nullptr;
+// Order in which the scheduler resumes the fibers between two barriers: 0 = ascending tid,
+// 1 = descending, 2 = pseudo-random per round.  A kernel without intra-phase data races gives
+// identical results under every order; tests run all three.
+static int g_order = 0;
+static unsigned g_rng = 12345u;
+static const size_t kStack = 256 * 1024;
+
+void EmuCtx::sync()
+{
+    EmuCta* c = cta;
+    c->nsync[tid_]++;
+    swapcontext(&c->fib[tid_], &c->sched);
+}
+
+static void fiber_main()
+{
+    EmuCta* c = g_cta;
+    int t = c->cur;
+    c->body(c->ctx[t]);
+    c->done[t] = 1;
+    swapcontext(&c->fib[t], &c->sched);
+}
+
+// run one CTA of nthreads threads; returns 0, or -1 if the threads disagree on the barrier count
+static int run_cta(int nthreads, int bx, int by, int bz, size_t smem_bytes, const std::function<void(EmuCtx&)>& body)
+{
+    static EmuCta cta;              // stacks are reused between CTAs
+    EmuCta* c = &cta;
+    g_cta = c;
+    c->body = body;
+    if ((int)c->stacks.size() < nthreads) {
+        size_t old = c->stacks.size();
+        c->stacks.resize(nthreads);
+        for (size_t t = old; t < (size_t)nthreads; ++t) c->stacks[t] = (char*)malloc(kStack);
+    }
+    c->fib.resize(nthreads); c->done.assign(nthreads, 0); c->nsync.assign(nthreads, 0); c->ctx.resize(nthreads);
+    unsigned char* smem = (unsigned char*)aligned_alloc(128, (smem_bytes + 127) / 128 * 128 + 128);
+    memset(smem, 0xCD, smem_bytes);            // garbage, like real shared memory
+    for (int t = 0; t < nthreads; ++t) {
+        c->ctx[t].tid_ = t; c->ctx[t].bx_ = bx; c->ctx[t].by_ = by; c->ctx[t].bz_ = bz;
+        c->ctx[t].smem_ = smem; c->ctx[t].cta = c;
+        getcontext(&c->fib[t]);
+        c->fib[t].uc_stack.ss_sp = c->stacks[t];
+        c->fib[t].uc_stack.ss_size = kStack;
+        c->fib[t].uc_link = &c->sched;
+        makecontext(&c->fib[t], fiber_main, 0);
+    }
+    int rc = 0;
+    for (;;) {
+        int alive = 0;
+        unsigned off = 0, mul = 1;
+        if (g_order == 2) {     // t -> (t*mul + off) mod n is a bijection when gcd(mul, n) = 1
+            g_rng = g_rng * 1664525u + 1013904223u;
+            off = (g_rng >> 8) % (unsigned)nthreads;
+            static const unsigned odd[] = { 1, 3, 5, 7, 9, 11, 13, 15, 17, 19, 21, 23 };
+            for (;;) {
+                g_rng = g_rng * 1664525u + 1013904223u; mul = odd[(g_rng >> 10) % 12];
+                unsigned a = mul, b = (unsigned)nthreads;
+                while (b) { unsigned r = a % b; a = b; b = r; }
+                if (a == 1) break;
+            }
+        }
+        for (int u = 0; u < nthreads; ++u) {
+            int t = g_order == 0 ? u : (g_order == 1 ? nthreads - 1 - u : (int)(((unsigned)u * mul + off) % (unsigned)nthreads));
+            if (c->done[t]) continue;
+            c->cur = t;
+            swapcontext(&c->sched, &c->fib[t]);
+            if (!c->done[t]) alive++;
+        }
+        if (alive == 0) break;
+        if (alive != nthreads) {               // some threads left the kernel while others wait at a barrier
+            bool any_done = false;
+            for (int t = 0; t < nthreads; ++t) any_done |= (c->done[t] != 0);
+            if (any_done) {
+                // legal in CUDA only if the finished threads never reach another barrier; our kernels
+                // have uniform barrier counts, so flag it
+                rc = -1;
+            }
+        }
+    }
+    for (int t = 1; t < nthreads; ++t) if (c->nsync[t] != c->nsync[0]) rc = -1;
+    free(smem);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// emulated handle: same state as the C-ABI handle, host memory
+// ------------------------------------------------------------------------------------------------
+struct EmuCloth {
+    oc_params p;
+    OcConst k;
+    OcSeq q;
+    OcHostTables T;
+    std::vector<float4> buf[4];
+    long long stored;
+    int rows_own;
+    long long barrier_errors;
+};
+
+template <class M, int S, int TW>
+static int emu_march(EmuCloth* e, const OcLaunch& L, int RS, int x_halo)
+{
+    const OcConst& k = e->k;
+    int W_out = TW - 2 * x_halo;
+    int nstrips = (k.U + W_out - 1) / W_out;
+    int rows = L.rb - L.ra;
+    if (RS <= 0 || RS > rows) RS = rows;
+    int nseg = (rows + RS - 1) / RS;
+    const float4* A = e->buf[L.src_a].data();
+    const float4* B = e->buf[L.src_b].data();
+    float4* C = e->buf[L.dst].data();
+    float4* D = e->buf[L.dst_prev].data();
+    int rc = 0;
+    for (int bz = 0; bz < k.batch; ++bz)
+        for (int by = 0; by < nseg; ++by)
+            for (int bx = 0; bx < nstrips; ++bx) {
+                int ra = L.ra, rb = L.rb;
+                rc |= run_cta(S * TW, bx, by, bz, sizeof(OcStageSmem<TW>) * S, [&](EmuCtx& ctx) {
+                    oc_march_body<M, S, TW, EmuCtx>(ctx, k, A, B, C, D, ra, rb, RS, x_halo);
+                });
+            }
+    return rc;
+}
+
+template <class M>
+static int emu_march_dispatch(EmuCloth* e, const OcLaunch& L, int TW, int RS)
+{
+    int x_halo = (e->k.U <= TW) ? 0 : 2 * L.S;
+    if (TW - 2 * x_halo <= 0) return -2;
+#define EMU_CASE(s, tw) if (L.S == s && TW == tw) return emu_march<M, s, tw>(e, L, RS, x_halo);
+    EMU_CASE(1, 16) EMU_CASE(2, 16) EMU_CASE(3, 16)
+    EMU_CASE(1, 32) EMU_CASE(2, 32) EMU_CASE(4, 32) EMU_CASE(8, 32)
+    EMU_CASE(1, 64) EMU_CASE(2, 64) EMU_CASE(4, 64) EMU_CASE(8, 64)
+    EMU_CASE(1, 128) EMU_CASE(2, 128) EMU_CASE(4, 128)
+#undef EMU_CASE
+    return -2;
+}
+
+template <class M>
+static void emu_gather(EmuCloth* e, const OcLaunch& L)
+{
+    const OcConst& k = e->k;
+    const float4* A = e->buf[L.src_a].data();
+    const float4* B = e->buf[L.src_b].data();
+    float4* C = e->buf[L.dst].data();
+    for (int b = 0; b < k.batch; ++b)
+        for (int j = L.ra; j < L.rb; ++j)
+            for (int i = 0; i < k.U; ++i) C[oc_index(k, b, i, j)] = oc_gather_particle<M>(k, A, B, b, i, j);
+}
+
+extern "C" {
+
+void* emu_create(const oc_params* p)
+{
+    if (!p || p->nx < 3 || p->ny < 3 || p->batch < 1) return nullptr;
+    EmuCloth* e = new EmuCloth();
+    e->p = *p;
+    memset(&e->k, 0, sizeof(e->k));
+    oc_host_geometry(e->p, e->k, e->q);
+    e->rows_own = e->p.row_end - e->p.row_begin;
+    e->stored = e->k.cloth_stride * p->batch;
+    oc_host_derive_scalars(e->p, e->k);
+    oc_host_build_tables(p->nx, p->ny, p->fullsize, e->T);
+    oc_host_bind_tables(e->k, e->T.t.data(), e->T);
+    const float* xs = &e->T.t[e->T.xs]; const float* zs = &e->T.t[e->T.zs];
+    for (int b = 0; b < 4; ++b) e->buf[b].resize((size_t)e->stored);
+    long long per = e->k.cloth_stride;
+    for (long long t = 0; t < e->stored; ++t) {
+        long long r = t % per;
+        int j = (int)(r / e->k.U) + e->k.row_lo, i = (int)(r % e->k.U);
+        float4 v = make_float4(xs[i], p->fullsize + 1, zs[j], oc_u2f(OC_W_PLAIN));
+        e->buf[0][t] = e->buf[1][t] = e->buf[2][t] = e->buf[3][t] = v;
+    }
+    e->barrier_errors = 0;
+    return e;
+}
+void emu_destroy(void* h) { delete (EmuCloth*)h; }
+void emu_set_order(int order) { g_order = order; }
+
+int emu_set_params(void* h, const oc_params* p)
+{
+    EmuCloth* e = (EmuCloth*)h;
+    oc_params q = *p;
+    q.row_begin = e->p.row_begin; q.row_end = e->p.row_end; q.halo_rows = e->p.halo_rows;
+    e->p = q;
+    oc_host_derive_scalars(e->p, e->k);
+    return 0;
+}
+
+int emu_upload(void* h, const float* X, const float* XL)
+{
+    EmuCloth* e = (EmuCloth*)h;
+    const OcConst& k = e->k;
+    long long t = 0;
+    for (int b = 0; b < k.batch; ++b)
+        for (int j = e->p.row_begin; j < e->p.row_end; ++j)
+            for (int i = 0; i < k.U; ++i, ++t) {
+                long long o = oc_index(k, b, i, j);
+                e->buf[e->q.ia][o] = make_float4(X[t * 3], X[t * 3 + 1], X[t * 3 + 2], oc_u2f(OC_W_PLAIN));
+                e->buf[e->q.ib][o] = make_float4(XL[t * 3], XL[t * 3 + 1], XL[t * 3 + 2], oc_u2f(OC_W_PLAIN));
+            }
+    if (e->q.band) e->q.fresh = e->q.kmax;
+    return 0;
+}
+
+int emu_download(void* h, float* X, float* XL)
+{
+    EmuCloth* e = (EmuCloth*)h;
+    const OcConst& k = e->k;
+    long long t = 0;
+    for (int b = 0; b < k.batch; ++b)
+        for (int j = e->p.row_begin; j < e->p.row_end; ++j)
+            for (int i = 0; i < k.U; ++i, ++t) {
+                long long o = oc_index(k, b, i, j);
+                float4 a = e->buf[e->q.ia][o];
+                float4 q = oc_hit(a.w) ? a : e->buf[e->q.ib][o];
+                if (X)  { X[t * 3] = a.x; X[t * 3 + 1] = a.y; X[t * 3 + 2] = a.z; }
+                if (XL) { XL[t * 3] = q.x; XL[t * 3 + 1] = q.y; XL[t * 3 + 2] = q.z; }
+            }
+    return 0;
+}
+
+// kernel: 1 = gather, 2 = march.  k = substeps per launch, TW = column window, RS = rows per segment
+// (0 = one segment).  Returns 0, -1 on a barrier-count mismatch, -2 unsupported variant, -3 halo exhausted.
+int emu_step(void* h, int n, int kernel, int exact, int k, int TW, int RS)
+{
+    EmuCloth* e = (EmuCloth*)h;
+    if (e->q.band && e->q.fresh + n > e->q.kmax) return -3;
+    int rc = 0;
+    while (n > 0) {
+        OcLaunch L;
+        // same stage-count choice as oc_step (TW = 16 exists only here and also has a 3-stage build)
+        int kk = 1;
+        if (kernel == 2) { int w = n < k ? n : k; kk = (TW == 16 && w <= 3) ? w : oc_host_pick_stages(w); }
+        oc_host_next_launch(e->q, n, kk, L);
+        if (kernel == 2) {
+            int r = exact ? emu_march_dispatch<MathExact>(e, L, TW, RS) : emu_march_dispatch<MathFast>(e, L, TW, RS);
+            if (r == -2) return -2;
+            rc |= r;
+        } else {
+            if (exact) emu_gather<MathExact>(e, L); else emu_gather<MathFast>(e, L);
+        }
+    }
+    return rc;
+}
+
+// copy the rows src sends towards `side` into dst's halo on the opposite side (both buffers)
+int emu_halo_copy(void* hsrc, int side, void* hdst)
+{
+    EmuCloth* s = (EmuCloth*)hsrc; EmuCloth* d = (EmuCloth*)hdst;
+    int r0s, ns, r0d, nd;
+    if (!oc_host_halo_rows(s->p, s->q.band, side, true, &r0s, &ns)) return 0;
+    if (!oc_host_halo_rows(d->p, d->q.band, 1 - side, false, &r0d, &nd)) return -1;
+    if (ns != nd || r0s != r0d) return -1;
+    const int U = s->k.U;
+    for (int which = 0; which < 2; ++which) {
+        const float4* src = s->buf[which == 0 ? s->q.ia : s->q.ib].data() + (long long)(r0s - s->k.row_lo) * U;
+        float4* dst = d->buf[which == 0 ? d->q.ia : d->q.ib].data() + (long long)(r0d - d->k.row_lo) * U;
+        memcpy(dst, src, (size_t)ns * U * sizeof(float4));
+    }
+    return 0;
+}
+// host pointer + float4 count of a halo region (same meaning as oc_halo_send_region / oc_halo_recv_region)
+int emu_halo_region(void* h, int side, int which, int send, void** ptr, size_t* count)
+{
+    EmuCloth* e = (EmuCloth*)h;
+    *ptr = nullptr; *count = 0;
+    int r0, rows;
+    if (!oc_host_halo_rows(e->p, e->q.band, side, send != 0, &r0, &rows)) return 0;
+    float4* base = e->buf[which == 0 ? e->q.ia : e->q.ib].data();
+    *ptr = (void*)(base + (long long)(r0 - e->k.row_lo) * e->k.U);
+    *count = (size_t)rows * e->k.U;
+    return 0;
+}
+int emu_halo_refreshed(void* h) { ((EmuCloth*)h)->q.fresh = 0; return 0; }
+int emu_halo_budget(void* h) { EmuCloth* e = (EmuCloth*)h; return e->q.band ? e->q.kmax - e->q.fresh : 0x7fffffff; }
+
+} // extern "C"

@@ -1,0 +1,336 @@
+"""Test helpers: ctypes wrappers of the CHECKERS (oracle restatement, verbatim reference build,
+CPU kernel emulator).  Test infrastructure only — nothing here is imported by the product."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_SO = os.path.join(ROOT, "oracle", "liboc_oracle.so")
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "libocref.so")
+EMU_SO = os.path.join(ROOT, "tests", "emu", "liboc_emu.so")
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+
+
+def _newer(target, *sources):
+    if not os.path.exists(target):
+        return False
+    t = os.path.getmtime(target)
+    return all(os.path.getmtime(s) <= t for s in sources if os.path.exists(s))
+
+
+def build_emulator():
+    src = os.path.join(ROOT, "tests", "emu", "oc_emu.cu")
+    csrc = os.path.join(ROOT, "opencloth_b200", "csrc")
+    deps = [src] + [os.path.join(csrc, f) for f in ("oc_core.cuh", "oc_host.h", "oc_gather.cuh", "oc_march.cuh")]
+    if _newer(EMU_SO, *deps):
+        return
+    subprocess.check_call([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-std=c++17",
+                           "-Xcompiler", "-fPIC,-ffp-contract=off,-O2", "-diag-suppress", "20011,20014",
+                           "-shared", src, "-o", EMU_SO])
+
+
+def ensure_built():
+    env = dict(os.environ, CC="gcc", CXX="g++")
+    if not _newer(ORACLE_SO, os.path.join(ROOT, "oracle", "oc_oracle.c")):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "liboc_oracle.so"], env=env)
+    if not os.path.exists(REF_SO) and os.path.exists("/root/reference"):
+        subprocess.check_call([os.path.join(ROOT, "oracle", "build_ref.sh")], env=env)
+    from opencloth_b200 import _abi
+    if not os.path.exists(_abi.LIB_PATH):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "opencloth_b200", "csrc"), "-j8"], env=env)
+    build_emulator()
+
+
+def vp(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def bitwise_equal(a, b):
+    return a.shape == b.shape and bool((bits(a) == bits(b)).all())
+
+
+# ---------------------------------------------------------------------------------------------
+# oracle restatement (oracle/oc_oracle.c)
+# ---------------------------------------------------------------------------------------------
+class OcoParams(ctypes.Structure):
+    _fields_ = [("nx", ctypes.c_int), ("ny", ctypes.c_int), ("fullsize", ctypes.c_float),
+                ("ks_struct", ctypes.c_float), ("kd_struct", ctypes.c_float),
+                ("ks_shear", ctypes.c_float), ("kd_shear", ctypes.c_float),
+                ("ks_bend", ctypes.c_float), ("kd_bend", ctypes.c_float),
+                ("damping", ctypes.c_float), ("gravity", ctypes.c_float * 3),
+                ("mass", ctypes.c_float), ("dt", ctypes.c_float),
+                ("ellipsoid", ctypes.c_float * 16), ("inv_ellipsoid", ctypes.c_float * 16),
+                ("center", ctypes.c_float * 3), ("radius", ctypes.c_float)]
+
+
+_oracle = None
+
+
+def oracle_lib():
+    global _oracle
+    if _oracle is None:
+        L = ctypes.CDLL(ORACLE_SO)
+        L.oco_create.restype = ctypes.c_void_p
+        L.oco_create.argtypes = [ctypes.POINTER(OcoParams)]
+        L.oco_default_params.argtypes = [ctypes.POINTER(OcoParams), ctypes.c_int, ctypes.c_int]
+        L.oco_destroy.argtypes = [ctypes.c_void_p]
+        L.oco_set_params.argtypes = [ctypes.c_void_p, ctypes.POINTER(OcoParams)]
+        L.oco_step.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        L.oco_step_rows.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+        L.oco_get_state.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        L.oco_set_state.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        L.oco_get_rows.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+        L.oco_set_rows.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+        L.oco_spring_energy.restype = ctypes.c_double
+        L.oco_spring_energy.argtypes = [ctypes.c_void_p]
+        L.oco_get_tables.argtypes = [ctypes.c_void_p] + [ctypes.c_void_p] * 6
+        _oracle = L
+    return _oracle
+
+
+class Oracle:
+    """CPU restatement of StepPhysics (gather order). The checker."""
+
+    def __init__(self, nx, ny, **overrides):
+        L = oracle_lib()
+        self.L = L
+        self.p = OcoParams()
+        L.oco_default_params(ctypes.byref(self.p), nx, ny)
+        self._apply(overrides)
+        self.h = ctypes.c_void_p(L.oco_create(ctypes.byref(self.p)))
+        assert self.h, "oco_create failed"
+        self.nx, self.ny, self.n = nx, ny, nx * ny
+
+    def _apply(self, overrides):
+        for k, v in overrides.items():
+            cur = getattr(self.p, k)
+            if hasattr(cur, "__len__"):
+                for i, x in enumerate(v):
+                    cur[i] = x
+            else:
+                setattr(self.p, k, v)
+
+    def set_params(self, **overrides):
+        self._apply(overrides)
+        assert self.L.oco_set_params(self.h, ctypes.byref(self.p)) == 0
+
+    def step(self, n=1):
+        self.L.oco_step(self.h, n)
+
+    def step_rows(self, j0, j1):
+        self.L.oco_step_rows(self.h, j0, j1)
+
+    def state(self):
+        x = np.empty((self.n, 3), np.float32)
+        xl = np.empty((self.n, 3), np.float32)
+        self.L.oco_get_state(self.h, vp(x), vp(xl))
+        return x, xl
+
+    def set_state(self, x, xl):
+        x = np.ascontiguousarray(x, np.float32)
+        xl = np.ascontiguousarray(xl, np.float32)
+        self.L.oco_set_state(self.h, vp(x), vp(xl))
+
+    def get_rows(self, j0, j1):
+        x = np.empty(((j1 - j0) * self.nx, 3), np.float32)
+        xl = np.empty_like(x)
+        self.L.oco_get_rows(self.h, j0, j1, vp(x), vp(xl))
+        return x, xl
+
+    def set_rows(self, j0, j1, x, xl):
+        self.L.oco_set_rows(self.h, j0, j1, vp(np.ascontiguousarray(x, np.float32)), vp(np.ascontiguousarray(xl, np.float32)))
+
+    def energy(self):
+        return self.L.oco_spring_energy(self.h)
+
+    def tables(self):
+        t = [np.empty(self.nx, np.float32) for _ in range(2)] + [np.empty(self.ny, np.float32) for _ in range(2)] + \
+            [np.empty(self.nx, np.float32), np.empty(self.ny, np.float32)]
+        self.L.oco_get_tables(self.h, *[vp(a) for a in t])
+        return dict(rh1=t[0], rh2=t[1], rv1=t[2], rv2=t[3], dx2=t[4], dz2=t[5])
+
+    def close(self):
+        if self.h:
+            self.L.oco_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ---------------------------------------------------------------------------------------------
+# verbatim reference build (oracle/_ref/libocref.so) — single global simulation, like the reference
+# ---------------------------------------------------------------------------------------------
+def have_ref():
+    return os.path.exists(REF_SO)
+
+
+_ref = None
+
+
+def ref_lib():
+    global _ref
+    if _ref is None:
+        L = ctypes.CDLL(REF_SO)
+        L.ref_num_particles.restype = ctypes.c_size_t
+        L.ref_num_springs.restype = ctypes.c_size_t
+        L.ref_spring_energy.restype = ctypes.c_double
+        L.ref_get_state.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        L.ref_set_state.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        L.ref_get_springs.argtypes = [ctypes.c_void_p] * 6
+        L.ref_get_ellipsoid.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        L.ref_get_params.argtypes = [ctypes.c_void_p]
+        _ref = L
+    return _ref
+
+
+class Ref:
+    def __init__(self, nx, ny):
+        self.L = ref_lib()
+        assert self.L.ref_init(nx, ny) == 0
+        self.n = self.L.ref_num_particles()
+        self.nx, self.ny = nx, ny
+
+    def step(self, n=1):
+        self.L.ref_step(n)
+
+    def state(self):
+        x = np.empty((self.n, 3), np.float32)
+        xl = np.empty((self.n, 3), np.float32)
+        self.L.ref_get_state(vp(x), vp(xl))
+        return x, xl
+
+    def set_state(self, x, xl):
+        self.L.ref_set_state(vp(np.ascontiguousarray(x, np.float32)), vp(np.ascontiguousarray(xl, np.float32)))
+
+    def energy(self):
+        return self.L.ref_spring_energy()
+
+    def springs(self):
+        s = self.L.ref_num_springs()
+        p1 = np.empty(s, np.int32); p2 = np.empty(s, np.int32); rest = np.empty(s, np.float32)
+        ks = np.empty(s, np.float32); kd = np.empty(s, np.float32); ty = np.empty(s, np.int32)
+        self.L.ref_get_springs(vp(p1), vp(p2), vp(rest), vp(ks), vp(kd), vp(ty))
+        return dict(p1=p1, p2=p2, rest=rest, ks=ks, kd=kd, type=ty)
+
+    def ellipsoid(self):
+        m = np.empty(16, np.float32); mi = np.empty(16, np.float32)
+        self.L.ref_get_ellipsoid(vp(m), vp(mi))
+        return m, mi
+
+    def params(self):
+        p = np.empty(16, np.float32)
+        self.L.ref_get_params(vp(p))
+        return p
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU emulation of the product's kernel bodies (tests/emu/oc_emu.cu)
+# ---------------------------------------------------------------------------------------------
+_emu = None
+
+
+def emu_lib():
+    global _emu
+    if _emu is None:
+        from opencloth_b200._abi import OcParams
+        L = ctypes.CDLL(EMU_SO)
+        L.emu_create.restype = ctypes.c_void_p
+        L.emu_create.argtypes = [ctypes.POINTER(OcParams)]
+        L.emu_destroy.argtypes = [ctypes.c_void_p]
+        L.emu_set_params.argtypes = [ctypes.c_void_p, ctypes.POINTER(OcParams)]
+        L.emu_upload.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        L.emu_download.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        L.emu_step.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 6
+        L.emu_halo_copy.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+        L.emu_halo_refreshed.argtypes = [ctypes.c_void_p]
+        L.emu_halo_budget.argtypes = [ctypes.c_void_p]
+        L.emu_halo_region.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                      ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_size_t)]
+        L.emu_set_order.argtypes = [ctypes.c_int]
+        _emu = L
+    return _emu
+
+
+class Emu:
+    """The product's kernels run on the CPU (fibers as CUDA threads). Same host sequencing as the C-ABI."""
+
+    def __init__(self, nx, ny, **overrides):
+        from opencloth_b200._abi import OcParams, load
+        self.L = emu_lib()
+        p = OcParams()
+        load().oc_default_params(ctypes.byref(p), nx, ny)       # host-only call, no GPU needed
+        for k, v in overrides.items():
+            cur = getattr(p, k)
+            if hasattr(cur, "__len__"):
+                for i, x in enumerate(v):
+                    cur[i] = x
+            else:
+                setattr(p, k, v)
+        self.p = p
+        self.h = ctypes.c_void_p(self.L.emu_create(ctypes.byref(p)))
+        assert self.h, "emu_create failed"
+        rb, re = p.row_begin, p.row_end
+        if rb == 0 and re == 0:
+            re = ny
+        self.nx, self.ny, self.rows = nx, ny, re - rb
+        self.n_local = p.batch * self.rows * nx
+
+    def step(self, n, kernel=2, exact=1, k=1, TW=32, RS=0):
+        rc = self.L.emu_step(self.h, n, kernel, exact, k, TW, RS)
+        assert rc == 0, f"emu_step rc={rc} (-1 barrier mismatch, -2 unsupported variant, -3 halo exhausted)"
+
+    def upload(self, x, xl):
+        self.L.emu_upload(self.h, vp(np.ascontiguousarray(x, np.float32)), vp(np.ascontiguousarray(xl, np.float32)))
+
+    def download(self):
+        x = np.empty((self.n_local, 3), np.float32)
+        xl = np.empty((self.n_local, 3), np.float32)
+        self.L.emu_download(self.h, vp(x), vp(xl))
+        return x, xl
+
+    def halo_region(self, side, which, send):
+        ptr = ctypes.c_void_p(); cnt = ctypes.c_size_t()
+        assert self.L.emu_halo_region(self.h, side, which, 1 if send else 0, ctypes.byref(ptr), ctypes.byref(cnt)) == 0
+        return (ptr.value or 0), cnt.value
+
+    def halo_refreshed(self):
+        self.L.emu_halo_refreshed(self.h)
+
+    @property
+    def halo_budget(self):
+        return self.L.emu_halo_budget(self.h)
+
+    def close(self):
+        if self.h:
+            self.L.emu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def developed_state(nx, ny, steps):
+    """(X, X_last) of the default cloth after `steps` oracle steps: a non-trivial start state."""
+    o = Oracle(nx, ny)
+    o.step(steps)
+    s = o.state()
+    o.close()
+    return s
+
+
+def load_golden(name):
+    return np.load(os.path.join(GOLDEN, name))

@@ -1,0 +1,159 @@
+"""CPU tier: the product's kernel BODIES (opencloth_b200/csrc/*.cuh) executed on the CPU by
+tests/emu (fibers as CUDA threads, cooperative barrier as __syncthreads) against the oracle.
+
+This checks the logic a GPU run would otherwise be needed for — index arithmetic of strips /
+segments / stages, the shared-memory pipeline hazards, the accumulation order, the k-substep
+temporal blocking, batches and the row-band halo protocol — bit for bit.  The arithmetic on the
+host (IEEE fp32, no contraction) is what MathExact's device intrinsics compute."""
+import numpy as np
+import pytest
+
+import helpers
+from helpers import Emu, Oracle, bitwise_equal
+
+GATHER, MARCH = 1, 2
+
+
+def run_pair(nx, ny, pre, steps, **kw):
+    x0, xl0 = helpers.developed_state(nx, ny, pre) if pre else Oracle(nx, ny).state()
+    o = Oracle(nx, ny); o.set_state(x0, xl0)
+    e = Emu(nx, ny)
+    if pre:
+        e.upload(x0, xl0)
+    e.step(steps, **kw)
+    o.step(steps)
+    ex, exl = e.download(); ox, oxl = o.state()
+    assert bitwise_equal(ex, ox), f"X differs in {(helpers.bits(ex) != helpers.bits(ox)).any(1).sum()} particles"
+    assert bitwise_equal(exl, oxl), "X_last differs"
+    return int((ox == oxl).all(1).sum())
+
+
+@pytest.mark.parametrize("nx,ny,pre,steps", [(21, 21, 0, 60), (21, 21, 1800, 150), (37, 23, 1900, 40), (3, 3, 3, 50), (5, 4, 3, 50)])
+def test_gather_kernel_body(nx, ny, pre, steps):
+    hits = run_pair(nx, ny, pre, steps, kernel=GATHER)
+    if pre >= 1800:
+        assert hits > 2          # the collider is active in this window
+
+
+# (nx, ny, pre-steps, steps, k, TW, RS): single strip / multi strip, one / many segments, every k
+MARCH_CASES = [
+    (21, 21, 0, 20, 1, 32, 0), (21, 21, 0, 20, 1, 32, 7), (21, 21, 0, 20, 2, 32, 0), (21, 21, 0, 20, 4, 32, 5),
+    (21, 21, 0, 16, 8, 32, 0), (21, 21, 1800, 100, 4, 32, 0), (21, 21, 1800, 40, 8, 32, 6),
+    (37, 23, 1900, 12, 1, 16, 5), (37, 23, 1900, 12, 2, 16, 6), (37, 23, 1900, 12, 3, 16, 4),
+    (64, 64, 2000, 8, 1, 32, 10), (64, 64, 2000, 8, 2, 32, 9), (64, 64, 2000, 8, 4, 32, 0),
+    (70, 40, 1500, 8, 4, 64, 13), (70, 40, 1500, 8, 8, 64, 0),
+    (130, 20, 500, 4, 4, 128, 7), (130, 20, 500, 4, 1, 128, 0), (128, 24, 500, 4, 2, 128, 0),
+    (3, 3, 5, 40, 1, 32, 0), (3, 3, 5, 40, 8, 32, 0), (5, 4, 5, 40, 2, 16, 2), (4, 9, 5, 23, 3, 16, 3),
+]
+
+
+@pytest.mark.parametrize("nx,ny,pre,steps,k,TW,RS", MARCH_CASES)
+def test_march_kernel_body(nx, ny, pre, steps, k, TW, RS):
+    run_pair(nx, ny, pre, steps, kernel=MARCH, k=k, TW=TW, RS=RS)
+
+
+@pytest.mark.parametrize("order", [1, 2])
+def test_march_is_independent_of_thread_schedule(order):
+    """No intra-phase data race: resuming the threads in reverse / pseudo-random order between
+    barriers must not change a bit."""
+    L = helpers.emu_lib()
+    L.emu_set_order(order)
+    try:
+        run_pair(37, 23, 1900, 9, kernel=MARCH, k=3, TW=16, RS=4)
+        run_pair(64, 64, 2000, 8, kernel=MARCH, k=4, TW=32, RS=11)
+        run_pair(70, 40, 1500, 8, kernel=MARCH, k=8, TW=64, RS=0)
+    finally:
+        L.emu_set_order(0)
+
+
+def test_temporal_blocking_equals_single_steps():
+    """k substeps per launch == k launches of one substep ('temporal blocking')."""
+    x0, xl0 = helpers.developed_state(40, 33, 1700)
+    ref = Emu(40, 33); ref.upload(x0, xl0); ref.step(24, kernel=MARCH, k=1, TW=64)
+    rx, rxl = ref.download()
+    for k in (2, 4, 8):
+        e = Emu(40, 33); e.upload(x0, xl0); e.step(24, kernel=MARCH, k=k, TW=64, RS=9)
+        x, xl = e.download()
+        assert bitwise_equal(x, rx) and bitwise_equal(xl, rxl), f"k={k}"
+
+
+def test_fast_mode_body_within_tolerance():
+    """MathFast on the host (FMA-free, 1/sqrt) still re-associates: must stay within the north-star
+    tolerance of the oracle: <= 1e-5 of the cloth extent (fullsize = 4) after 100 steps."""
+    o = Oracle(21, 21); o.step(100)
+    e = Emu(21, 21); e.step(100, kernel=MARCH, exact=0, k=4, TW=32)
+    err = np.abs(e.download()[0].astype(np.float64) - o.state()[0]).max() / 4.0
+    assert err <= 1e-5, err
+
+
+def test_batched_cloths_are_independent():
+    """batch > 1: every cloth of the batch evolves exactly like a single cloth from the same start."""
+    nx, ny, B = 20, 17, 3
+    rng = np.random.RandomState(7)
+    base = Oracle(nx, ny).state()[0]
+    starts = []
+    for b in range(B):
+        x = base.copy()
+        x[:, 1] += (1e-3 * rng.uniform(-1, 1, len(x))).astype(np.float32)
+        starts.append(x)
+    e = Emu(nx, ny, batch=B)
+    X0 = np.concatenate(starts)
+    e.upload(X0, X0)
+    e.step(30, kernel=MARCH, k=2, TW=32, RS=6)
+    ex, exl = e.download()
+    for b in range(B):
+        o = Oracle(nx, ny); o.set_state(starts[b], starts[b]); o.step(30)
+        ox, oxl = o.state()
+        sl = slice(b * nx * ny, (b + 1) * nx * ny)
+        assert bitwise_equal(ex[sl], ox) and bitwise_equal(exl[sl], oxl), f"cloth {b}"
+
+
+@pytest.mark.parametrize("nbands,halo,k,kernel", [(2, 4, 1, MARCH), (3, 8, 2, MARCH), (4, 4, 2, MARCH), (2, 6, 1, GATHER), (3, 8, 4, MARCH)])
+def test_row_bands_with_halo_exchange_equal_single_domain(nbands, halo, k, kernel):
+    """Row-band decomposition: g bands with halo_rows rows of neighbour state, one
+    exchange per halo_rows/2 substeps, redundant recomputation of the shrinking halo in between.
+    Result must equal the undivided cloth bit for bit."""
+    nx, ny = 23, 48
+    x0, xl0 = helpers.developed_state(nx, ny, 1500)
+    whole = Oracle(nx, ny); whole.set_state(x0, xl0)
+    cuts = [round(ny * b / nbands) for b in range(nbands + 1)]
+    bands = []
+    for b in range(nbands):
+        e = Emu(nx, ny, row_begin=cuts[b], row_end=cuts[b + 1], halo_rows=halo)
+        sl = slice(cuts[b] * nx, cuts[b + 1] * nx)
+        e.upload(x0[sl], xl0[sl])
+        assert e.halo_budget == 0           # an uploaded band must exchange before it may step
+        bands.append(e)
+
+    def exchange():
+        L = helpers.emu_lib()
+        for b in range(nbands):
+            if b + 1 < nbands:
+                assert L.emu_halo_copy(bands[b].h, 1, bands[b + 1].h) == 0
+                assert L.emu_halo_copy(bands[b + 1].h, 0, bands[b].h) == 0
+        for e in bands:
+            e.halo_refreshed()
+
+    total = 0
+    per = halo // 2
+    for rnd in range(3):
+        exchange()
+        n = per if rnd < 2 else max(1, per - 1)     # last round: a partial group
+        for e in bands:
+            e.step(n, kernel=kernel, k=k, TW=32, RS=5)
+        total += n
+    whole.step(total)
+    wx, wxl = whole.state()
+    for b, e in enumerate(bands):
+        x, xl = e.download()
+        sl = slice(cuts[b] * nx, cuts[b + 1] * nx)
+        assert bitwise_equal(x, wx[sl]) and bitwise_equal(xl, wxl[sl]), f"band {b}"
+
+
+def test_band_refuses_to_step_past_its_halo():
+    e = Emu(21, 40, row_begin=10, row_end=30, halo_rows=4)
+    assert e.halo_budget == 2
+    e.step(2, kernel=MARCH, k=1, TW=32)
+    assert e.halo_budget == 0
+    rc = helpers.emu_lib().emu_step(e.h, 1, MARCH, 1, 1, 32, 0)
+    assert rc == -3
