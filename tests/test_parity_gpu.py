@@ -1,0 +1,263 @@
+"""GPU tier (-m gpu): the CUDA path, called through the C-ABI, against the oracle and the committed
+golden vectors.  Bar: BIT-EXACT in exact mode (the kernels evaluate the reference's fp32 operations
+in the reference's order); in fast mode the north-star tolerance: max position error <= 1e-5 of the
+cloth extent (fullsize = 4) after 100 steps and <= 1e-3 after 1000 steps."""
+import hashlib
+import json
+
+import numpy as np
+import pytest
+
+import helpers
+from helpers import Oracle, bitwise_equal
+
+pytestmark = pytest.mark.gpu
+
+EXTENT = 4.0
+
+
+def oc():
+    import opencloth_b200
+    return opencloth_b200
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a, np.float32).tobytes()).hexdigest()
+
+
+def golden(name):
+    g = helpers.load_golden(name)
+    return g, json.loads(bytes(g["meta"]).decode())
+
+
+def nbad(a, b):
+    return int((helpers.bits(a) != helpers.bits(b)).any(1).sum())
+
+
+# ---------------------------------------------------------------------------------------------
+# golden vectors of the verbatim reference
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["grid_21x21.npz", "grid_37x23.npz", "grid_64x64.npz", "grid_256x256.npz"])
+@pytest.mark.parametrize("kernel,k", [("march", 1), ("march", 4), ("gather", 1)])
+def test_cuda_matches_reference_golden(name, kernel, k):
+    g, meta = golden(name)
+    nx, ny = meta["nx"], meta["ny"]
+    m = oc()
+    c = m.Cloth(nx, ny, kernel=m.OC_KERNEL_MARCH if kernel == "march" else m.OC_KERNEL_GATHER, substeps_per_launch=k)
+    step = 0
+    for cp in meta["checkpoints"]:
+        c.step(cp - step)
+        step = cp
+        x, xl = c.download()
+        assert sha(x) == meta["sha_x"][str(cp)], f"X differs from the reference at step {cp}"
+        assert sha(xl) == meta["sha_xl"][str(cp)], f"X_last differs from the reference at step {cp}"
+        assert int((x == xl).all(1).sum()) == meta["hits"][str(cp)]
+        assert c.spring_energy() == pytest.approx(meta["energy"][str(cp)], rel=1e-9)
+    c.close()
+
+
+def test_energy_trajectory_matches_reference():
+    """Spring energy every 10 steps over 1000 steps of the 256x256 cloth (north star)."""
+    g, meta = golden("grid_256x256.npz")
+    m = oc()
+    c = m.Cloth(256, 256, substeps_per_launch=2)
+    e = []
+    for _ in range(100):
+        c.step(10)
+        e.append(c.spring_energy())
+    np.testing.assert_allclose(np.asarray(e), g["energy_traj"][:100], rtol=1e-9)
+    c.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# oracle on the same seeded inputs
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("nx,ny,pre,steps", [(3, 3, 0, 300), (4, 7, 0, 300), (21, 21, 1650, 400), (37, 23, 1800, 300),
+                                             (100, 61, 1500, 200), (129, 40, 800, 100), (300, 200, 600, 100), (1000, 37, 300, 50)])
+@pytest.mark.parametrize("kernel,k", [("march", 1), ("march", 2), ("march", 8), ("gather", 1)])
+def test_cuda_matches_oracle_bitwise(nx, ny, pre, steps, kernel, k):
+    m = oc()
+    x0, xl0 = helpers.developed_state(nx, ny, pre)
+    o = Oracle(nx, ny); o.set_state(x0, xl0); o.step(steps)
+    c = m.Cloth(nx, ny, kernel=m.OC_KERNEL_MARCH if kernel == "march" else m.OC_KERNEL_GATHER, substeps_per_launch=k)
+    c.upload(x0, xl0)
+    c.step(steps)
+    x, xl = c.download()
+    ox, oxl = o.state()
+    assert bitwise_equal(x, ox), f"{nbad(x, ox)} particles differ"
+    assert bitwise_equal(xl, oxl)
+    c.close()
+
+
+def test_temporal_blocking_equals_single_steps():
+    """k in {1,2,4,8} substeps per launch, and odd step counts that split into mixed launches."""
+    m = oc()
+    nx, ny = 517, 260
+    x0, xl0 = helpers.developed_state(nx, ny, 400)
+    outs = []
+    for k in (1, 2, 4, 8, 3, 7):
+        c = m.Cloth(nx, ny, kernel=m.OC_KERNEL_MARCH, substeps_per_launch=k)
+        c.upload(x0, xl0)
+        c.step(29)
+        outs.append(c.download())
+        c.close()
+    for x, xl in outs[1:]:
+        assert bitwise_equal(x, outs[0][0]) and bitwise_equal(xl, outs[0][1])
+
+
+def test_large_grid_matches_oracle_2048():
+    """BASELINE config 3 size: 2048 x 2048, 20 steps, bitwise, plus the stride-4 host layout."""
+    m = oc()
+    n = 2048
+    o = Oracle(n, n); o.step(20)
+    ox, oxl = o.state()
+    for k in (1, 4):
+        c = m.Cloth(n, n, substeps_per_launch=k)
+        c.step(20)
+        x, xl = c.download()
+        assert bitwise_equal(x, ox) and bitwise_equal(xl, oxl), f"k={k}: {nbad(x, ox)} particles differ"
+        x4, xl4 = c.download(stride=4)
+        assert bitwise_equal(x4[:, :3], ox) and (x4[:, 3] == 1.0).all()
+        c.close()
+
+
+def test_upload_download_round_trip_and_strides():
+    m = oc()
+    rng = np.random.RandomState(0)
+    c = m.Cloth(50, 30)
+    x = rng.randn(1500, 3).astype(np.float32); xl = rng.randn(1500, 3).astype(np.float32)
+    c.upload(x, xl)
+    gx, gxl = c.download()
+    assert bitwise_equal(gx, x) and bitwise_equal(gxl, xl)
+    x4 = np.concatenate([x, np.ones((1500, 1), np.float32)], 1); xl4 = np.concatenate([xl, np.ones((1500, 1), np.float32)], 1)
+    c.upload(x4, xl4)
+    gx, gxl = c.download(stride=4)
+    assert bitwise_equal(gx, x4) and bitwise_equal(gxl, xl4)
+    c.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# fast mode: tolerance of the north star
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("nx,ny", [(21, 21), (256, 256)])
+def test_fast_mode_within_tolerance(nx, ny):
+    m = oc()
+    o = Oracle(nx, ny)
+    c = m.Cloth(nx, ny, exact=0, substeps_per_launch=4)
+    o.step(100); c.step(100)
+    err100 = np.abs(c.download()[0].astype(np.float64) - o.state()[0]).max() / EXTENT
+    assert err100 <= 1e-5, f"fast mode: {err100:.3e} of extent after 100 steps (tolerance 1e-5)"
+    o.step(900); c.step(900)
+    err1000 = np.abs(c.download()[0].astype(np.float64) - o.state()[0]).max() / EXTENT
+    assert err1000 <= 1e-3, f"fast mode: {err1000:.3e} of extent after 1000 steps (tolerance 1e-3)"
+    e_o, e_c = o.energy(), c.spring_energy()
+    assert e_c == pytest.approx(e_o, rel=2e-2)
+    c.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# parameters, interaction, batches, bands
+# ---------------------------------------------------------------------------------------------
+def test_set_params_and_set_particle_follow_the_oracle():
+    m = oc()
+    nx, ny = 40, 40
+    o = Oracle(nx, ny); c = m.Cloth(nx, ny, substeps_per_launch=2)
+    o.step(50); c.step(50)
+    kw = dict(ks_struct=80.5, kd_shear=-0.5, damping=-0.05, gravity=(0.001, -0.02, 0.0005), mass=1.5, dt=1 / 90.0, radius=1.25)
+    o.set_params(**kw); c.set_params(**kw)
+    o.step(60); c.step(60)
+    # mouse drag (V:203-208): X[idx] = X_last[idx] = p
+    idx, p = 20 * nx + 20, (0.1, 3.0, 2.2)
+    x, xl = o.state(); x[idx] = p; xl[idx] = p; o.set_state(x, xl)
+    c.set_particle(idx, p)
+    o.step(200); c.step(200)
+    x, xl = c.download(); ox, oxl = o.state()
+    assert bitwise_equal(x, ox) and bitwise_equal(xl, oxl)
+    c.close()
+
+
+def test_floor_clamp_and_collider_are_exercised():
+    """Cloth dropped with strong gravity: reaches the ellipsoid and the floor (y < 0 -> 0, V:440-442)."""
+    m = oc()
+    nx, ny = 48, 48
+    kw = dict(gravity=(0.0, -0.5, 0.0))
+    o = Oracle(nx, ny, **kw); c = m.Cloth(nx, ny, substeps_per_launch=4, **kw)
+    o.step(1200); c.step(1200)
+    x, xl = c.download(); ox, oxl = o.state()
+    assert (ox[:, 1] == 0.0).sum() > 0, "test does not reach the floor"
+    assert int((ox == oxl).all(1).sum()) > 10, "test does not reach the collider"
+    assert bitwise_equal(x, ox) and bitwise_equal(xl, oxl)
+    c.close()
+
+
+def test_batched_cloths_match_per_cloth_oracle():
+    """BASELINE config 5 shape (128x128 cloths, per-cloth perturbation X.y += 1e-3 u, velocities 0),
+    a 24-cloth batch; every cloth checked against its own oracle run."""
+    m = oc()
+    nx = ny = 128
+    B = 24
+    base = Oracle(nx, ny).state()[0]
+    X0 = np.empty((B, nx * ny, 3), np.float32)
+    for b in range(B):
+        rng = np.random.RandomState(1234 + b)
+        X0[b] = base
+        X0[b, :, 1] += (1e-3 * rng.uniform(-1, 1, nx * ny)).astype(np.float32)
+    for k in (1, 4):
+        c = m.Cloth(nx, ny, batch=B, substeps_per_launch=k)
+        c.upload(X0.reshape(-1, 3), X0.reshape(-1, 3))
+        c.step(60)
+        x, xl = c.download()
+        x = x.reshape(B, -1, 3); xl = xl.reshape(B, -1, 3)
+        for b in (0, 1, 7, 13, 23):
+            o = Oracle(nx, ny); o.set_state(X0[b], X0[b]); o.step(60)
+            ox, oxl = o.state()
+            assert bitwise_equal(x[b], ox) and bitwise_equal(xl[b], oxl), f"k={k} cloth {b}"
+        c.close()
+
+
+@pytest.mark.parametrize("nbands,halo,k", [(2, 4, 1), (4, 8, 4), (3, 16, 8), (8, 8, 2)])
+def test_row_bands_single_process_equal_whole_cloth(nbands, halo, k):
+    """SURVEY.md 8(e) on one device: g band handles exchanging halos with oc_halo_exchange
+    (device-to-device copies ordered by events) must equal the undivided cloth bitwise."""
+    import ctypes
+    m = oc()
+    from opencloth_b200 import _abi
+    nx, ny = 200, 256
+    x0, xl0 = helpers.developed_state(nx, ny, 500)
+    whole = m.Cloth(nx, ny, substeps_per_launch=k); whole.upload(x0, xl0)
+    cuts = [round(ny * b / nbands) for b in range(nbands + 1)]
+    bands = []
+    for b in range(nbands):
+        c = m.Cloth(nx, ny, row_begin=cuts[b], row_end=cuts[b + 1], halo_rows=halo, substeps_per_launch=k)
+        sl = slice(cuts[b] * nx, cuts[b + 1] * nx)
+        c.upload(x0[sl], xl0[sl])
+        assert c.halo_budget == 0
+        bands.append(c)
+    arr = (ctypes.c_void_p * nbands)(*[c._h for c in bands])
+    per = halo // 2
+    total = 0
+    for rnd in range(4):
+        _abi.check(_abi.load().oc_halo_exchange(arr, nbands))
+        n = per if rnd != 2 else max(1, per - 1)
+        for c in bands:
+            c.step(n)
+        total += n
+    whole.step(total)
+    wx, wxl = whole.download()
+    for b, c in enumerate(bands):
+        x, xl = c.download()
+        sl = slice(cuts[b] * nx, cuts[b + 1] * nx)
+        assert bitwise_equal(x, wx[sl]) and bitwise_equal(xl, wxl[sl]), f"band {b}"
+        with pytest.raises(m.OpenClothError):
+            c.step(per + 1)          # more substeps than the halo allows
+        c.close()
+    whole.close()
+
+
+def test_launch_counter_and_timed_step():
+    m = oc()
+    c = m.Cloth(256, 256, substeps_per_launch=4)
+    n0 = c.launch_count
+    ms = c.step_timed(16)
+    assert c.launch_count - n0 == 4 and ms > 0
+    c.close()
