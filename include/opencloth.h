@@ -154,6 +154,11 @@ int oc_halo_exchange(oc_cloth* const* bands, int n);
 /* Spring energy  sum 1/2 Ks (|p1-p2| - rest)^2  over the reference's spring list (duplicated edge
  * bend springs included), reduced in double on the device; whole-cloth handles only. */
 int oc_spring_energy(oc_cloth* c, int cloth, double* energy);
+/* Device self-test of the branch-free IEEE sequences the exact-mode kernels use for sqrt, 1/x and
+ * a/b: n random operands (seeded) inside the accepted exponent ranges are compared with the
+ * correctly rounded intrinsics (sqrt.rn, rcp.rn, div.rn); *mismatches receives the number of
+ * differing results (must be 0). */
+int oc_selftest_math(unsigned long long n, unsigned int seed, unsigned long long* mismatches);
 /* sizeof(oc_params) as the library was compiled, so that FFI bindings can verify their mirror */
 size_t oc_sizeof_params(void);
 /* library / device info string: "opencloth_b200 abi=1 sm=100 device=NVIDIA B200 ..." */

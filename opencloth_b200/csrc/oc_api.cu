@@ -530,6 +530,72 @@ extern "C" int oc_halo_exchange(oc_cloth* const* bands, int n)
 // ------------------------------------------------------------------------------------------------
 // diagnostics
 // ------------------------------------------------------------------------------------------------
+// ---- self-test of the branch-free IEEE sequences (oc_core.cuh) against the rounding intrinsics ----
+__device__ __forceinline__ unsigned oc_rng(unsigned long long& st)
+{
+    st = st * 6364136223846793005ULL + 1442695040888963407ULL;
+    return (unsigned)(st >> 32);
+}
+// random float with a uniformly random exponent in [elo, ehi] (unbiased), random mantissa and sign s
+__device__ __forceinline__ float oc_rand_float(unsigned long long& st, int elo, int ehi, bool neg_ok)
+{
+    unsigned r = oc_rng(st);
+    unsigned e = (unsigned)(elo + 127) + (oc_rng(st) % (unsigned)(ehi - elo + 1));
+    unsigned bits = (e << 23) | (r & 0x7fffffu);
+    if (neg_ok && (r & 0x80000000u)) bits |= 0x80000000u;
+    return __uint_as_float(bits);
+}
+__global__ void oc_k_selftest(unsigned long long per_thread, unsigned seed, float dt, unsigned long long* out)
+{
+    unsigned long long st = ((unsigned long long)seed << 32) ^ (0x9E3779B97F4A7C15ULL * (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x + 1));
+    unsigned long long bad_count = 0;
+    const float ydt = oc_rcp_bf(dt);
+    for (unsigned long long it = 0; it < per_thread; ++it) {
+        bool bad = false;
+        // sqrt over [2^-94, 2^94], rcp of the result, spring-style division
+        float x = oc_rand_float(st, -94, 93, false);
+        float s = oc_sqrt_bf(x, bad);
+        if (__float_as_uint(s) != __float_as_uint(__fsqrt_rn(x))) bad_count++;
+        float y = oc_rcp_bf(s);
+        if (__float_as_uint(y) != __float_as_uint(__frcp_rn(s))) bad_count++;
+        float a = oc_rand_float(st, -70, 69, true);
+        if ((it & 63) == 0) a = (it & 64) ? -0.0f : 0.0f;
+        float q = oc_div_bf(a, s, y, OC_NUM_LO, OC_NUM_HI, bad);
+        if (__float_as_uint(q) != __float_as_uint(__fdiv_rn(a, s))) bad_count++;
+        // clustered operands: a/b close to 1 and to powers of two (hard rounding cases)
+        float b2 = oc_rand_float(st, -40, 40, false);
+        bool bad2 = false;
+        float sb = oc_sqrt_bf(b2 * b2, bad2);
+        float yb = oc_rcp_bf(sb);
+        float a2 = __uint_as_float(__float_as_uint(sb) + (oc_rng(st) & 7u) - 3u);
+        float q2 = oc_div_bf(a2, sb, yb, OC_NUM_LO, OC_NUM_HI, bad2);
+        if (__float_as_uint(q2) != __float_as_uint(__fdiv_rn(a2, sb))) bad_count++;
+        // velocity-style division by dt over [2^-100, 2^100]
+        float d = oc_rand_float(st, -100, 99, true);
+        float v = oc_div_bf(d, dt, ydt, OC_VEL_LO, OC_VEL_HI, bad);
+        if (__float_as_uint(v) != __float_as_uint(__fdiv_rn(d, dt))) bad_count++;
+        if (bad || bad2) bad_count += 1000000;      // operands were generated inside the accepted ranges
+    }
+    if (bad_count) atomicAdd(out, bad_count);
+}
+extern "C" int oc_selftest_math(unsigned long long n, unsigned int seed, unsigned long long* mismatches)
+{
+    if (!mismatches) return oc_fail(OC_ERR_INVALID, "oc_selftest_math: null");
+    unsigned long long* d = nullptr;
+    OC_CUDA(cudaMalloc(&d, sizeof(*d)));
+    OC_CUDA(cudaMemset(d, 0, sizeof(*d)));
+    const int blocks = 1184, threads = 256;
+    unsigned long long per = (n + (unsigned long long)blocks * threads - 1) / ((unsigned long long)blocks * threads);
+    const float dts[4] = { 1 / 60.0f, 1 / 90.0f, 0.001f, 0.37f };
+    for (int t = 0; t < 4; ++t) {
+        oc_k_selftest<<<blocks, threads>>>((per + 3) / 4, seed + t, dts[t], d);
+        OC_CUDA(cudaGetLastError());
+    }
+    OC_CUDA(cudaMemcpy(mismatches, d, sizeof(*d), cudaMemcpyDeviceToHost));
+    OC_CUDA(cudaFree(d));
+    return OC_OK;
+}
+
 extern "C" size_t oc_sizeof_params(void) { return sizeof(oc_params); }
 
 extern "C" int oc_spring_energy(oc_cloth* c, int cloth, double* energy)

@@ -51,6 +51,7 @@ static inline void oc_host_derive_scalars(const oc_params& p, OcConst& k)
 {
     k.dt = p.dt;
     k.inv_dt = 1.0f / p.dt;
+    k.dt_bf = (p.dt >= 0x1.0p-20f && p.dt <= 0x1.0p+20f) ? 1 : 0;
     k.dt2m = (p.dt * p.dt) / p.mass;                                  // V:429
     k.damping = p.damping;
     for (int a = 0; a < 3; ++a) k.f0[a] = 0.0f + p.gravity[a] * p.mass;   // V:452, V:456

@@ -47,8 +47,13 @@ struct OcPV { f3 x, v; };
 
 #ifdef __CUDA_ARCH__
 #define OC_LDG(p) __ldg(p)
+// Optimisation fence on a float4 held in registers: whatever consumes it is scheduled after this
+// point.  Used to keep the consumers of a global load behind the barrier, so that the load's
+// latency is covered by the spring phase instead of stalling it.
+#define OC_KEEP4(v) asm volatile("" : "+f"((v).x), "+f"((v).y), "+f"((v).z), "+f"((v).w))
 #else
 #define OC_LDG(p) (*(p))
+#define OC_KEEP4(v) ((void)0)
 #endif
 
 template <int TW>
@@ -124,6 +129,16 @@ OC_HD void oc_march_body(Ctx& ctx, const OcConst& c,
     const bool has_l1 = gi - 1 >= 0, has_l2 = gi - 2 >= 0, has_r1 = gi + 1 < U, has_r2 = gi + 2 < U;
     const bool dup_r = gi == U - 3, dup_l = gi == U - 1;
 
+    const float ydt = oc_rcp_bf(c.dt);   // reciprocal of dt for the branch-free velocity division
+
+    // row constants (rest lengths that depend on the row only) are fetched one iteration ahead
+    float rv1_n, rv2_n, dz2_n;
+    {
+        int r = first - OC_MARCH_LAG * (s + 1);
+        r = r < 0 ? 0 : (r >= V ? V - 1 : r);
+        rv1_n = OC_LDG(c.rv1 + r); rv2_n = OC_LDG(c.rv2 + r); dz2_n = OC_LDG(c.dz2 + r);
+    }
+
     OcPV n1, n2;                         // own column, rows c+1 and c+2
     n1.x = n1.v = n2.x = n2.v = make_f3(0.f, 0.f, 0.f);
     f3 k1 = make_f3(0.f, 0.f, 0.f), k2a = k1, k2b = k1;     // carried vertical forces (on me, from rows above)
@@ -137,6 +152,12 @@ OC_HD void oc_march_body(Ctx& ctx, const OcConst& c,
         if (doL) {
             long long o = oc_index(c, b, gi, lrow);
             la = A[o]; lq = B[o];
+        }
+        const float rv1_j = rv1_n, rv2_j = rv2_n, dz2_j = dz2_n;
+        {
+            int r = row + 1;
+            r = r < 0 ? 0 : (r >= V ? V - 1 : r);
+            rv1_n = OC_LDG(c.rv1 + r); rv2_n = OC_LDG(c.rv2 + r); dz2_n = OC_LDG(c.dz2 + r);
         }
 
         // ---- P phase: forward springs of row `row` -------------------------------------------------
@@ -154,16 +175,26 @@ OC_HD void oc_march_body(Ctx& ctx, const OcConst& c,
             const OcPV a2 = oc_ld_pv<TW>(in, row, ci + 2);
             const OcPV d1 = oc_ld_pv<TW>(in, row + 1, ci + 1);
             const OcPV d0 = oc_ld_pv<TW>(in, row + 1, ci - 1);
-            const int rc = row;                                   // 0 <= row < V here
-            const float rv1_j = OC_LDG(c.rv1 + rc), rv2_j = OC_LDG(c.rv2 + rc), dz2_j = OC_LDG(c.dz2 + rc);
-            const float rD = M::sqrt(M::add(dx2_i, dz2_j));
-            const float rA = M::sqrt(M::add(dx2_m, dz2_j));
-            gH1 = oc_spring<M>(me.x, me.v, a1.x, a1.v, rh1_i, c.nks_struct, c.kd_struct);
-            gV1 = oc_spring<M>(me.x, me.v, n1.x, n1.v, rv1_j, c.nks_struct, c.kd_struct);
-            gA  = oc_spring<M>(me.x, me.v, d0.x, d0.v, rA,    c.nks_shear,  c.kd_shear);
-            gD  = oc_spring<M>(me.x, me.v, d1.x, d1.v, rD,    c.nks_shear,  c.kd_shear);
-            gH2 = oc_spring<M>(me.x, me.v, a2.x, a2.v, rh2_i, c.nks_bend,   c.kd_bend);
-            gV2 = oc_spring<M>(me.x, me.v, n2.x, n2.v, rv2_j, c.nks_bend,   c.kd_bend);
+            bool bad = false;
+            const float rD = oc_len_bf<M>(M::add(dx2_i, dz2_j), bad);
+            const float rA = oc_len_bf<M>(M::add(dx2_m, dz2_j), bad);
+            gH1 = oc_spring_bf<M>(me.x, me.v, a1.x, a1.v, rh1_i, c.nks_struct, c.kd_struct, bad);
+            gV1 = oc_spring_bf<M>(me.x, me.v, n1.x, n1.v, rv1_j, c.nks_struct, c.kd_struct, bad);
+            gA  = oc_spring_bf<M>(me.x, me.v, d0.x, d0.v, rA,    c.nks_shear,  c.kd_shear,  bad);
+            gD  = oc_spring_bf<M>(me.x, me.v, d1.x, d1.v, rD,    c.nks_shear,  c.kd_shear,  bad);
+            gH2 = oc_spring_bf<M>(me.x, me.v, a2.x, a2.v, rh2_i, c.nks_bend,   c.kd_bend,   bad);
+            gV2 = oc_spring_bf<M>(me.x, me.v, n2.x, n2.v, rv2_j, c.nks_bend,   c.kd_bend,   bad);
+            if (M::kExact && bad) {
+                // an operand left the range of the branch-free sequences (or the neighbour does not
+                // exist and the lane holds garbage): redo this lane with the IEEE intrinsics
+                const float sD = M::sqrt(M::add(dx2_i, dz2_j)), sA = M::sqrt(M::add(dx2_m, dz2_j));
+                gH1 = oc_spring<M>(me.x, me.v, a1.x, a1.v, rh1_i, c.nks_struct, c.kd_struct);
+                gV1 = oc_spring<M>(me.x, me.v, n1.x, n1.v, rv1_j, c.nks_struct, c.kd_struct);
+                gA  = oc_spring<M>(me.x, me.v, d0.x, d0.v, sA,    c.nks_shear,  c.kd_shear);
+                gD  = oc_spring<M>(me.x, me.v, d1.x, d1.v, sD,    c.nks_shear,  c.kd_shear);
+                gH2 = oc_spring<M>(me.x, me.v, a2.x, a2.v, rh2_i, c.nks_bend,   c.kd_bend);
+                gV2 = oc_spring<M>(me.x, me.v, n2.x, n2.v, rv2_j, c.nks_bend,   c.kd_bend);
+            }
             in.FH[row & 1][0][ci] = oc_neg4(gH1);
             in.FH[row & 1][1][ci] = oc_neg4(gH2);
             in.FD[sl][0][ci] = oc_neg4(gD);
@@ -172,6 +203,7 @@ OC_HD void oc_march_body(Ctx& ctx, const OcConst& c,
         }
 
         ctx.sync();
+        OC_KEEP4(la); OC_KEEP4(lq);
 
         // ---- G phase: gather in the reference's order, integrate, collide, hand on ------------------
         const bool doG = row >= lo_s && row < hi_s;
@@ -207,7 +239,9 @@ OC_HD void oc_march_body(Ctx& ctx, const OcConst& c,
                 // new X_last is the old X (V:438) unless the collider moved the particle (V:530)
                 const f3 dn = hit ? make_f3(0.f, 0.f, 0.f)
                                   : make_f3(M::sub(xn.x, me.x.x), M::sub(xn.y, me.x.y), M::sub(xn.z, me.x.z));
-                const f3 vn = M::velocity(dn, c);
+                bool badv = false;
+                f3 vn = oc_velocity_bf<M>(dn, c, ydt, badv);
+                if (M::kExact && badv) vn = M::velocity(dn, c);
                 oc_st_pvd<TW>(rings[s + 1], row, ci, xn, vn, dn);
                 if (s == S - 2 && col_store && row >= r0 && row < r1) Dst[oc_index(c, b, gi, row)] = out;   // X(t+S-1)
             }
@@ -217,7 +251,9 @@ OC_HD void oc_march_body(Ctx& ctx, const OcConst& c,
         // ---- stage 0: publish the loaded row into its own ring --------------------------------------
         if (doL) {
             const f3 d = oc_delta<M>(la, lq);
-            const f3 v = M::velocity(d, c);
+            bool badv = false;
+            f3 v = oc_velocity_bf<M>(d, c, ydt, badv);
+            if (M::kExact && badv) v = M::velocity(d, c);
             oc_st_pvd<TW>(rings[0], lrow, ci, make_f3(la.x, la.y, la.z), v, d);
         }
     }
@@ -233,8 +269,11 @@ struct OcDevCtx {
     __device__ __forceinline__ unsigned char* smem() const { extern __shared__ __align__(16) unsigned char oc_dyn_smem[]; return oc_dyn_smem; }
 };
 
+// resident CTAs per SM the register allocation is capped for: 4 x 128 threads, 2 x 256, 1 x 512
+#define OC_MARCH_MIN_CTAS(threads) ((threads) <= 128 ? 4 : ((threads) <= 256 ? 2 : 1))
+
 template <class M, int S, int TW>
-__global__ void __launch_bounds__(S * TW)
+__global__ void __launch_bounds__(S * TW, OC_MARCH_MIN_CTAS(S * TW))
 oc_k_march(OcConst c, const float4* __restrict__ A, const float4* __restrict__ B,
            float4* __restrict__ C, float4* __restrict__ Dst, int ra, int rb, int RS, int x_halo)
 {

@@ -254,6 +254,16 @@ def test_row_bands_single_process_equal_whole_cloth(nbands, halo, k):
     whole.close()
 
 
+def test_branch_free_math_is_ieee():
+    """The MUFU+FFMA sequences used instead of sqrt.rn / rcp.rn / div.rn (no slow-path branch) give
+    the correctly rounded result on 2^30 random operands in their accepted exponent ranges."""
+    import ctypes
+    from opencloth_b200 import _abi
+    bad = ctypes.c_ulonglong(123)
+    _abi.check(_abi.load().oc_selftest_math(1 << 30, 20261017, ctypes.byref(bad)))
+    assert bad.value == 0, f"{bad.value} mismatches against the IEEE intrinsics"
+
+
 def test_launch_counter_and_timed_step():
     m = oc()
     c = m.Cloth(256, 256, substeps_per_launch=4)
