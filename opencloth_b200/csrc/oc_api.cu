@@ -575,6 +575,53 @@ __global__ void oc_k_selftest(unsigned long long per_thread, unsigned seed, floa
         float v = oc_div_bf(d, dt, ydt, OC_VEL_LO, OC_VEL_HI, bad);
         if (__float_as_uint(v) != __float_as_uint(__fdiv_rn(d, dt))) bad_count++;
         if (bad || bad2) bad_count += 1000000;      // operands were generated inside the accepted ranges
+        // packed FP32x2 forms: primitive ops and the pair sequences of the marching kernel
+        {
+            const float u0 = oc_rand_float(st, -30, 30, true), u1 = oc_rand_float(st, -30, 30, true);
+            const float w0 = oc_rand_float(st, -30, 30, true), w1 = oc_rand_float(st, -30, 30, true);
+            const float z0 = oc_rand_float(st, -30, 30, true), z1 = oc_rand_float(st, -30, 30, true);
+            const float2 pa = p_add(make_float2(u0, u1), make_float2(w0, w1));
+            const float2 pm = p_mul(make_float2(u0, u1), make_float2(w0, w1));
+            const float2 pf = p_fma(make_float2(u0, u1), p_neg(make_float2(w0, w1)), make_float2(z0, z1));
+            if (__float_as_uint(pa.x) != __float_as_uint(__fadd_rn(u0, w0)) || __float_as_uint(pa.y) != __float_as_uint(__fadd_rn(u1, w1))) bad_count += 1ull << 20;
+            if (__float_as_uint(pm.x) != __float_as_uint(__fmul_rn(u0, w0)) || __float_as_uint(pm.y) != __float_as_uint(__fmul_rn(u1, w1))) bad_count += 1ull << 24;
+            if (__float_as_uint(pf.x) != __float_as_uint(__fmaf_rn(u0, -w0, z0)) || __float_as_uint(pf.y) != __float_as_uint(__fmaf_rn(u1, -w1, z1))) bad_count += 1ull << 28;
+            bool b3 = false;
+            const float x2 = oc_rand_float(st, -94, 93, false);
+            const float2 sq = oc_sqrt2<MathExact>(make_float2(x, x2), b3);
+            if (__float_as_uint(sq.x) != __float_as_uint(__fsqrt_rn(x)) || __float_as_uint(sq.y) != __float_as_uint(__fsqrt_rn(x2))) bad_count += 1ull << 32;
+            const float2 y0 = p_rcp(sq);
+            const float2 inv = p_fma(y0, p_fma(y0, p_neg(sq), p_bc(1.0f)), y0);
+            if (__float_as_uint(inv.x) != __float_as_uint(__frcp_rn(sq.x)) || __float_as_uint(inv.y) != __float_as_uint(__frcp_rn(sq.y))) bad_count += 1ull << 36;
+            const float a3 = oc_rand_float(st, -70, 69, true);
+            const float2 aa = make_float2(a, a3);
+            const float2 q0 = p_mul(aa, inv);
+            const float2 qq = p_fma(inv, p_fma(q0, p_neg(sq), aa), q0);
+            if (a != 0.0f && __float_as_uint(qq.x) != __float_as_uint(__fdiv_rn(a, sq.x))) bad_count += 1ull << 40;
+            if (__float_as_uint(qq.y) != __float_as_uint(__fdiv_rn(a3, sq.y))) bad_count += 1ull << 40;
+        }
+        // whole spring pair on cloth-like operands against the scalar intrinsic formula
+        {
+            auto jitter = [&](float base, float amp) { return base + amp * ((float)(oc_rng(st) & 0xffff) / 65536.0f - 0.5f); };
+            const f3 mx = make_f3(jitter(1.6f, 1e-3f), jitter(4.99f, 1e-3f), jitter(0.0f, 1e-6f));
+            const f3 mv = make_f3(jitter(0.0f, 1e-4f), jitter(-0.01f, 1e-4f), jitter(0.0f, 1e-5f));
+            const f3 ax = make_f3(mx.x + jitter(0.2f, 1e-3f), mx.y + jitter(0.0f, 1e-3f), mx.z + jitter(0.2f, 1e-3f));
+            const f3 bx = make_f3(mx.x - jitter(0.2f, 1e-3f), mx.y + jitter(0.0f, 1e-3f), mx.z + jitter(0.2f, 1e-3f));
+            const f3 av = make_f3(jitter(0.0f, 1e-4f), jitter(-0.01f, 1e-4f), jitter(0.0f, 1e-5f));
+            const f3 bv = make_f3(jitter(0.0f, 1e-4f), jitter(-0.01f, 1e-4f), jitter(0.0f, 1e-5f));
+            OcPair3 qx, qv;
+            qx.x = make_float2(ax.x, bx.x); qx.y = make_float2(ax.y, bx.y); qx.z = make_float2(ax.z, bx.z);
+            qv.x = make_float2(av.x, bv.x); qv.y = make_float2(av.y, bv.y); qv.z = make_float2(av.z, bv.z);
+            const float ra = jitter(0.2828f, 1e-4f), rb = jitter(0.2828f, 1e-4f);
+            bool b4 = false;
+            const OcPair3 g = oc_spring2<MathExact>(mx, mv, qx, qv, make_float2(ra, rb), p_bc(-50.75f), p_bc(-0.25f), b4);
+            const f3 fa = oc_spring<MathExact>(mx, mv, ax, av, ra, -50.75f, -0.25f);
+            const f3 fb = oc_spring<MathExact>(mx, mv, bx, bv, rb, -50.75f, -0.25f);
+            if (!b4) {
+                if (__float_as_uint(g.x.x) != __float_as_uint(fa.x) || __float_as_uint(g.y.x) != __float_as_uint(fa.y) || __float_as_uint(g.z.x) != __float_as_uint(fa.z)) bad_count += 1ull << 44;
+                if (__float_as_uint(g.x.y) != __float_as_uint(fb.x) || __float_as_uint(g.y.y) != __float_as_uint(fb.y) || __float_as_uint(g.z.y) != __float_as_uint(fb.z)) bad_count += 1ull << 44;
+            }
+        }
     }
     if (bad_count) atomicAdd(out, bad_count);
 }

@@ -11,6 +11,7 @@
 #include <vector>
 #include <math.h>
 #include <string.h>
+#include <stdlib.h>
 
 // ellipsoid = translate(0,2,0) * rotate(45 deg about x) * scale(1,1,0.5), inverse = glm::inverse(ellipsoid)
 // (V:324-327).  The reference builds them with GLM 0.9.0.0 at start-up; these are the resulting fp32
@@ -52,6 +53,7 @@ static inline void oc_host_derive_scalars(const oc_params& p, OcConst& k)
     k.dt = p.dt;
     k.inv_dt = 1.0f / p.dt;
     k.dt_bf = (p.dt >= 0x1.0p-20f && p.dt <= 0x1.0p+20f) ? 1 : 0;
+    { const char* e = getenv("OC_DEBUG"); k.dbg = e ? atoi(e) : 0; }
     k.dt2m = (p.dt * p.dt) / p.mass;                                  // V:429
     k.damping = p.damping;
     for (int a = 0; a < 3; ++a) k.f0[a] = 0.0f + p.gravity[a] * p.mass;   // V:452, V:456
@@ -60,6 +62,7 @@ static inline void oc_host_derive_scalars(const oc_params& p, OcConst& k)
     k.nks_bend   = -p.ks_bend;   k.kd_bend   = p.kd_bend;
     for (int r = 0; r < 3; ++r)
         for (int col = 0; col < 4; ++col) k.im[r][col] = p.inv_ellipsoid[col * 4 + r];
+    for (int col = 0; col < 4; ++col) { k.imxy[col][0] = k.im[0][col]; k.imxy[col][1] = k.im[1][col]; }
     for (int a = 0; a < 3; ++a) k.center[a] = p.center[a];
     k.radius = p.radius;
     for (int a = 0; a < 3; ++a) {                                     // V:520-527

@@ -37,6 +37,11 @@ static int tw_index(int TW) { return TW == 32 ? 0 : (TW == 64 ? 1 : 2); }
 // width of the column window for a cloth of nx columns stepped S substeps per launch
 static int pick_tw(int nx, int S)
 {
+    const char* env = getenv("OC_MARCH_TW");      // development override: 32 | 64 | 128
+    if (env) {
+        int tw = atoi(env);
+        if ((tw == 32 || tw == 64 || (tw == 128 && S <= 4)) && tw - 4 * S > 0) return tw;
+    }
     if (nx <= 32) return 32;
     if (nx <= 64) return 64;
     if (S <= 4) return 128;

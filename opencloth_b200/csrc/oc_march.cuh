@@ -31,79 +31,279 @@
 #include "oc_core.cuh"
 
 #define OC_MARCH_MAX_STAGES 8
-#define OC_MARCH_LAG 4          // rows between consecutive stages
+#define OC_MARCH_LAG 4          // rows between consecutive stages (must be a multiple of OC_RING)
 #define OC_RING 4               // ring depth (power of two)
 
+// Shared memory of one stage.  Structure-of-arrays rows (2 pad columns either side) in rings:
+// a 32-bit load per component lets the two partners of a spring PAIR land in adjacent registers,
+// ready for the packed FP32x2 instructions, and consecutive lanes hit consecutive banks.
 template <int TW>
 struct OcStageSmem {
-    float4 P[OC_RING][TW + 4];      // x, y, z, vx        (2 pad columns either side)
-    float2 Q[OC_RING][TW + 4];      // vy, vz
-    float  D[OC_RING][3][TW + 4];   // X - X_last, read by the owning column only
-    float4 FH[2][2][TW + 4];        // [row&1][0] = -f(+1,0), [row&1][1] = -f(+2,0)   forces on the partner
-    float4 FD[OC_RING][2][TW + 4];  // [row&3][0] = -f(+1,+1), [row&3][1] = -f(-1,+1)
+    float  X[6][OC_RING][TW + 4];   // x, y, z, vx, vy, vz of the stage's input rows      slot = row & 3
+    float4 D[OC_RING][TW + 4];      // X - X_last (w unused), read by the owning column only
+    float  FH[6][2][TW + 4];        // f(+1,0).xyz, f(+2,0).xyz of row (row & 1): force ON the publishing
+    float  FD[6][OC_RING][TW + 4];  // f(+1,+1).xyz, f(-1,+1).xyz of row (row & 3)   particle; the partner SUBTRACTS it
 };
-
-struct OcPV { f3 x, v; };
 
 #ifdef __CUDA_ARCH__
 #define OC_LDG(p) __ldg(p)
 // Optimisation fence on a float4 held in registers: whatever consumes it is scheduled after this
-// point.  Used to keep the consumers of a global load behind the barrier, so that the load's
-// latency is covered by the spring phase instead of stalling it.
+// point, and all four registers stay allocated until here.  Used to keep the consumers of a global
+// load behind the barrier (its latency is then covered by the spring phase) and to stop ptxas from
+// recycling a register of the in-flight 128-bit load (a write-after-write wait of a full DRAM latency).
 #define OC_KEEP4(v) asm volatile("" : "+f"((v).x), "+f"((v).y), "+f"((v).z), "+f"((v).w))
 #else
 #define OC_LDG(p) (*(p))
 #define OC_KEEP4(v) ((void)0)
 #endif
 
+// position (x) and velocity (v) of two particles as pairs
+struct OcPV2 { OcPair3 x, v; };
 template <int TW>
-OC_HD OcPV oc_ld_pv(const OcStageSmem<TW>& sm, int row, int col /* padded index */)
+OC_HD OcPV2 oc_ld_pv2(const OcStageSmem<TW>& sm, int slotA, int colA, int slotB, int colB)
 {
-    float4 p = sm.P[row & (OC_RING - 1)][col];
-    float2 q = sm.Q[row & (OC_RING - 1)][col];
-    OcPV r; r.x = make_f3(p.x, p.y, p.z); r.v = make_f3(p.w, q.x, q.y);
+    OcPV2 r;
+    r.x.x = make_float2(sm.X[0][slotA][colA], sm.X[0][slotB][colB]);
+    r.x.y = make_float2(sm.X[1][slotA][colA], sm.X[1][slotB][colB]);
+    r.x.z = make_float2(sm.X[2][slotA][colA], sm.X[2][slotB][colB]);
+    r.v.x = make_float2(sm.X[3][slotA][colA], sm.X[3][slotB][colB]);
+    r.v.y = make_float2(sm.X[4][slotA][colA], sm.X[4][slotB][colB]);
+    r.v.z = make_float2(sm.X[5][slotA][colA], sm.X[5][slotB][colB]);
     return r;
 }
 template <int TW>
-OC_HD void oc_st_pvd(OcStageSmem<TW>& sm, int row, int col, f3 x, f3 v, f3 d)
+OC_HD void oc_st_pvd(OcStageSmem<TW>& sm, int slot, int col, f3 x, f3 v, f3 d, float pad)
 {
-    const int s = row & (OC_RING - 1);
-    sm.P[s][col] = make_float4(x.x, x.y, x.z, v.x);
-    sm.Q[s][col] = make_float2(v.y, v.z);
-    sm.D[s][0][col] = d.x; sm.D[s][1][col] = d.y; sm.D[s][2][col] = d.z;
-}
-OC_HD float4 oc_neg4(f3 f) { return make_float4(-f.x, -f.y, -f.z, 0.0f); }
-template <class M> OC_HD void oc_acc(f3& F, f3 g, bool on)
-{
-    if (on) { F.x = M::add(F.x, g.x); F.y = M::add(F.y, g.y); F.z = M::add(F.z, g.z); }
-}
-template <class M> OC_HD void oc_acc4(f3& F, float4 g, bool on)
-{
-    if (on) { F.x = M::add(F.x, g.x); F.y = M::add(F.y, g.y); F.z = M::add(F.z, g.z); }
+    sm.X[0][slot][col] = x.x; sm.X[1][slot][col] = x.y; sm.X[2][slot][col] = x.z;
+    sm.X[3][slot][col] = v.x; sm.X[4][slot][col] = v.y; sm.X[5][slot][col] = v.z;
+    sm.D[slot][col] = make_float4(d.x, d.y, d.z, pad);
 }
 
-// Ctx: tid(), bx(), by(), bz(), sync(), smem()  (see DevCtx below and tests/emu/oc_emu.cu)
+// Force accumulator as (xy pair, z).  a - b is a + (-b) exactly, so the partner of a spring
+// subtracts the force its publisher computed for itself (f(b,a) == -f(a,b), oc_core.cuh).
+struct OcF { float2 xy; float z; };
+template <class M> OC_HD void oc_add(OcF& F, float x, float y, float z, bool on)
+{
+    if (on) { F.xy.x = M::add(F.xy.x, x); F.xy.y = M::add(F.xy.y, y); F.z = M::add(F.z, z); }
+}
+template <class M> OC_HD void oc_sub(OcF& F, float x, float y, float z, bool on)
+{
+    if (on) { F.xy.x = M::sub(F.xy.x, x); F.xy.y = M::sub(F.xy.y, y); F.z = M::sub(F.z, z); }
+}
+// received force: (x, y) arrive in adjacent registers straight from shared memory -> one packed op
+template <class M> OC_HD void oc_sub_pk(OcF& F, float2 xy, float z, bool on)
+{
+    if (on) { F.xy = p_sub(F.xy, xy); F.z = M::sub(F.z, z); }
+}
+
+// Cold path of exact mode: an operand of this lane left the range of the branch-free sequences
+// (or a neighbour does not exist and the lane holds garbage).  Re-reads the inputs from shared memory
+// and evaluates the six springs with the IEEE intrinsics.  Not inlined: keeps the hot loop small and
+// its registers free.
+template <class M, int TW>
+#ifdef __CUDA_ARCH__
+__device__ __noinline__
+#else
+inline
+#endif
+void oc_march_redo(const OcStageSmem<TW>& in, int sl, int s1, int s2, int ci, const OcConst& c,
+                   float rh1_i, float rh2_i, float dx2_i, float dx2_m, float rv1_j, float rv2_j, float dz2_j,
+                   OcPair3& gH, OcPair3& gV, OcPair3& gS)
+{
+#define OC_LDX(slot, col) make_f3(in.X[0][slot][col], in.X[1][slot][col], in.X[2][slot][col])
+#define OC_LDV(slot, col) make_f3(in.X[3][slot][col], in.X[4][slot][col], in.X[5][slot][col])
+    const f3 mx = OC_LDX(sl, ci), mv = OC_LDV(sl, ci);
+    const float sD = M::sqrt(M::add(dx2_i, dz2_j)), sA = M::sqrt(M::add(dx2_m, dz2_j));
+    const f3 h1 = oc_spring<M>(mx, mv, OC_LDX(sl, ci + 1), OC_LDV(sl, ci + 1), rh1_i, c.nks_struct, c.kd_struct);
+    const f3 h2 = oc_spring<M>(mx, mv, OC_LDX(sl, ci + 2), OC_LDV(sl, ci + 2), rh2_i, c.nks_bend,   c.kd_bend);
+    const f3 v1 = oc_spring<M>(mx, mv, OC_LDX(s1, ci),     OC_LDV(s1, ci),     rv1_j, c.nks_struct, c.kd_struct);
+    const f3 v2 = oc_spring<M>(mx, mv, OC_LDX(s2, ci),     OC_LDV(s2, ci),     rv2_j, c.nks_bend,   c.kd_bend);
+    const f3 dd = oc_spring<M>(mx, mv, OC_LDX(s1, ci + 1), OC_LDV(s1, ci + 1), sD,    c.nks_shear,  c.kd_shear);
+    const f3 da = oc_spring<M>(mx, mv, OC_LDX(s1, ci - 1), OC_LDV(s1, ci - 1), sA,    c.nks_shear,  c.kd_shear);
+#undef OC_LDX
+#undef OC_LDV
+    gH.x = make_float2(h1.x, h2.x); gH.y = make_float2(h1.y, h2.y); gH.z = make_float2(h1.z, h2.z);
+    gV.x = make_float2(v1.x, v2.x); gV.y = make_float2(v1.y, v2.y); gV.z = make_float2(v1.z, v2.z);
+    gS.x = make_float2(dd.x, da.x); gS.y = make_float2(dd.y, da.y); gS.z = make_float2(dd.z, da.z);
+}
+
+// All per-thread state of the marching loop.  iter<kSteady, kSlot>() is one row iteration; the
+// steady variant is used when this stage's row is interior (rows row-2 .. row+2 exist, no duplicated
+// vertical bend spring, not the pinned row) and all three activities (load, spring phase, gather
+// phase) are on: it carries no row predicates and no dead-path initialisations.
+template <class M, int S, int TW, class Ctx>
+struct OcMarch {
+    typedef OcStageSmem<TW> Smem;
+    Ctx& ctx;
+    const OcConst& c;
+    const float4* __restrict__ A; const float4* __restrict__ B;
+    float4* __restrict__ C; float4* __restrict__ Dst;
+    Smem* rings;
+    int s, ci, gi, U, V, r0, r1;
+    int lo_s, hi_s, plo_s, in_lo, in_hi, first, row0;
+    bool col_ok, col_store;
+    bool has_l1, has_l2, has_r1, has_r2, dup_r, dup_l;
+    float rh1_i, rh2_i, dx2_i, dx2_m, ydt;
+    float rv1_n, rv2_n, dz2_n;            // row constants of the NEXT iteration's row
+    long long goff;                       // element offset of (cloth, gi, row 0) in a position buffer
+    f3 k1, k2a, k2b;                      // vertical forces published by rows row-1 (0,+1), row-1 and row-2 (0,+2)
+
+    OC_HD OcMarch(Ctx& ctx_, const OcConst& c_) : ctx(ctx_), c(c_) {}
+
+    // kSlot = row & 3 when it is known at compile time (the steady loop is unrolled by 4 so that every
+    // shared-memory address is the thread's base plus an immediate), -1 otherwise
+    template <bool kSteady, int kSlot>
+    OC_HD void iter(int it)
+    {
+        Smem& in = rings[s];
+        const int row = row0 + it;                                // row this stage works on
+        const int lrow = first + it;                              // row stage 0 loads
+        // ---- stage 0: issue the global loads of row lrow early -------------------------------------
+        float4 la, lq;
+        const bool doL = (s == 0) && col_ok && (kSteady || (lrow >= in_lo && lrow < in_hi));
+        if (doL) {
+            const long long o = goff + (long long)lrow * U;
+            la = A[o]; lq = B[o];
+        }
+        const float rv1_j = rv1_n, rv2_j = rv2_n, dz2_j = dz2_n;
+        {
+            int r = row + 1;
+            if (!kSteady) r = r < 0 ? 0 : (r >= V ? V - 1 : r);
+            rv1_n = OC_LDG(c.rv1 + r); rv2_n = OC_LDG(c.rv2 + r); dz2_n = OC_LDG(c.dz2 + r);
+        }
+        const int sl = kSlot >= 0 ? kSlot : (row & (OC_RING - 1));           // slot of row
+        const int s1 = (sl + 1) & (OC_RING - 1);                             // row + 1
+        const int s2 = (sl + 2) & (OC_RING - 1);                             // row + 2
+        const int s3 = (sl + 3) & (OC_RING - 1);                             // row - 1
+
+        // ---- P phase: forward springs of row `row`, as three pairs ----------------------------------
+        const bool doP = kSteady || (row >= plo_s && row < hi_s);
+        OcPair3 gH, gV, gS;          // (f(+1,0), f(+2,0)), (f(0,+1), f(0,+2)), (f(+1,+1), f(-1,+1))
+        f3 mx, mv, dme;
+        if (doP) {
+            mx = make_f3(in.X[0][sl][ci], in.X[1][sl][ci], in.X[2][sl][ci]);
+            mv = make_f3(in.X[3][sl][ci], in.X[4][sl][ci], in.X[5][sl][ci]);
+            const float4 d4 = in.D[sl][ci];
+            dme = make_f3(d4.x, d4.y, d4.z);
+            const OcPV2 nH = oc_ld_pv2<TW>(in, sl, ci + 1, sl, ci + 2);      // (i+1, j), (i+2, j)
+            const OcPV2 nV = oc_ld_pv2<TW>(in, s1, ci,     s2, ci);          // (i, j+1), (i, j+2)
+            const OcPV2 nS = oc_ld_pv2<TW>(in, s1, ci + 1, s1, ci - 1);      // (i+1, j+1), (i-1, j+1)
+            bool bad = false;
+            float2 rS = oc_sqrt2<M>(p_add(make_float2(dx2_i, dx2_m), p_bc(dz2_j)), bad);     // shear rest lengths
+            float2 rH = make_float2(rh1_i, rh2_i), rV = make_float2(rv1_j, rv2_j);
+            const float2 nksHV = make_float2(c.nks_struct, c.nks_bend), kdHV = make_float2(c.kd_struct, c.kd_bend);
+            const float2 nksS = p_bc(c.nks_shear), kdS = p_bc(c.kd_shear);
+            if (!M::kExact) { rH = p_mul(rH, nksHV); rV = p_mul(rV, nksHV); rS = p_mul(rS, nksS); }
+            gH = oc_spring2<M>(mx, mv, nH.x, nH.v, rH, nksHV, kdHV, bad);
+            gV = oc_spring2<M>(mx, mv, nV.x, nV.v, rV, nksHV, kdHV, bad);
+            gS = oc_spring2<M>(mx, mv, nS.x, nS.v, rS, nksS,  kdS,  bad);
+            if (c.dbg & 1) bad = true;
+            if (c.dbg & 2) bad = false;
+            if (M::kExact && bad) oc_march_redo<M, TW>(in, sl, s1, s2, ci, c, rh1_i, rh2_i, dx2_i, dx2_m, rv1_j, rv2_j, dz2_j, gH, gV, gS);
+            in.FH[0][sl & 1][ci] = gH.x.x; in.FH[1][sl & 1][ci] = gH.y.x; in.FH[2][sl & 1][ci] = gH.z.x;
+            in.FH[3][sl & 1][ci] = gH.x.y; in.FH[4][sl & 1][ci] = gH.y.y; in.FH[5][sl & 1][ci] = gH.z.y;
+            in.FD[0][sl][ci] = gS.x.x; in.FD[1][sl][ci] = gS.y.x; in.FD[2][sl][ci] = gS.z.x;
+            in.FD[3][sl][ci] = gS.x.y; in.FD[4][sl][ci] = gS.y.y; in.FD[5][sl][ci] = gS.z.y;
+        }
+
+        ctx.sync();
+        if (doL) { OC_KEEP4(la); OC_KEEP4(lq); }
+
+        // ---- G phase: gather in the reference's order, integrate, collide, hand on ------------------
+        const bool doG = kSteady || (row >= lo_s && row < hi_s);
+        if (doG) {
+            const bool pinned = !kSteady && oc_pinned(c, gi, row);
+            // F = 0 + gravity*mass (unless pinned) + DEFAULT_DAMPING*V     V:451-459
+            OcF F;
+            F.xy = pinned ? p_bc(0.0f) : make_float2(c.f0[0], c.f0[1]);
+            F.z  = pinned ? 0.0f : c.f0[2];
+            F.xy = p_add(F.xy, p_mulx(p_bc(c.damping), make_float2(mv.x, mv.y)));
+            F.z  = M::add(F.z, M::mul(c.damping, mv.z));
+            if (!pinned) {
+                const bool up1 = kSteady || row - 1 >= 0, up2 = kSteady || row - 2 >= 0;
+                const bool dn1 = kSteady || row + 1 < V,  dn2 = kSteady || row + 2 < V;
+                const int h = sl & 1;
+                oc_sub_pk<M>(F, make_float2(in.FH[0][h][ci - 1], in.FH[1][h][ci - 1]), in.FH[2][h][ci - 1], has_l1);   // 1  (i-1, j)   structural
+                oc_add<M>(F, gH.x.x, gH.y.x, gH.z.x, has_r1);                                                        // 2  (i+1, j)
+                oc_sub<M>(F, k1.x, k1.y, k1.z, up1);                                                                 // 3  (i, j-1)
+                oc_add<M>(F, gV.x.x, gV.y.x, gV.z.x, dn1);                                                           // 4  (i, j+1)
+                oc_sub_pk<M>(F, make_float2(in.FD[0][s3][ci - 1], in.FD[1][s3][ci - 1]), in.FD[2][s3][ci - 1], has_l1 && up1);   // 5  (i-1, j-1) shear
+                oc_sub_pk<M>(F, make_float2(in.FD[3][s3][ci + 1], in.FD[4][s3][ci + 1]), in.FD[5][s3][ci + 1], has_r1 && up1);   // 6  (i+1, j-1)
+                oc_add<M>(F, gS.x.y, gS.y.y, gS.z.y, has_l1 && dn1);                                                 // 7  (i-1, j+1)
+                oc_add<M>(F, gS.x.x, gS.y.x, gS.z.x, has_r1 && dn1);                                                 // 8  (i+1, j+1)
+                const float2 h2xy = make_float2(in.FH[3][h][ci - 2], in.FH[4][h][ci - 2]);
+                const float h2z = in.FH[5][h][ci - 2];
+                oc_sub_pk<M>(F, h2xy, h2z, has_l2);                                                                  // 9  (i-2, j)   bend
+                oc_add<M>(F, gH.x.y, gH.y.y, gH.z.y, has_r2);                                                        // 10 (i+2, j)
+                oc_add<M>(F, gH.x.y, gH.y.y, gH.z.y, dup_r);                                                         // 11 duplicate of the row's last bend spring (V:313)
+                oc_sub_pk<M>(F, h2xy, h2z, dup_l);
+                oc_sub<M>(F, k2b.x, k2b.y, k2b.z, up2);                                                              // 12 (i, j-2)
+                oc_add<M>(F, gV.x.y, gV.y.y, gV.z.y, dn2);                                                           // 13 (i, j+2)
+                if (!kSteady) {
+                    oc_add<M>(F, gV.x.y, gV.y.y, gV.z.y, row == V - 3);                                              // 14 duplicate of the column's last bend spring (V:319)
+                    oc_sub<M>(F, k2b.x, k2b.y, k2b.z, row == V - 1);
+                }
+            }
+            bool hit;
+            float2 nxy; float nz;
+            oc_integrate_collide2<M>(c, make_float2(mx.x, mx.y), mx.z, make_float2(dme.x, dme.y), dme.z, F.xy, F.z, nxy, nz, &hit);
+            const float4 out = make_float4(nxy.x, nxy.y, nz, oc_u2f(hit ? OC_W_HIT : OC_W_PLAIN));
+            if (s == S - 1) {
+                if (col_store) C[goff + (long long)row * U] = out;                // X(t+S)
+            } else {
+                // new X_last is the old X (V:438) unless the collider moved the particle (V:530)
+                float2 dnxy = p_sub(nxy, make_float2(mx.x, mx.y));
+                float dnz = M::sub(nz, mx.z);
+                if (hit) { dnxy = p_bc(0.0f); dnz = 0.0f; }
+                bool badv = false;
+                float2 vxy; float vz;
+                oc_velocity2<M>(dnxy, dnz, c, ydt, badv, vxy, vz);
+                if (M::kExact && badv) { const f3 v = M::velocity(make_f3(dnxy.x, dnxy.y, dnz), c); vxy = make_float2(v.x, v.y); vz = v.z; }
+                oc_st_pvd<TW>(rings[s + 1], sl, ci, make_f3(nxy.x, nxy.y, nz), make_f3(vxy.x, vxy.y, vz), make_f3(dnxy.x, dnxy.y, dnz), 0.0f);
+                if (s == S - 2 && col_store && row >= r0 && row < r1) Dst[goff + (long long)row * U] = out;   // X(t+S-1)
+            }
+        }
+        if (doP) {
+            k2b = k2a;
+            k2a = make_f3(gV.x.y, gV.y.y, gV.z.y);
+            k1  = make_f3(gV.x.x, gV.y.x, gV.z.x);
+        }
+
+        // ---- stage 0: publish the loaded row into its own ring --------------------------------------
+        if (doL) {
+            float2 dxy = p_sub(make_float2(la.x, la.y), make_float2(lq.x, lq.y));
+            float dz = M::sub(la.z, lq.z);
+            if (oc_hit(la.w)) { dxy = p_bc(0.0f); dz = 0.0f; }                   // X_last == X (V:530)
+            bool badv = false;
+            float2 vxy; float vz;
+            oc_velocity2<M>(dxy, dz, c, ydt, badv, vxy, vz);
+            if (M::kExact && badv) { const f3 v = M::velocity(make_f3(dxy.x, dxy.y, dz), c); vxy = make_float2(v.x, v.y); vz = v.z; }
+            oc_st_pvd<TW>(rings[0], sl, ci, make_f3(la.x, la.y, la.z), make_f3(vxy.x, vxy.y, vz), make_f3(dxy.x, dxy.y, dz), lq.w);   // lrow = row + 4: same slot
+        }
+    }
+};
+
+// Ctx: tid(), bx(), by(), bz(), sync(), smem()  (see OcDevCtx below and tests/emu/oc_emu.cu)
 template <class M, int S, int TW, class Ctx>
 OC_HD void oc_march_body(Ctx& ctx, const OcConst& c,
                          const float4* __restrict__ A, const float4* __restrict__ B,
                          float4* __restrict__ C, float4* __restrict__ Dst,
                          int ra, int rb, int RS, int x_halo)
 {
-    typedef OcStageSmem<TW> Smem;
-    Smem* rings = reinterpret_cast<Smem*>(ctx.smem());
+    OcMarch<M, S, TW, Ctx> m(ctx, c);
+    m.A = A; m.B = B; m.C = C; m.Dst = Dst;
+    m.rings = reinterpret_cast<OcStageSmem<TW>*>(ctx.smem());
     const int tid = ctx.tid();
     const int s = tid / TW;              // stage (substep s+1 of this launch)
     const int i = tid - s * TW;          // column lane
-    const int ci = i + 2;                // padded smem column
     const int U = c.U, V = c.V;
     // x_halo = 2*S columns either side are recomputed by the neighbouring strips; 0 when one strip
     // spans the whole cloth width (both strip edges are cloth edges: nothing to recompute)
     const int W_out = TW - 2 * x_halo;
-    const int cx0 = ctx.bx() * W_out - x_halo;
-    const int gi = cx0 + i;              // global column
-    const int b = ctx.bz();
+    const int gi = ctx.bx() * W_out - x_halo + i;      // global column
     const int r0 = ra + ctx.by() * RS;
     const int r1 = (r0 + RS < rb) ? r0 + RS : rb;
+    m.s = s; m.ci = i + 2; m.gi = gi; m.U = U; m.V = V; m.r0 = r0; m.r1 = r1;
 
     // rows this stage produces, rows it must run the spring phase on, rows it needs as input
     int lo_s = r0 - 2 * (S - 1 - s); if (lo_s < 0) lo_s = 0;
@@ -115,147 +315,53 @@ OC_HD void oc_march_body(Ctx& ctx, const OcConst& c,
     int in_hi = hi_0 + 2; if (in_hi > V) in_hi = V;
     const int first = lo_0 - 2;
     const int n_it = r1 - first + OC_MARCH_LAG * S;
+    const int row0 = first - OC_MARCH_LAG * (s + 1);
+    m.lo_s = lo_s; m.hi_s = hi_s; m.plo_s = plo_s; m.in_lo = in_lo; m.in_hi = in_hi; m.first = first; m.row0 = row0;
 
-    Smem& in = rings[s];
-    const bool col_ok = gi >= 0 && gi < U;
-    // columns this CTA stores (valid after S substeps)
-    const bool col_store = col_ok && i >= x_halo && i < TW - x_halo;
-
-    // per-column constants
+    m.col_ok = gi >= 0 && gi < U;
+    m.col_store = m.col_ok && i >= x_halo && i < TW - x_halo;      // columns valid after S substeps
     const int gic = gi < 0 ? 0 : (gi >= U ? U - 1 : gi);
     const int gim = gic > 0 ? gic - 1 : 0;
-    const float rh1_i = OC_LDG(c.rh1 + gic), rh2_i = OC_LDG(c.rh2 + gic);
-    const float dx2_i = OC_LDG(c.dx2 + gic), dx2_m = OC_LDG(c.dx2 + gim);
-    const bool has_l1 = gi - 1 >= 0, has_l2 = gi - 2 >= 0, has_r1 = gi + 1 < U, has_r2 = gi + 2 < U;
-    const bool dup_r = gi == U - 3, dup_l = gi == U - 1;
-
-    const float ydt = oc_rcp_bf(c.dt);   // reciprocal of dt for the branch-free velocity division
-
-    // row constants (rest lengths that depend on the row only) are fetched one iteration ahead
-    float rv1_n, rv2_n, dz2_n;
+    m.rh1_i = OC_LDG(c.rh1 + gic); m.rh2_i = OC_LDG(c.rh2 + gic);
+    m.dx2_i = OC_LDG(c.dx2 + gic); m.dx2_m = OC_LDG(c.dx2 + gim);
+    m.has_l1 = gi - 1 >= 0; m.has_l2 = gi - 2 >= 0; m.has_r1 = gi + 1 < U; m.has_r2 = gi + 2 < U;
+    m.dup_r = gi == U - 3; m.dup_l = gi == U - 1;
+    m.ydt = oc_rcp_bf(c.dt);             // reciprocal of dt for the branch-free velocity division
+    m.goff = (long long)ctx.bz() * c.cloth_stride - (long long)c.row_lo * U + gic;
     {
-        int r = first - OC_MARCH_LAG * (s + 1);
-        r = r < 0 ? 0 : (r >= V ? V - 1 : r);
-        rv1_n = OC_LDG(c.rv1 + r); rv2_n = OC_LDG(c.rv2 + r); dz2_n = OC_LDG(c.dz2 + r);
+        int r = row0 < 0 ? 0 : (row0 >= V ? V - 1 : row0);
+        m.rv1_n = OC_LDG(c.rv1 + r); m.rv2_n = OC_LDG(c.rv2 + r); m.dz2_n = OC_LDG(c.dz2 + r);
     }
+    m.k1 = m.k2a = m.k2b = make_f3(0.f, 0.f, 0.f);
 
-    OcPV n1, n2;                         // own column, rows c+1 and c+2
-    n1.x = n1.v = n2.x = n2.v = make_f3(0.f, 0.f, 0.f);
-    f3 k1 = make_f3(0.f, 0.f, 0.f), k2a = k1, k2b = k1;     // carried vertical forces (on me, from rows above)
+    // Steady iterations of this stage: its row is interior and inside the rows it produces, the
+    // springs of the two rows above have been evaluated, and (stage 0) the row to load exists.
+    //   row >= max(lo_s, plo_s + 1, 2)   row < min(hi_s, V - 3)   lrow = row + 4(s+1) < in_hi
+    int st_lo = lo_s > plo_s + 1 ? lo_s : plo_s + 1; if (st_lo < 2) st_lo = 2;
+    int st_hi = hi_s < V - 3 ? hi_s : V - 3;
+    if (s == 0 && st_hi > in_hi - OC_MARCH_LAG) st_hi = in_hi - OC_MARCH_LAG;
+    int it_lo = st_lo - row0, it_hi = st_hi - row0;            // steady for it in [it_lo, it_hi)
+    if (it_lo < 0) it_lo = 0;
+    if (it_hi > n_it) it_hi = n_it;
+    if (it_hi <= it_lo) it_lo = it_hi = n_it;                  // no steady range
 
-    for (int it = 0; it < n_it; ++it) {
-        const int row = first - OC_MARCH_LAG * (s + 1) + it;      // row this stage works on
-        const int lrow = first + it;                              // row stage 0 loads
-        // ---- stage 0: issue the global loads of row lrow early -------------------------------------
-        float4 la = make_float4(0.f, 0.f, 0.f, 0.f), lq = la;
-        const bool doL = (s == 0) && lrow >= in_lo && lrow < in_hi && col_ok;
-        if (doL) {
-            long long o = oc_index(c, b, gi, lrow);
-            la = A[o]; lq = B[o];
-        }
-        const float rv1_j = rv1_n, rv2_j = rv2_n, dz2_j = dz2_n;
-        {
-            int r = row + 1;
-            r = r < 0 ? 0 : (r >= V ? V - 1 : r);
-            rv1_n = OC_LDG(c.rv1 + r); rv2_n = OC_LDG(c.rv2 + r); dz2_n = OC_LDG(c.dz2 + r);
-        }
+    // the steady loop is unrolled by 4 and starts on a row with row & 3 == 0
+    while (it_lo < it_hi && ((row0 + it_lo) & (OC_RING - 1)) != 0) ++it_lo;
+    it_hi = it_lo + ((it_hi - it_lo) & ~(OC_RING - 1));
+    if (it_hi <= it_lo) it_lo = it_hi = n_it;
 
-        // ---- P phase: forward springs of row `row` -------------------------------------------------
-        const bool doP = row >= plo_s && row < hi_s;
-        f3 gH1, gH2, gV1, gV2, gD, gA, dme, F0;
-        OcPV me;
-        gH1 = gH2 = gV1 = gV2 = gD = gA = dme = F0 = make_f3(0.f, 0.f, 0.f);
-        me.x = me.v = make_f3(0.f, 0.f, 0.f);
-        if (doP) {
-            if (row == plo_s) { n1 = oc_ld_pv<TW>(in, row, ci); n2 = oc_ld_pv<TW>(in, row + 1, ci); }
-            me = n1; n1 = n2; n2 = oc_ld_pv<TW>(in, row + 2, ci);
-            const int sl = row & (OC_RING - 1);
-            dme = make_f3(in.D[sl][0][ci], in.D[sl][1][ci], in.D[sl][2][ci]);
-            const OcPV a1 = oc_ld_pv<TW>(in, row, ci + 1);
-            const OcPV a2 = oc_ld_pv<TW>(in, row, ci + 2);
-            const OcPV d1 = oc_ld_pv<TW>(in, row + 1, ci + 1);
-            const OcPV d0 = oc_ld_pv<TW>(in, row + 1, ci - 1);
-            bool bad = false;
-            const float rD = oc_len_bf<M>(M::add(dx2_i, dz2_j), bad);
-            const float rA = oc_len_bf<M>(M::add(dx2_m, dz2_j), bad);
-            gH1 = oc_spring_bf<M>(me.x, me.v, a1.x, a1.v, rh1_i, c.nks_struct, c.kd_struct, bad);
-            gV1 = oc_spring_bf<M>(me.x, me.v, n1.x, n1.v, rv1_j, c.nks_struct, c.kd_struct, bad);
-            gA  = oc_spring_bf<M>(me.x, me.v, d0.x, d0.v, rA,    c.nks_shear,  c.kd_shear,  bad);
-            gD  = oc_spring_bf<M>(me.x, me.v, d1.x, d1.v, rD,    c.nks_shear,  c.kd_shear,  bad);
-            gH2 = oc_spring_bf<M>(me.x, me.v, a2.x, a2.v, rh2_i, c.nks_bend,   c.kd_bend,   bad);
-            gV2 = oc_spring_bf<M>(me.x, me.v, n2.x, n2.v, rv2_j, c.nks_bend,   c.kd_bend,   bad);
-            if (M::kExact && bad) {
-                // an operand left the range of the branch-free sequences (or the neighbour does not
-                // exist and the lane holds garbage): redo this lane with the IEEE intrinsics
-                const float sD = M::sqrt(M::add(dx2_i, dz2_j)), sA = M::sqrt(M::add(dx2_m, dz2_j));
-                gH1 = oc_spring<M>(me.x, me.v, a1.x, a1.v, rh1_i, c.nks_struct, c.kd_struct);
-                gV1 = oc_spring<M>(me.x, me.v, n1.x, n1.v, rv1_j, c.nks_struct, c.kd_struct);
-                gA  = oc_spring<M>(me.x, me.v, d0.x, d0.v, sA,    c.nks_shear,  c.kd_shear);
-                gD  = oc_spring<M>(me.x, me.v, d1.x, d1.v, sD,    c.nks_shear,  c.kd_shear);
-                gH2 = oc_spring<M>(me.x, me.v, a2.x, a2.v, rh2_i, c.nks_bend,   c.kd_bend);
-                gV2 = oc_spring<M>(me.x, me.v, n2.x, n2.v, rv2_j, c.nks_bend,   c.kd_bend);
+    // generic iterations up to the steady range, the steady loop, generic iterations to the end
+    int it = 0;
+    for (int phase = 0; phase < 2; ++phase) {
+        const int end = phase == 0 ? it_lo : n_it;
+        for (; it < end; ++it) m.template iter<false, -1>(it);
+        if (phase == 0)
+            for (; it < it_hi; it += 4) {
+                m.template iter<true, 0>(it);
+                m.template iter<true, 1>(it + 1);
+                m.template iter<true, 2>(it + 2);
+                m.template iter<true, 3>(it + 3);
             }
-            in.FH[row & 1][0][ci] = oc_neg4(gH1);
-            in.FH[row & 1][1][ci] = oc_neg4(gH2);
-            in.FD[sl][0][ci] = oc_neg4(gD);
-            in.FD[sl][1][ci] = oc_neg4(gA);
-            F0 = oc_base_force<M>(c, me.v, oc_pinned(c, gi, row));
-        }
-
-        ctx.sync();
-        OC_KEEP4(la); OC_KEEP4(lq);
-
-        // ---- G phase: gather in the reference's order, integrate, collide, hand on ------------------
-        const bool doG = row >= lo_s && row < hi_s;
-        if (doG) {
-            f3 F = F0;
-            if (!oc_pinned(c, gi, row)) {
-                const bool up1 = row - 1 >= 0, up2 = row - 2 >= 0, dn1 = row + 1 < V, dn2 = row + 2 < V;
-                const int su = (row - 1) & (OC_RING - 1);
-                oc_acc4<M>(F, in.FH[row & 1][0][ci - 1], has_l1);                 // 1  (i-1, j)   structural
-                oc_acc<M>(F, gH1, has_r1);                                        // 2  (i+1, j)
-                oc_acc<M>(F, k1, up1);                                            // 3  (i, j-1)
-                oc_acc<M>(F, gV1, dn1);                                           // 4  (i, j+1)
-                oc_acc4<M>(F, in.FD[su][0][ci - 1], has_l1 && up1);               // 5  (i-1, j-1) shear
-                oc_acc4<M>(F, in.FD[su][1][ci + 1], has_r1 && up1);               // 6  (i+1, j-1)
-                oc_acc<M>(F, gA, has_l1 && dn1);                                  // 7  (i-1, j+1)
-                oc_acc<M>(F, gD, has_r1 && dn1);                                  // 8  (i+1, j+1)
-                const float4 hl2 = in.FH[row & 1][1][ci - 2];
-                oc_acc4<M>(F, hl2, has_l2);                                       // 9  (i-2, j)   bend
-                oc_acc<M>(F, gH2, has_r2);                                        // 10 (i+2, j)
-                oc_acc<M>(F, gH2, dup_r);                                         // 11 duplicate of the row's last bend spring (V:313)
-                oc_acc4<M>(F, hl2, dup_l);
-                oc_acc<M>(F, k2b, up2);                                           // 12 (i, j-2)
-                oc_acc<M>(F, gV2, dn2);                                           // 13 (i, j+2)
-                oc_acc<M>(F, gV2, row == V - 3);                                  // 14 duplicate of the column's last bend spring (V:319)
-                oc_acc<M>(F, k2b, row == V - 1);
-            }
-            bool hit;
-            const f3 xn = oc_integrate_collide<M>(c, me.x, dme, F, &hit);
-            const float4 out = make_float4(xn.x, xn.y, xn.z, oc_u2f(hit ? OC_W_HIT : OC_W_PLAIN));
-            if (s == S - 1) {
-                if (col_store) C[oc_index(c, b, gi, row)] = out;                  // X(t+S)
-            } else {
-                // new X_last is the old X (V:438) unless the collider moved the particle (V:530)
-                const f3 dn = hit ? make_f3(0.f, 0.f, 0.f)
-                                  : make_f3(M::sub(xn.x, me.x.x), M::sub(xn.y, me.x.y), M::sub(xn.z, me.x.z));
-                bool badv = false;
-                f3 vn = oc_velocity_bf<M>(dn, c, ydt, badv);
-                if (M::kExact && badv) vn = M::velocity(dn, c);
-                oc_st_pvd<TW>(rings[s + 1], row, ci, xn, vn, dn);
-                if (s == S - 2 && col_store && row >= r0 && row < r1) Dst[oc_index(c, b, gi, row)] = out;   // X(t+S-1)
-            }
-        }
-        if (doP) { k2b = k2a; k2a = make_f3(-gV2.x, -gV2.y, -gV2.z); k1 = make_f3(-gV1.x, -gV1.y, -gV1.z); }
-
-        // ---- stage 0: publish the loaded row into its own ring --------------------------------------
-        if (doL) {
-            const f3 d = oc_delta<M>(la, lq);
-            bool badv = false;
-            f3 v = oc_velocity_bf<M>(d, c, ydt, badv);
-            if (M::kExact && badv) v = M::velocity(d, c);
-            oc_st_pvd<TW>(rings[0], lrow, ci, make_f3(la.x, la.y, la.z), v, d);
-        }
     }
 }
 
