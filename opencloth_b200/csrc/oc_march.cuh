@@ -159,11 +159,18 @@ struct OcMarch {
         const int row = row0 + it;                                // row this stage works on
         const int lrow = first + it;                              // row stage 0 loads
         // ---- stage 0: issue the global loads of row lrow early -------------------------------------
+        // (columns of the window that lie outside the cloth publish a benign far-away particle at rest, so
+        // that the lanes next to them stay inside the operand range of the branch-free sequences)
         float4 la, lq;
-        const bool doL = (s == 0) && col_ok && (kSteady || (lrow >= in_lo && lrow < in_hi));
+        const bool doL = (s == 0) && (kSteady || (lrow >= in_lo && lrow < in_hi));
         if (doL) {
-            const long long o = goff + (long long)lrow * U;
-            la = A[o]; lq = B[o];
+            if (col_ok) {
+                const long long o = goff + (long long)lrow * U;
+                la = A[o]; lq = B[o];
+            } else {
+                // distinct per column and row: the springs between two such particles must not be degenerate
+                la = lq = make_float4(1.0e3f + 8.0f * (float)ci, 1.0e3f, 1.0e3f + 8.0f * (float)(lrow & 63), oc_u2f(OC_W_PLAIN));
+            }
         }
         const float rv1_j = rv1_n, rv2_j = rv2_n, dz2_j = dz2_n;
         {
@@ -333,6 +340,19 @@ OC_HD void oc_march_body(Ctx& ctx, const OcConst& c,
         m.rv1_n = OC_LDG(c.rv1 + r); m.rv2_n = OC_LDG(c.rv2 + r); m.dz2_n = OC_LDG(c.dz2 + r);
     }
     m.k1 = m.k2a = m.k2b = make_f3(0.f, 0.f, 0.f);
+
+    // Pad columns (2 either side of the window) are never written by a particle: give them the same
+    // benign content once.  The first spring phase comes at least OC_MARCH_LAG barriers later.
+    {
+        OcStageSmem<TW>& sm = m.rings[s];
+        for (int e = i; e < 6 * OC_RING * 4; e += TW) {
+            const int comp = e / (OC_RING * 4), slot = (e / 4) % OC_RING, pc = e % 4;
+            const int col = pc < 2 ? pc : TW + pc;
+            sm.X[comp][slot][col] = comp < 3 ? 1.0e3f : 0.0f;
+            sm.FD[comp][slot][col] = 0.0f;
+            if (slot < 2) sm.FH[comp][slot][col] = 0.0f;
+        }
+    }
 
     // Steady iterations of this stage: its row is interior and inside the rows it produces, the
     // springs of the two rows above have been evaluated, and (stage 0) the row to load exists.
