@@ -396,7 +396,10 @@ struct OcDevCtx {
 };
 
 // resident CTAs per SM the register allocation is capped for: 4 x 128 threads, 2 x 256, 1 x 512
-#define OC_MARCH_MIN_CTAS(threads) ((threads) <= 128 ? 4 : ((threads) <= 256 ? 2 : 1))
+#define OC_MARCH_MIN_CTAS(threads) ((threads) <= 32 ? 16 : ((threads) <= 64 ? 8 : ((threads) <= 128 ? OC_CTAS128 : ((threads) <= 256 ? 2 : 1))))
+#ifndef OC_CTAS128
+#define OC_CTAS128 4
+#endif
 
 template <class M, int S, int TW>
 __global__ void __launch_bounds__(S * TW, OC_MARCH_MIN_CTAS(S * TW))
