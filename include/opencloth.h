@@ -159,6 +159,9 @@ int oc_spring_energy(oc_cloth* c, int cloth, double* energy);
  * correctly rounded intrinsics (sqrt.rn, rcp.rn, div.rn); *mismatches receives the number of
  * differing results (must be 0). */
 int oc_selftest_math(unsigned long long n, unsigned int seed, unsigned long long* mismatches);
+/* Development counters (only counted when the environment has OC_DEBUG=4 at oc_create): lanes and warps
+ * that took the IEEE-intrinsic fallback of the exact-mode spring phase, velocity fallbacks; reset on read. */
+int oc_debug_counters(oc_cloth* c, unsigned long long out[4]);
 /* sizeof(oc_params) as the library was compiled, so that FFI bindings can verify their mirror */
 size_t oc_sizeof_params(void);
 /* library / device info string: "opencloth_b200 abi=1 sm=100 device=NVIDIA B200 ..." */

@@ -64,6 +64,7 @@ struct oc_cloth {
     float*    stage[2];          // device staging for upload/download
     size_t    stage_bytes;
     double*   d_energy;
+    unsigned long long* d_dbg;   // development counters (OC_DEBUG & 4)
 };
 
 static int free_handle(oc_cloth* c)
@@ -74,6 +75,7 @@ static int free_handle(oc_cloth* c)
     if (c->stage[0]) cudaFree(c->stage[0]);
     if (c->stage[1]) cudaFree(c->stage[1]);
     if (c->d_energy) cudaFree(c->d_energy);
+    if (c->d_dbg) cudaFree(c->d_dbg);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->ev_ready) cudaEventDestroy(c->ev_ready);
@@ -256,6 +258,9 @@ extern "C" int oc_create(oc_cloth** out, const oc_params* p)
 
     for (int b = 0; b < 4; ++b) OC_CREATE_CUDA(cudaMalloc(&c->buf[b], (size_t)c->stored * sizeof(float4)));
     OC_CREATE_CUDA(cudaMalloc(&c->d_energy, sizeof(double)));
+    OC_CREATE_CUDA(cudaMalloc(&c->d_dbg, 4 * sizeof(unsigned long long)));
+    OC_CREATE_CUDA(cudaMemset(c->d_dbg, 0, 4 * sizeof(unsigned long long)));
+    k.dbg_cnt = c->d_dbg;
     OC_CREATE_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
     OC_CREATE_CUDA(cudaEventCreate(&c->ev0));
@@ -640,6 +645,16 @@ extern "C" int oc_selftest_math(unsigned long long n, unsigned int seed, unsigne
     }
     OC_CUDA(cudaMemcpy(mismatches, d, sizeof(*d), cudaMemcpyDeviceToHost));
     OC_CUDA(cudaFree(d));
+    return OC_OK;
+}
+
+extern "C" int oc_debug_counters(oc_cloth* c, unsigned long long out[4])
+{
+    if (!c || !out) return oc_fail(OC_ERR_INVALID, "oc_debug_counters: null");
+    OC_CUDA(cudaSetDevice(c->dev));
+    OC_CUDA(cudaStreamSynchronize(c->stream));
+    OC_CUDA(cudaMemcpy(out, c->d_dbg, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    OC_CUDA(cudaMemset(c->d_dbg, 0, 4 * sizeof(unsigned long long)));
     return OC_OK;
 }
 

@@ -201,11 +201,26 @@ struct OcMarch {
             const float2 nksHV = make_float2(c.nks_struct, c.nks_bend), kdHV = make_float2(c.kd_struct, c.kd_bend);
             const float2 nksS = p_bc(c.nks_shear), kdS = p_bc(c.kd_shear);
             if (!M::kExact) { rH = p_mul(rH, nksHV); rV = p_mul(rV, nksHV); rS = p_mul(rS, nksS); }
-            gH = oc_spring2<M>(mx, mv, nH.x, nH.v, rH, nksHV, kdHV, bad);
-            gV = oc_spring2<M>(mx, mv, nV.x, nV.v, rV, nksHV, kdHV, bad);
-            gS = oc_spring2<M>(mx, mv, nS.x, nS.v, rS, nksS,  kdS,  bad);
+            unsigned cls = 0;
+            gH = oc_spring2<M>(mx, mv, nH.x, nH.v, rH, nksHV, kdHV, bad, &cls);
+            gV = oc_spring2<M>(mx, mv, nV.x, nV.v, rV, nksHV, kdHV, bad, &cls);
+            gS = oc_spring2<M>(mx, mv, nS.x, nS.v, rS, nksS,  kdS,  bad, &cls);
+#if defined(OC_CLASSIFY) && defined(__CUDA_ARCH__)
+            if (M::kExact && (c.dbg & 4) && col_store && row >= lo_s && row < hi_s) {
+                if (cls & 1u) atomicAdd(c.dbg_cnt + 3, 1ull);                       // -0 numerator
+                if (cls & 2u) atomicAdd(c.dbg_cnt + 3, 1ull << 20);                // tiny numerator
+                if (cls & 4u) atomicAdd(c.dbg_cnt + 3, 1ull << 40);                // huge numerator
+                if (cls & 8u) atomicAdd(c.dbg_cnt + 2, 1ull << 32);                // squared length
+            }
+#endif
             if (c.dbg & 1) bad = true;
             if (c.dbg & 2) bad = false;
+#ifdef __CUDA_ARCH__
+            if (M::kExact && bad && (c.dbg & 4)) {
+                atomicAdd(c.dbg_cnt, 1ull);
+                if ((threadIdx.x & 31) == __ffs(__activemask()) - 1) atomicAdd(c.dbg_cnt + 1, 1ull);
+            }
+#endif
             if (M::kExact && bad) oc_march_redo<M, TW>(in, sl, s1, s2, ci, c, rh1_i, rh2_i, dx2_i, dx2_m, rv1_j, rv2_j, dz2_j, gH, gV, gS);
             in.FH[0][sl & 1][ci] = gH.x.x; in.FH[1][sl & 1][ci] = gH.y.x; in.FH[2][sl & 1][ci] = gH.z.x;
             in.FH[3][sl & 1][ci] = gH.x.y; in.FH[4][sl & 1][ci] = gH.y.y; in.FH[5][sl & 1][ci] = gH.z.y;
@@ -284,6 +299,9 @@ struct OcMarch {
             bool badv = false;
             float2 vxy; float vz;
             oc_velocity2<M>(dxy, dz, c, ydt, badv, vxy, vz);
+#ifdef __CUDA_ARCH__
+            if (M::kExact && badv && (c.dbg & 4)) atomicAdd(c.dbg_cnt + 2, 1ull);
+#endif
             if (M::kExact && badv) { const f3 v = M::velocity(make_f3(dxy.x, dxy.y, dz), c); vxy = make_float2(v.x, v.y); vz = v.z; }
             oc_st_pvd<TW>(rings[0], sl, ci, make_f3(la.x, la.y, la.z), make_f3(vxy.x, vxy.y, vz), make_f3(dxy.x, dxy.y, dz), lq.w);   // lrow = row + 4: same slot
         }
