@@ -494,6 +494,16 @@ extern "C" int oc_halo_exchange(oc_cloth* const* bands, int n)
                       bands[b]->p.ny != bands[0]->p.ny || bands[b]->p.halo_rows != bands[0]->p.halo_rows))
             return oc_fail(OC_ERR_INVALID, "oc_halo_exchange: bands must be consecutive row bands of one cloth with equal halo_rows");
     }
+    // 0. direct peer access between neighbouring bands' devices (NVLink on an HGX box); without it the
+    //    peer copies are staged through the host.  "already enabled" / "not supported" are not errors.
+    for (int b = 0; b + 1 < n; ++b) {
+        const int d0 = bands[b]->dev, d1 = bands[b + 1]->dev;
+        if (d0 == d1) continue;
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, d0, d1) == cudaSuccess && can) { cudaSetDevice(d0); cudaDeviceEnablePeerAccess(d1, 0); }
+        if (cudaDeviceCanAccessPeer(&can, d1, d0) == cudaSuccess && can) { cudaSetDevice(d1); cudaDeviceEnablePeerAccess(d0, 0); }
+        cudaGetLastError();
+    }
     // 1. every band announces that its owned rows are final
     for (int b = 0; b < n; ++b) {
         OC_CUDA(cudaSetDevice(bands[b]->dev));

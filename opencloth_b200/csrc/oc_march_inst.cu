@@ -1,6 +1,15 @@
 // oc_march_inst.cu — explicit instantiations of the marching kernel.  Compiled once per
 // (OC_INST_TW, OC_INST_EXACT) pair so that the variants build in parallel:
 //   TW = 32, 64 : S = 1, 2, 4, 8      TW = 128 : S = 1, 2, 4
+// Resident CTAs per SM the 128-thread kernels are register-capped for: the exact kernels need ~160
+// registers to hold three spring pairs without spilling (3 CTAs), the fast ones fit 128 (4 CTAs).
+// Measured on B200 at 2048^2: exact 3 CTAs 32.5 vs 4 CTAs 30.5 G updates/s; 5 CTAs (96 regs, spills) is
+// slower in both modes.
+#if OC_INST_EXACT
+#define OC_CTAS128 3
+#else
+#define OC_CTAS128 4
+#endif
 #include "oc_march.cuh"
 
 #ifndef OC_INST_TW
