@@ -45,7 +45,8 @@ typedef enum oc_status {
 typedef enum oc_kernel {
     OC_KERNEL_AUTO = 0,      /* marching stencil kernel where the grid allows, else gather */
     OC_KERNEL_GATHER = 1,    /* one thread per particle, 12-neighbour gather from global memory */
-    OC_KERNEL_MARCH = 2      /* fused shared-memory marching stencil, k substeps per launch */
+    OC_KERNEL_MARCH = 2,     /* fused shared-memory marching stencil, one column per thread, k substeps per launch */
+    OC_KERNEL_MARCH2 = 3     /* the same with two columns per thread (one substep per launch) */
 } oc_kernel;
 
 typedef struct oc_cloth oc_cloth;      /* opaque; owns all device memory of one simulation */

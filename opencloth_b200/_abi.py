@@ -20,6 +20,7 @@ OC_ERR_UNSUPPORTED = -5
 OC_KERNEL_AUTO = 0
 OC_KERNEL_GATHER = 1
 OC_KERNEL_MARCH = 2
+OC_KERNEL_MARCH2 = 3
 
 
 class OcParams(ctypes.Structure):

@@ -10,6 +10,7 @@
 #include "oc_host.h"
 #include "oc_gather.cuh"
 #include "oc_march.cuh"
+#include "oc_march2.cuh"
 
 #include <cstdio>
 #include <cstdlib>
@@ -215,7 +216,7 @@ static int validate(const oc_params* p)
     if (!(p->dt > 0.0f) || !(p->mass > 0.0f)) return oc_fail(OC_ERR_INVALID, "dt and mass must be positive");
     if (p->substeps_per_launch < 0 || p->substeps_per_launch > OC_MARCH_MAX_STAGES)
         return oc_fail(OC_ERR_INVALID, "substeps_per_launch must be 0..%d", OC_MARCH_MAX_STAGES);
-    if (p->kernel < OC_KERNEL_AUTO || p->kernel > OC_KERNEL_MARCH) return oc_fail(OC_ERR_INVALID, "bad kernel id");
+    if (p->kernel < OC_KERNEL_AUTO || p->kernel > OC_KERNEL_MARCH2) return oc_fail(OC_ERR_INVALID, "bad kernel id");
     return OC_OK;
 }
 
@@ -277,6 +278,7 @@ extern "C" int oc_create(oc_cloth** out, const oc_params* p)
         OC_CREATE_CUDA(cudaMemcpyAsync(c->buf[3], c->buf[0], (size_t)n * sizeof(float4), cudaMemcpyDeviceToDevice, c->stream));
     }
     rc = oc_march_configure(c->dev);
+    if (rc == 0) rc = oc_march2_configure(c->dev);
     if (rc != 0) { free_handle(c); return oc_fail(OC_ERR_CUDA, "oc_march_configure failed: %s", cudaGetErrorString((cudaError_t)rc)); }
 #undef OC_CREATE_CUDA
     *out = c;
@@ -424,7 +426,13 @@ extern "C" int oc_step(oc_cloth* c, int n)
         const int kmaxS = (kern == OC_KERNEL_MARCH) ? oc_host_pick_stages(n < kdef ? n : kdef) : 1;
         OcLaunch L;
         oc_host_next_launch(c->q, n, kmaxS, L);
-        if (kern == OC_KERNEL_MARCH) {
+        if (kern == OC_KERNEL_MARCH2) {
+            int nl = 0;
+            cudaError_t e = oc_march2_launch(c->k, c->p.exact != 0, L.ra, L.rb, c->sm_count,
+                                             c->buf[L.src_a], c->buf[L.src_b], c->buf[L.dst], c->stream, &nl);
+            c->launches += nl;
+            if (e != cudaSuccess) return oc_fail(OC_ERR_CUDA, "march2 kernel launch failed: %s", cudaGetErrorString(e));
+        } else if (kern == OC_KERNEL_MARCH) {
             int nl = 0;
             cudaError_t e = oc_march_launch(c->k, c->p.exact != 0, L.S, L.ra, L.rb, c->sm_count,
                                             c->buf[L.src_a], c->buf[L.src_b], c->buf[L.dst], c->buf[L.dst_prev], c->stream, &nl);

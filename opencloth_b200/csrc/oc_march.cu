@@ -1,5 +1,6 @@
 // oc_march.cu — host side of the marching kernel: variant table, launch geometry, launch.
 #include "oc_march.cuh"
+#include "oc_march2.cuh"
 #include <cstdlib>
 #include <cstdio>
 
@@ -124,6 +125,85 @@ cudaError_t oc_march_launch(const OcConst& c, bool exact, int S, int ra, int rb,
     OcConst cc = c;
     int RS = pl.RS, xh = pl.x_halo;
     void* args[] = { &cc, (void*)&A, (void*)&B, (void*)&C, (void*)&Dst, &ra, &rb, &RS, &xh };
+    cudaError_t e = cudaLaunchKernel(fn, grid, block, args, pl.smem, stream);
+    if (e == cudaSuccess) *n_launches = 1;
+    return e;
+}
+
+// ------------------------------------------------------------------------------------------------
+// two-columns-per-thread kernel (oc_march2.cuh), one substep per launch
+// ------------------------------------------------------------------------------------------------
+extern "C" const void* oc_march2_fn_exact(int WC);
+extern "C" const void* oc_march2_fn_fast(int WC);
+static int g_occ2[2][2];      // [exact][WC == 128]
+
+static size_t smem2(int WC) { return WC == 64 ? sizeof(OcSmem2<64>) : sizeof(OcSmem2<128>); }
+static int pick_wc(int nx)
+{
+    const char* env = getenv("OC_MARCH2_WC");
+    if (env && (atoi(env) == 64 || atoi(env) == 128)) return atoi(env);
+    return nx <= 64 ? 64 : 128;
+}
+
+int oc_march2_configure(int device)
+{
+    (void)device;
+    for (int e = 0; e < 2; ++e)
+        for (int w = 0; w < 2; ++w) {
+            const int WC = w ? 128 : 64;
+            const void* fn = e ? oc_march2_fn_exact(WC) : oc_march2_fn_fast(WC);
+            cudaError_t err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2(WC));
+            if (err != cudaSuccess) return (int)err;
+            int occ = 0;
+            err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, WC / 2, smem2(WC));
+            if (err != cudaSuccess) return (int)err;
+            g_occ2[e][w] = occ;
+        }
+    return 0;
+}
+
+int oc_march2_plan(const OcConst& c, int ra, int rb, int sm_count, int occ_hint, OcMarchPlan* pl)
+{
+    const int U = c.U;
+    const int WC = pick_wc(U);
+    const int x_halo = (U <= WC) ? 0 : 2;
+    const int W_out = WC - 2 * x_halo;
+    const int nstrips = (U + W_out - 1) / W_out;
+    const int rows = rb - ra;
+    if (rows <= 0) return -1;
+    const long long slots = (long long)sm_count * (occ_hint > 0 ? occ_hint : 1);
+    const int fill = OC_MARCH_LAG + 2;
+    int best_rs = rows; double best = -1.0;
+    const char* env = getenv("OC_MARCH_RS");
+    if (env && atoi(env) > 0) { best_rs = atoi(env) < rows ? atoi(env) : rows; }
+    else for (int nseg = 1; nseg <= rows; ++nseg) {
+        int rs = (rows + nseg - 1) / nseg;
+        if (rs < 8 && nseg > 1) break;
+        int ns = (rows + rs - 1) / rs;
+        long long ctas = (long long)nstrips * ns * c.batch;
+        long long waves = (ctas + slots - 1) / slots;
+        double eff = (double)rows * nstrips * c.batch / ((double)waves * slots * (rs + fill));
+        if (eff > best * 1.0001) { best = eff; best_rs = rs; }
+    }
+    pl->TW = WC; pl->S = 1; pl->x_halo = x_halo; pl->W_out = W_out; pl->nstrips = nstrips;
+    pl->RS = best_rs; pl->nseg = (rows + best_rs - 1) / best_rs; pl->threads = WC / 2; pl->smem = smem2(WC);
+    return 0;
+}
+
+cudaError_t oc_march2_launch(const OcConst& c, bool exact, int ra, int rb, int sm_count,
+                             const float4* A, const float4* B, float4* C, cudaStream_t stream, int* n_launches)
+{
+    *n_launches = 0;
+    OcMarchPlan pl;
+    const int WC = pick_wc(c.U);
+    if (oc_march2_plan(c, ra, rb, sm_count, g_occ2[exact ? 1 : 0][WC == 128], &pl) != 0) return cudaErrorInvalidValue;
+    const void* fn = exact ? oc_march2_fn_exact(WC) : oc_march2_fn_fast(WC);
+    if (!fn) return cudaErrorInvalidDeviceFunction;
+    if (pl.nseg > 65535 || c.batch > 65535) return cudaErrorInvalidConfiguration;
+    dim3 grid(pl.nstrips, pl.nseg, c.batch), block(pl.threads, 1, 1);
+    OcConst cc = c;
+    int RS = pl.RS, xh = pl.x_halo;
+    void* args[] = { &cc, (void*)&A, (void*)&B, (void*)&C, &ra, &rb, &RS, &xh };
     cudaError_t e = cudaLaunchKernel(fn, grid, block, args, pl.smem, stream);
     if (e == cudaSuccess) *n_launches = 1;
     return e;

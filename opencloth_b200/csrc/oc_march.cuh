@@ -57,6 +57,23 @@ struct OcStageSmem {
 #define OC_KEEP4(v) ((void)0)
 #endif
 
+// Asynchronous 16-byte copy global -> shared (LDGSTS): the row of the next-but-three iteration is requested
+// at the top of an iteration without occupying registers and without giving ptxas the chance to sink the
+// load next to its use; the requesting thread waits for its own copies just before it consumes them.
+#ifdef __CUDA_ARCH__
+OC_HD void oc_cp_async16(void* smem_dst, const void* gsrc)
+{
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(sa), "l"(gsrc) : "memory");
+}
+OC_HD void oc_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+OC_HD void oc_cp_async_wait()   { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+#else
+OC_HD void oc_cp_async16(void* smem_dst, const void* gsrc) { *reinterpret_cast<float4*>(smem_dst) = *reinterpret_cast<const float4*>(gsrc); }
+OC_HD void oc_cp_async_commit() {}
+OC_HD void oc_cp_async_wait() {}
+#endif
+
 // position (x) and velocity (v) of two particles as pairs
 struct OcPV2 { OcPair3 x, v; };
 template <int TW>
@@ -229,7 +246,6 @@ struct OcMarch {
         }
 
         ctx.sync();
-        if (doL) { OC_KEEP4(la); OC_KEEP4(lq); }
 
         // ---- G phase: gather in the reference's order, integrate, collide, hand on ------------------
         const bool doG = kSteady || (row >= lo_s && row < hi_s);
@@ -239,7 +255,7 @@ struct OcMarch {
             OcF F;
             F.xy = pinned ? p_bc(0.0f) : make_float2(c.f0[0], c.f0[1]);
             F.z  = pinned ? 0.0f : c.f0[2];
-            F.xy = p_add(F.xy, p_mulx(p_bc(c.damping), make_float2(mv.x, mv.y)));
+            F.xy = p_add(F.xy, p_mulm<M>(p_bc(c.damping), make_float2(mv.x, mv.y)));
             F.z  = M::add(F.z, M::mul(c.damping, mv.z));
             if (!pinned) {
                 const bool up1 = kSteady || row - 1 >= 0, up2 = kSteady || row - 2 >= 0;
@@ -292,7 +308,9 @@ struct OcMarch {
         }
 
         // ---- stage 0: publish the loaded row into its own ring --------------------------------------
+        // (the register fence sits here, not right after the barrier: the loads get the whole iteration to land)
         if (doL) {
+            OC_KEEP4(la); OC_KEEP4(lq);
             float2 dxy = p_sub(make_float2(la.x, la.y), make_float2(lq.x, lq.y));
             float dz = M::sub(la.z, lq.z);
             if (oc_hit(la.w)) { dxy = p_bc(0.0f); dz = 0.0f; }                   // X_last == X (V:530)

@@ -1,0 +1,491 @@
+// oc_march2.cuh — kernel 3: the marching stencil kernel with TWO COLUMNS PER THREAD (one substep per launch).
+//
+// Same algorithm, data flow and arithmetic as oc_march.cuh (read that header first); what changes is the
+// mapping of work to threads, chosen to cut the instruction-issue and shared-memory load that bound the
+// one-column kernel (profiles/r1_march_*):
+//   * A thread owns two adjacent columns a = 2i, b = 2i+1 of the window.  The packed FP32x2 pairs are
+//     now (particle a, particle b) for ONE spring type, so the own-column window, the (+2,0) partners and
+//     every received (+2,0) force are naturally aligned 64-bit shared-memory accesses.
+//   * Three of the twelve springs of a thread are internal (a-b, a-b', b-a'): their partner force never
+//     touches shared memory.  Per particle the kernel issues ~20 shared loads instead of 55 and ~10
+//     stores instead of 19.
+//   * The force accumulation, the base force, the integration and the collider test run as packed
+//     operations over the two particles.
+// The accumulation ORDER per particle is unchanged (the reference's spring-list order), and so is every
+// rounding: exact mode stays bit-identical.
+//
+// Kernel: S = 1 (no temporal blocking; k > 1 is served by oc_k_march).  WC window columns per CTA,
+// WC/2 threads.  "Interior" CTAs (every column of the window has all four horizontal neighbours) run a
+// steady loop without any predicate; edge CTAs and edge rows use a generic, per-half predicated path.
+#pragma once
+#include "oc_core.cuh"
+#include "oc_march.cuh"
+
+template <int WC>
+struct OcSmem2 {
+    float X[6][OC_RING][WC + 4];        // x, y, z, vx, vy, vz     slot = row & 3, index = window column + 2
+    float Dd[3][OC_RING][WC + 4];       // X - X_last
+    float FH2[3][2][WC + 4];            // f(+2,0) of every column, slot = row & 1
+    float FH1[3][2][WC / 2 + 2];        // f(+1,0) of each thread's b column, index = thread + 1
+    float FDb[3][OC_RING][WC / 2 + 2];  // f(+1,+1) of the b column
+    float FAa[3][OC_RING][WC / 2 + 2];  // f(-1,+1) of the a column
+    float4 stage[4][WC / 2];            // landing zone of the asynchronous row loads: A[a], B[a], A[b], B[b] per thread
+};
+
+// ---- spring pair with a pair-valued first end (particles a and b of the thread) ----------------------
+template <class M>
+OC_HD OcPair3 oc_spring2v(const OcPair3& px, const OcPair3& pv, const OcPair3& qx, const OcPair3& qv,
+                          float2 rest, float2 nks, float2 kd, bool& bad)
+{
+    OcPair3 dp, dv, f;
+    dp.x = p_sub(px.x, qx.x); dp.y = p_sub(px.y, qx.y); dp.z = p_sub(px.z, qx.z);                     // V:471
+    dv.x = p_sub(pv.x, qv.x); dv.y = p_sub(pv.y, qv.y); dv.z = p_sub(pv.z, qv.z);                     // V:472
+    if (M::kExact) {
+        const float2 sqr  = p_add(p_add(p_mulx(dp.x, dp.x), p_mulx(dp.y, dp.y)), p_mulx(dp.z, dp.z));
+        const float2 dist = oc_sqrt2<M>(sqr, bad);                                                   // V:473
+#ifdef __CUDA_ARCH__
+        const float2 y0  = p_rcp(dist);
+        const float2 inv = p_fma(y0, p_fma(y0, p_neg(dist), p_bc(1.0f)), y0);
+        const float2 a   = p_add(p_add(p_mulx(dv.x, dp.x), p_mulx(dv.y, dp.y)), p_mulx(dv.z, dp.z));
+        bad |= oc_bad_num(a.x, OC_NUM_LO_BITS, OC_NUM_HI_BITS) | oc_bad_num(a.y, OC_NUM_LO_BITS, OC_NUM_HI_BITS);
+        const float2 q0  = p_mul(a, inv);
+        const float2 q   = p_fma(inv, p_fma(q0, p_neg(dist), a), q0);
+#else
+        const float2 inv = make_float2(1.0f / dist.x, 1.0f / dist.y);
+        const float2 a   = p_add(p_add(p_mulx(dv.x, dp.x), p_mulx(dv.y, dp.y)), p_mulx(dv.z, dp.z));
+        const float2 q   = make_float2(a.x / dist.x, a.y / dist.y);
+#endif
+        const float2 left  = p_mulx(nks, p_sub(dist, rest));                                         // V:475
+        const float2 right = p_mulx(kd, q);                                                          // V:476
+        const float2 s = p_add(left, right);
+        f.x = p_mul(s, p_mul(dp.x, inv)); f.y = p_mul(s, p_mul(dp.y, inv)); f.z = p_mul(s, p_mul(dp.z, inv));   // V:477
+    } else {
+        const float2 sqr  = p_fma(dp.z, dp.z, p_fma(dp.y, dp.y, p_mul(dp.x, dp.x)));
+        const float2 rinv = p_rsq(sqr);
+        const float2 dist = p_mul(sqr, rinv);
+        const float2 left = p_fma(nks, dist, p_neg(rest));                      // rest pre-multiplied by nks
+        const float2 dot  = p_fma(dv.z, dp.z, p_fma(dv.y, dp.y, p_mul(dv.x, dp.x)));
+        const float2 s    = p_mul(p_fma(p_mul(kd, dot), rinv, left), rinv);
+        f.x = p_mul(s, dp.x); f.y = p_mul(s, dp.y); f.z = p_mul(s, dp.z);
+    }
+    return f;
+}
+
+// Cold path of exact mode: one spring pair of the thread redone with the IEEE intrinsics.  The operands
+// are re-read from shared memory (nothing of the hot loop has its address taken) and the result comes
+// back by value.  kind: 0 (+1,0)  1 (+2,0)  2 (0,+1)  3 (0,+2)  4 (+1,+1)  5 (-1,+1)
+template <class M, int WC>
+#ifdef __CUDA_ARCH__
+__device__ __noinline__
+#else
+inline
+#endif
+OcPair3 oc_march2_redo(const OcSmem2<WC>* s, int kind, int sl, int pa, float rest_a, float rest_b, float nks, float kd)
+{
+    const int s1 = (sl + 1) & (OC_RING - 1), s2 = (sl + 2) & (OC_RING - 1);
+#define OC_LDX(slot, col) make_f3(s->X[0][slot][col], s->X[1][slot][col], s->X[2][slot][col])
+#define OC_LDV(slot, col) make_f3(s->X[3][slot][col], s->X[4][slot][col], s->X[5][slot][col])
+    // partner of a / of b: (slot, column)
+    int sa = sl, ca = pa, sb = sl, cb = pa;
+    switch (kind) {
+    case 0: sa = sl; ca = pa + 1; sb = sl; cb = pa + 2; break;
+    case 1: sa = sl; ca = pa + 2; sb = sl; cb = pa + 3; break;
+    case 2: sa = s1; ca = pa;     sb = s1; cb = pa + 1; break;
+    case 3: sa = s2; ca = pa;     sb = s2; cb = pa + 1; break;
+    case 4: sa = s1; ca = pa + 1; sb = s1; cb = pa + 2; break;
+    default: sa = s1; ca = pa - 1; sb = s1; cb = pa;    break;
+    }
+    const f3 fa = oc_spring<M>(OC_LDX(sl, pa),     OC_LDV(sl, pa),     OC_LDX(sa, ca), OC_LDV(sa, ca), rest_a, nks, kd);
+    const f3 fb = oc_spring<M>(OC_LDX(sl, pa + 1), OC_LDV(sl, pa + 1), OC_LDX(sb, cb), OC_LDV(sb, cb), rest_b, nks, kd);
+#undef OC_LDX
+#undef OC_LDV
+    OcPair3 f;
+    f.x = make_float2(fa.x, fb.x); f.y = make_float2(fa.y, fb.y); f.z = make_float2(fa.z, fb.z);
+    return f;
+}
+
+// F (+|-)= g for both particles, or per half under predicates
+template <class M, bool kAll> OC_HD void oc_acc2(OcPair3& F, const OcPair3& g, bool pa, bool pb, bool sub)
+{
+    if (kAll) {
+        if (sub) { F.x = p_sub(F.x, g.x); F.y = p_sub(F.y, g.y); F.z = p_sub(F.z, g.z); }
+        else     { F.x = p_add(F.x, g.x); F.y = p_add(F.y, g.y); F.z = p_add(F.z, g.z); }
+    } else {
+        if (pa) {
+            if (sub) { F.x.x = M::sub(F.x.x, g.x.x); F.y.x = M::sub(F.y.x, g.y.x); F.z.x = M::sub(F.z.x, g.z.x); }
+            else     { F.x.x = M::add(F.x.x, g.x.x); F.y.x = M::add(F.y.x, g.y.x); F.z.x = M::add(F.z.x, g.z.x); }
+        }
+        if (pb) {
+            if (sub) { F.x.y = M::sub(F.x.y, g.x.y); F.y.y = M::sub(F.y.y, g.y.y); F.z.y = M::sub(F.z.y, g.z.y); }
+            else     { F.x.y = M::add(F.x.y, g.x.y); F.y.y = M::add(F.y.y, g.y.y); F.z.y = M::add(F.z.y, g.z.y); }
+        }
+    }
+}
+
+template <class M, int WC, class Ctx>
+struct OcMarch2 {
+    typedef OcSmem2<WC> Smem;
+    static constexpr int T = WC / 2;
+    Ctx& ctx;
+    const OcConst& c;
+    const float4* __restrict__ A; const float4* __restrict__ B;
+    float4* __restrict__ C;
+    Smem* sm;
+    int i, pa, ga, U, V;
+    int lo, hi, plo, in_lo, in_hi, first, row0;
+    bool oka, okb, sta, stb;                 // column exists / column is stored by this CTA
+    float2 rh1, rh2, dx2ab, dx2ma;           // (rh1[ga], rh1[gb]) ... (dx2[ga-1], dx2[ga])
+    float ydt;
+    float rv1_n, rv2_n, dz2_n;
+    long long goff;                          // element offset of (cloth, ga, row 0)
+    OcPV2 me, w1;                            // own columns, rows row and row+1
+    OcPair3 k1, k2a, k2b;                    // carried (0,+1) of row-1, (0,+2) of row-1 and row-2
+    f3 kDa, kAb;                             // carried internal shear forces of row-1: f(a->b'), f(b->a')
+
+    OC_HD OcMarch2(Ctx& ctx_, const OcConst& c_) : ctx(ctx_), c(c_) {}
+
+    OC_HD OcPV2 ld_own(int slot) const
+    {
+        OcPV2 r;
+        r.x.x = *reinterpret_cast<const float2*>(&sm->X[0][slot][pa]); r.x.y = *reinterpret_cast<const float2*>(&sm->X[1][slot][pa]);
+        r.x.z = *reinterpret_cast<const float2*>(&sm->X[2][slot][pa]); r.v.x = *reinterpret_cast<const float2*>(&sm->X[3][slot][pa]);
+        r.v.y = *reinterpret_cast<const float2*>(&sm->X[4][slot][pa]); r.v.z = *reinterpret_cast<const float2*>(&sm->X[5][slot][pa]);
+        return r;
+    }
+
+    template <bool kSteady, bool kInterior, int kSlot>
+    OC_HD void iter(int it)
+    {
+        Smem& s = *sm;
+        const int row = row0 + it;
+        const int lrow = first + it;
+        // ---- asynchronous global loads of row lrow (both columns) into the thread's landing zone ------
+        // (columns of the window outside the cloth get a benign far-away particle at rest)
+        const bool doL = kSteady || (lrow >= in_lo && lrow < in_hi);
+        if (doL) {
+            const long long o = goff + (long long)lrow * U;
+            if (kInterior || oka) { oc_cp_async16(&s.stage[0][i], A + o); oc_cp_async16(&s.stage[1][i], B + o); }
+            else s.stage[0][i] = s.stage[1][i] = make_float4(1.0e3f + 8.0f * (float)pa, 1.0e3f, 1.0e3f + 8.0f * (float)(lrow & 63), oc_u2f(OC_W_PLAIN));
+            if (kInterior || okb) { oc_cp_async16(&s.stage[2][i], A + o + 1); oc_cp_async16(&s.stage[3][i], B + o + 1); }
+            else s.stage[2][i] = s.stage[3][i] = make_float4(1.0e3f + 8.0f * (float)(pa + 1), 1.0e3f, 1.0e3f + 8.0f * (float)(lrow & 63), oc_u2f(OC_W_PLAIN));
+            oc_cp_async_commit();
+        }
+        const float rv1_j = rv1_n, rv2_j = rv2_n, dz2_j = dz2_n;
+        {
+            int r = row + 1;
+            if (!kSteady) r = r < 0 ? 0 : (r >= V ? V - 1 : r);
+            rv1_n = OC_LDG(c.rv1 + r); rv2_n = OC_LDG(c.rv2 + r); dz2_n = OC_LDG(c.dz2 + r);
+        }
+        const int sl = kSlot >= 0 ? kSlot : (row & (OC_RING - 1));
+        const int s1 = (sl + 1) & (OC_RING - 1), s2 = (sl + 2) & (OC_RING - 1), s3 = (sl + 3) & (OC_RING - 1);
+        const int h = sl & 1;
+
+        // ---- P phase ---------------------------------------------------------------------------------
+        const bool doP = kSteady || (row >= plo && row < hi);
+        OcPair3 gH1, gH2, gV1, gV2, gD, gA, dme;
+        OcPV2 w2;
+        if (doP) {
+            if (!kSteady && row == plo) { me = ld_own(sl); w1 = ld_own(s1); }
+            w2 = ld_own(s2);
+            dme.x = *reinterpret_cast<const float2*>(&s.Dd[0][sl][pa]);
+            dme.y = *reinterpret_cast<const float2*>(&s.Dd[1][sl][pa]);
+            dme.z = *reinterpret_cast<const float2*>(&s.Dd[2][sl][pa]);
+            // partners of the next thread's columns, this row: (a_n, b_n)
+            OcPV2 n0;
+            n0.x.x = *reinterpret_cast<const float2*>(&s.X[0][sl][pa + 2]); n0.x.y = *reinterpret_cast<const float2*>(&s.X[1][sl][pa + 2]);
+            n0.x.z = *reinterpret_cast<const float2*>(&s.X[2][sl][pa + 2]); n0.v.x = *reinterpret_cast<const float2*>(&s.X[3][sl][pa + 2]);
+            n0.v.y = *reinterpret_cast<const float2*>(&s.X[4][sl][pa + 2]); n0.v.z = *reinterpret_cast<const float2*>(&s.X[5][sl][pa + 2]);
+            // shifted pairs: (b, a_n) this row; (b', a_n') and (b_prev', a') next row
+            OcPV2 qH1, qD, qA;
+            qH1.x.x = make_float2(me.x.x.y, n0.x.x.x); qH1.x.y = make_float2(me.x.y.y, n0.x.y.x); qH1.x.z = make_float2(me.x.z.y, n0.x.z.x);
+            qH1.v.x = make_float2(me.v.x.y, n0.v.x.x); qH1.v.y = make_float2(me.v.y.y, n0.v.y.x); qH1.v.z = make_float2(me.v.z.y, n0.v.z.x);
+            qD.x.x = make_float2(w1.x.x.y, s.X[0][s1][pa + 2]); qD.x.y = make_float2(w1.x.y.y, s.X[1][s1][pa + 2]); qD.x.z = make_float2(w1.x.z.y, s.X[2][s1][pa + 2]);
+            qD.v.x = make_float2(w1.v.x.y, s.X[3][s1][pa + 2]); qD.v.y = make_float2(w1.v.y.y, s.X[4][s1][pa + 2]); qD.v.z = make_float2(w1.v.z.y, s.X[5][s1][pa + 2]);
+            qA.x.x = make_float2(s.X[0][s1][pa - 1], w1.x.x.x); qA.x.y = make_float2(s.X[1][s1][pa - 1], w1.x.y.x); qA.x.z = make_float2(s.X[2][s1][pa - 1], w1.x.z.x);
+            qA.v.x = make_float2(s.X[3][s1][pa - 1], w1.v.x.x); qA.v.y = make_float2(s.X[4][s1][pa - 1], w1.v.y.x); qA.v.z = make_float2(s.X[5][s1][pa - 1], w1.v.z.x);
+
+            bool bad = false;
+            float2 rD = oc_sqrt2<M>(p_add(dx2ab, p_bc(dz2_j)), bad);        // cells (ga, row), (gb, row)
+            float2 rA = oc_sqrt2<M>(p_add(dx2ma, p_bc(dz2_j)), bad);        // cells (ga-1, row), (ga, row)
+            float2 rH1 = rh1, rH2 = rh2, rV1 = p_bc(rv1_j), rV2 = p_bc(rv2_j);
+            const float2 nS = p_bc(c.nks_struct), kS = p_bc(c.kd_struct), nB = p_bc(c.nks_bend), kB = p_bc(c.kd_bend);
+            const float2 nSh = p_bc(c.nks_shear), kSh = p_bc(c.kd_shear);
+            if (!M::kExact) { rH1 = p_mul(rH1, nS); rH2 = p_mul(rH2, nB); rV1 = p_mul(rV1, nS); rV2 = p_mul(rV2, nB); rD = p_mul(rD, nSh); rA = p_mul(rA, nSh); }
+            bool b1 = false, b2 = false, b3 = false, b4 = false, b5 = false, b6 = false;
+            gH1 = oc_spring2v<M>(me.x, me.v, qH1.x, qH1.v, rH1, nS, kS, b1);
+            gH2 = oc_spring2v<M>(me.x, me.v, n0.x,  n0.v,  rH2, nB, kB, b2);
+            gV1 = oc_spring2v<M>(me.x, me.v, w1.x,  w1.v,  rV1, nS, kS, b3);
+            gV2 = oc_spring2v<M>(me.x, me.v, w2.x,  w2.v,  rV2, nB, kB, b4);
+            gD  = oc_spring2v<M>(me.x, me.v, qD.x,  qD.v,  rD,  nSh, kSh, b5);
+            gA  = oc_spring2v<M>(me.x, me.v, qA.x,  qA.v,  rA,  nSh, kSh, b6);
+            if (M::kExact && (bad | b1 | b2 | b3 | b4 | b5 | b6)) {
+                // rare: an operand left the exact range of the branch-free sequences -> IEEE intrinsics
+                if (bad | b1) gH1 = oc_march2_redo<M, WC>(sm, 0, sl, pa, rh1.x, rh1.y, c.nks_struct, c.kd_struct);
+                if (bad | b2) gH2 = oc_march2_redo<M, WC>(sm, 1, sl, pa, rh2.x, rh2.y, c.nks_bend, c.kd_bend);
+                if (bad | b3) gV1 = oc_march2_redo<M, WC>(sm, 2, sl, pa, rv1_j, rv1_j, c.nks_struct, c.kd_struct);
+                if (bad | b4) gV2 = oc_march2_redo<M, WC>(sm, 3, sl, pa, rv2_j, rv2_j, c.nks_bend, c.kd_bend);
+                if (bad | b5) gD  = oc_march2_redo<M, WC>(sm, 4, sl, pa, M::sqrt(M::add(dx2ab.x, dz2_j)), M::sqrt(M::add(dx2ab.y, dz2_j)), c.nks_shear, c.kd_shear);
+                if (bad | b6) gA  = oc_march2_redo<M, WC>(sm, 5, sl, pa, M::sqrt(M::add(dx2ma.x, dz2_j)), M::sqrt(M::add(dx2ma.y, dz2_j)), c.nks_shear, c.kd_shear);
+            }
+            // publish the forces whose partner lives in another thread
+            s.FH1[0][h][i + 1] = gH1.x.y; s.FH1[1][h][i + 1] = gH1.y.y; s.FH1[2][h][i + 1] = gH1.z.y;
+            *reinterpret_cast<float2*>(&s.FH2[0][h][pa]) = gH2.x; *reinterpret_cast<float2*>(&s.FH2[1][h][pa]) = gH2.y; *reinterpret_cast<float2*>(&s.FH2[2][h][pa]) = gH2.z;
+            s.FDb[0][sl][i + 1] = gD.x.y; s.FDb[1][sl][i + 1] = gD.y.y; s.FDb[2][sl][i + 1] = gD.z.y;
+            s.FAa[0][sl][i + 1] = gA.x.x; s.FAa[1][sl][i + 1] = gA.y.x; s.FAa[2][sl][i + 1] = gA.z.x;
+        }
+
+        ctx.sync();
+
+        // ---- G phase ---------------------------------------------------------------------------------
+        const bool doG = kSteady || (row >= lo && row < hi);
+        if (doG) {
+            constexpr bool kAll = kSteady && kInterior;
+            const int gb = ga + 1;
+            const bool pin_a = !kSteady && oc_pinned(c, ga, row), pin_b = !kSteady && oc_pinned(c, gb, row);
+            const bool ea = !pin_a, eb = !pin_b;                                  // springs act on the particle
+            // existence of the horizontal neighbours of a and of b
+            const bool al1 = kAll || ga - 1 >= 0, al2 = kAll || ga - 2 >= 0, ar1 = kAll || gb < U, ar2 = kAll || ga + 2 < U;
+            const bool bl1 = kAll || ga >= 0,     bl2 = kAll || ga - 1 >= 0, br1 = kAll || gb + 1 < U, br2 = kAll || gb + 2 < U;
+            const bool up1 = kSteady || row - 1 >= 0, up2 = kSteady || row - 2 >= 0, dn1 = kSteady || row + 1 < V, dn2 = kSteady || row + 2 < V;
+            // F = 0 + gravity*mass (unless pinned) + DEFAULT_DAMPING*V     V:451-459
+            OcPair3 F;
+            F.x = make_float2(pin_a ? 0.0f : c.f0[0], pin_b ? 0.0f : c.f0[0]);
+            F.y = make_float2(pin_a ? 0.0f : c.f0[1], pin_b ? 0.0f : c.f0[1]);
+            F.z = make_float2(pin_a ? 0.0f : c.f0[2], pin_b ? 0.0f : c.f0[2]);
+            F.x = p_add(F.x, p_mulm<M>(p_bc(c.damping), me.v.x));
+            F.y = p_add(F.y, p_mulm<M>(p_bc(c.damping), me.v.y));
+            F.z = p_add(F.z, p_mulm<M>(p_bc(c.damping), me.v.z));
+            // 1  (i-1, j): a <- b of the previous thread (shared), b <- a (own pair, first half)
+            {
+                const bool p = ea && al1, q = eb && bl1;
+                if (kAll || p) { F.x.x = M::sub(F.x.x, s.FH1[0][h][i]); F.y.x = M::sub(F.y.x, s.FH1[1][h][i]); F.z.x = M::sub(F.z.x, s.FH1[2][h][i]); }
+                if (kAll || q) { F.x.y = M::sub(F.x.y, gH1.x.x); F.y.y = M::sub(F.y.y, gH1.y.x); F.z.y = M::sub(F.z.y, gH1.z.x); }
+            }
+            oc_acc2<M, kAll>(F, gH1, ea && ar1, eb && br1, false);                                  // 2  (i+1, j)
+            oc_acc2<M, kAll>(F, k1,  ea && up1, eb && up1, true);                                   // 3  (i, j-1)
+            oc_acc2<M, kAll>(F, gV1, ea && dn1, eb && dn1, false);                                  // 4  (i, j+1)
+            // 5  (i-1, j-1): a <- b_prev at row-1 (shared), b <- a at row-1 (carried)
+            {
+                const bool p = ea && al1 && up1, q = eb && bl1 && up1;
+                if (kAll || p) { F.x.x = M::sub(F.x.x, s.FDb[0][s3][i]); F.y.x = M::sub(F.y.x, s.FDb[1][s3][i]); F.z.x = M::sub(F.z.x, s.FDb[2][s3][i]); }
+                if (kAll || q) { F.x.y = M::sub(F.x.y, kDa.x); F.y.y = M::sub(F.y.y, kDa.y); F.z.y = M::sub(F.z.y, kDa.z); }
+            }
+            // 6  (i+1, j-1): a <- b at row-1 (carried), b <- a_next at row-1 (shared)
+            {
+                const bool p = ea && ar1 && up1, q = eb && br1 && up1;
+                if (kAll || p) { F.x.x = M::sub(F.x.x, kAb.x); F.y.x = M::sub(F.y.x, kAb.y); F.z.x = M::sub(F.z.x, kAb.z); }
+                if (kAll || q) { F.x.y = M::sub(F.x.y, s.FAa[0][s3][i + 2]); F.y.y = M::sub(F.y.y, s.FAa[1][s3][i + 2]); F.z.y = M::sub(F.z.y, s.FAa[2][s3][i + 2]); }
+            }
+            oc_acc2<M, kAll>(F, gA, ea && al1 && dn1, eb && bl1 && dn1, false);                     // 7  (i-1, j+1)
+            oc_acc2<M, kAll>(F, gD, ea && ar1 && dn1, eb && br1 && dn1, false);                     // 8  (i+1, j+1)
+            OcPair3 r2;                                                                             // 9  (i-2, j)
+            r2.x = *reinterpret_cast<const float2*>(&s.FH2[0][h][pa - 2]);
+            r2.y = *reinterpret_cast<const float2*>(&s.FH2[1][h][pa - 2]);
+            r2.z = *reinterpret_cast<const float2*>(&s.FH2[2][h][pa - 2]);
+            oc_acc2<M, kAll>(F, r2,  ea && al2, eb && bl2, true);
+            oc_acc2<M, kAll>(F, gH2, ea && ar2, eb && br2, false);                                  // 10 (i+2, j)
+            if (!kAll) {                                                                            // 11 duplicated last bend spring of the row (V:313)
+                oc_acc2<M, false>(F, gH2, ea && ga == U - 3, eb && gb == U - 3, false);
+                oc_acc2<M, false>(F, r2,  ea && ga == U - 1, eb && gb == U - 1, true);
+            }
+            oc_acc2<M, kAll>(F, k2b, ea && up2, eb && up2, true);                                   // 12 (i, j-2)
+            oc_acc2<M, kAll>(F, gV2, ea && dn2, eb && dn2, false);                                  // 13 (i, j+2)
+            if (!kSteady) {                                                                         // 14 duplicated last bend spring of the column (V:319)
+                oc_acc2<M, false>(F, gV2, ea && row == V - 3, eb && row == V - 3, false);
+                oc_acc2<M, false>(F, k2b, ea && row == V - 1, eb && row == V - 1, true);
+            }
+            // ---- IntegrateVerlet (V:428-444) + EllipsoidCollision (V:509-533), both particles ----------
+            OcPair3 n;
+            n.x = p_add(p_add(me.x.x, dme.x), p_mulm<M>(p_bc(c.dt2m), F.x));
+            n.y = p_add(p_add(me.x.y, dme.y), p_mulm<M>(p_bc(c.dt2m), F.y));
+            n.z = p_add(p_add(me.x.z, dme.z), p_mulm<M>(p_bc(c.dt2m), F.z));
+            if (n.y.x < 0.0f) n.y.x = 0.0f;
+            if (n.y.y < 0.0f) n.y.y = 0.0f;
+            OcPair3 p0;         // X_0 = inverse_ellipsoid * vec4(X,1) - center, rows x, y, z for (a, b)
+            p0.x = p_sub(p_add(p_add(p_add(p_mulm<M>(p_bc(c.im[0][0]), n.x), p_mulm<M>(p_bc(c.im[0][1]), n.y)), p_mulm<M>(p_bc(c.im[0][2]), n.z)), p_bc(c.im[0][3])), p_bc(c.center[0]));
+            p0.y = p_sub(p_add(p_add(p_add(p_mulm<M>(p_bc(c.im[1][0]), n.x), p_mulm<M>(p_bc(c.im[1][1]), n.y)), p_mulm<M>(p_bc(c.im[1][2]), n.z)), p_bc(c.im[1][3])), p_bc(c.center[1]));
+            p0.z = p_sub(p_add(p_add(p_add(p_mulm<M>(p_bc(c.im[2][0]), n.x), p_mulm<M>(p_bc(c.im[2][1]), n.y)), p_mulm<M>(p_bc(c.im[2][2]), n.z)), p_bc(c.im[2][3])), p_bc(c.center[2]));
+            const float2 sq = p_add(p_add(p_mulm<M>(p0.x, p0.x), p_mulm<M>(p0.y, p0.y)), p_mulm<M>(p0.z, p0.z));
+            bool hit_a = sq.x < 1.0f, hit_b = sq.y < 1.0f;                                           // V:513-514 (see oc_core.cuh)
+            if (hit_a | hit_b) {
+                for (int hh = 0; hh < 2; ++hh) {
+                    if (!(hh ? hit_b : hit_a)) continue;
+                    f3 d0 = hh ? make_f3(p0.x.y, p0.y.y, p0.z.y) : make_f3(p0.x.x, p0.y.x, p0.z.x);
+                    const float distance = M::sqrt(hh ? sq.y : sq.x);
+                    const float sc = M::sub(c.radius, distance);                                    // V:515
+                    if (M::kExact) d0 = make_f3(M::div(M::mul(sc, d0.x), distance), M::div(M::mul(sc, d0.y), distance), M::div(M::mul(sc, d0.z), distance));
+                    else { const float q = M::div(sc, distance); d0 = make_f3(q * d0.x, q * d0.y, q * d0.z); }
+                    const float ddx = M::dot(d0, make_f3(c.tinv[0][0], c.tinv[0][1], c.tinv[0][2]));     // V:520-528
+                    const float ddy = M::dot(d0, make_f3(c.tinv[1][0], c.tinv[1][1], c.tinv[1][2]));
+                    const float ddz = M::dot(d0, make_f3(c.tinv[2][0], c.tinv[2][1], c.tinv[2][2]));
+                    if (hh) { n.x.y = M::add(n.x.y, ddx); n.y.y = M::add(n.y.y, ddy); n.z.y = M::add(n.z.y, ddz); }
+                    else    { n.x.x = M::add(n.x.x, ddx); n.y.x = M::add(n.y.x, ddy); n.z.x = M::add(n.z.x, ddz); }
+                }
+            }
+            const long long o = goff + (long long)row * U;
+            if (sta) C[o]     = make_float4(n.x.x, n.y.x, n.z.x, oc_u2f(hit_a ? OC_W_HIT : OC_W_PLAIN));
+            if (stb) C[o + 1] = make_float4(n.x.y, n.y.y, n.z.y, oc_u2f(hit_b ? OC_W_HIT : OC_W_PLAIN));
+        }
+        if (doP) {
+            k2b = k2a; k2a = gV2; k1 = gV1;
+            kDa = make_f3(gD.x.x, gD.y.x, gD.z.x);
+            kAb = make_f3(gA.x.y, gA.y.y, gA.z.y);
+            me = w1; w1 = w2;
+        }
+
+        // ---- publish the loaded row ------------------------------------------------------------------
+        if (doL) {
+            oc_cp_async_wait();
+            const float4 laa = s.stage[0][i], lqa = s.stage[1][i], lab = s.stage[2][i], lqb = s.stage[3][i];
+            OcPair3 d;
+            d.x = make_float2(M::sub(laa.x, lqa.x), M::sub(lab.x, lqb.x));
+            d.y = make_float2(M::sub(laa.y, lqa.y), M::sub(lab.y, lqb.y));
+            d.z = make_float2(M::sub(laa.z, lqa.z), M::sub(lab.z, lqb.z));
+            if (oc_hit(laa.w)) { d.x.x = 0.0f; d.y.x = 0.0f; d.z.x = 0.0f; }       // X_last == X (V:530)
+            if (oc_hit(lab.w)) { d.x.y = 0.0f; d.y.y = 0.0f; d.z.y = 0.0f; }
+            OcPair3 v;
+#ifdef __CUDA_ARCH__
+            if (M::kExact) {
+                bool badv = (c.dt_bf == 0) | oc_bad_vel(d.x.x, OC_VEL_LO_BITS, OC_VEL_HI_BITS) | oc_bad_vel(d.x.y, OC_VEL_LO_BITS, OC_VEL_HI_BITS) |
+                            oc_bad_vel(d.y.x, OC_VEL_LO_BITS, OC_VEL_HI_BITS) | oc_bad_vel(d.y.y, OC_VEL_LO_BITS, OC_VEL_HI_BITS) |
+                            oc_bad_vel(d.z.x, OC_VEL_LO_BITS, OC_VEL_HI_BITS) | oc_bad_vel(d.z.y, OC_VEL_LO_BITS, OC_VEL_HI_BITS);
+                const float2 y = p_bc(ydt), nd = p_bc(-c.dt);
+                float2 q0 = p_mul(d.x, y); v.x = p_fma(y, p_fma(q0, nd, d.x), q0);
+                q0 = p_mul(d.y, y);        v.y = p_fma(y, p_fma(q0, nd, d.y), q0);
+                q0 = p_mul(d.z, y);        v.z = p_fma(y, p_fma(q0, nd, d.z), q0);
+                if (badv) {
+                    v.x = make_float2(M::div(d.x.x, c.dt), M::div(d.x.y, c.dt));
+                    v.y = make_float2(M::div(d.y.x, c.dt), M::div(d.y.y, c.dt));
+                    v.z = make_float2(M::div(d.z.x, c.dt), M::div(d.z.y, c.dt));
+                }
+            } else
+#endif
+            {
+                if (M::kExact) {
+                    v.x = make_float2(d.x.x / c.dt, d.x.y / c.dt); v.y = make_float2(d.y.x / c.dt, d.y.y / c.dt); v.z = make_float2(d.z.x / c.dt, d.z.y / c.dt);
+                } else {
+                    v.x = p_mul(d.x, p_bc(c.inv_dt)); v.y = p_mul(d.y, p_bc(c.inv_dt)); v.z = p_mul(d.z, p_bc(c.inv_dt));
+                }
+            }
+            *reinterpret_cast<float2*>(&s.X[0][sl][pa]) = make_float2(laa.x, lab.x);          // lrow = row + 4: same slot
+            *reinterpret_cast<float2*>(&s.X[1][sl][pa]) = make_float2(laa.y, lab.y);
+            *reinterpret_cast<float2*>(&s.X[2][sl][pa]) = make_float2(laa.z, lab.z);
+            *reinterpret_cast<float2*>(&s.X[3][sl][pa]) = v.x;
+            *reinterpret_cast<float2*>(&s.X[4][sl][pa]) = v.y;
+            *reinterpret_cast<float2*>(&s.X[5][sl][pa]) = v.z;
+            *reinterpret_cast<float2*>(&s.Dd[0][sl][pa]) = d.x;
+            *reinterpret_cast<float2*>(&s.Dd[1][sl][pa]) = d.y;
+            *reinterpret_cast<float2*>(&s.Dd[2][sl][pa]) = d.z;
+        }
+    }
+};
+
+template <class M, int WC, class Ctx>
+OC_HD void oc_march2_body(Ctx& ctx, const OcConst& c, const float4* __restrict__ A, const float4* __restrict__ B,
+                          float4* __restrict__ C, int ra, int rb, int RS, int x_halo)
+{
+    OcMarch2<M, WC, Ctx> m(ctx, c);
+    m.A = A; m.B = B; m.C = C;
+    m.sm = reinterpret_cast<OcSmem2<WC>*>(ctx.smem());
+    const int i = ctx.tid();
+    const int U = c.U, V = c.V;
+    const int W_out = WC - 2 * x_halo;
+    const int cx0 = ctx.bx() * W_out - x_halo;
+    const int ga = cx0 + 2 * i, gb = ga + 1;
+    const int r0 = ra + ctx.by() * RS;
+    const int r1 = (r0 + RS < rb) ? r0 + RS : rb;
+    m.i = i; m.pa = 2 * i + 2; m.ga = ga; m.U = U; m.V = V;
+    int lo = r0, hi = r1;
+    int plo = lo - 2; if (plo < 0) plo = 0;
+    int in_lo = plo, in_hi = hi + 2; if (in_hi > V) in_hi = V;
+    const int first = lo - 2;
+    const int n_it = r1 - first + OC_MARCH_LAG;
+    const int row0 = first - OC_MARCH_LAG;
+    m.lo = lo; m.hi = hi; m.plo = plo; m.in_lo = in_lo; m.in_hi = in_hi; m.first = first; m.row0 = row0;
+    m.oka = ga >= 0 && ga < U; m.okb = gb >= 0 && gb < U;
+    m.sta = m.oka && 2 * i >= x_halo && 2 * i < WC - x_halo;
+    m.stb = m.okb && 2 * i + 1 >= x_halo && 2 * i + 1 < WC - x_halo;
+    auto clampc = [&](int g) { return g < 0 ? 0 : (g >= U ? U - 1 : g); };
+    m.rh1 = make_float2(OC_LDG(c.rh1 + clampc(ga)), OC_LDG(c.rh1 + clampc(gb)));
+    m.rh2 = make_float2(OC_LDG(c.rh2 + clampc(ga)), OC_LDG(c.rh2 + clampc(gb)));
+    m.dx2ab = make_float2(OC_LDG(c.dx2 + clampc(ga)), OC_LDG(c.dx2 + clampc(gb)));
+    m.dx2ma = make_float2(OC_LDG(c.dx2 + clampc(ga - 1)), OC_LDG(c.dx2 + clampc(ga)));
+    m.ydt = oc_rcp_bf(c.dt);
+    m.goff = (long long)ctx.bz() * c.cloth_stride - (long long)c.row_lo * U + ga;
+    {
+        int r = row0 < 0 ? 0 : (row0 >= V ? V - 1 : row0);
+        m.rv1_n = OC_LDG(c.rv1 + r); m.rv2_n = OC_LDG(c.rv2 + r); m.dz2_n = OC_LDG(c.dz2 + r);
+    }
+    const float2 z2 = make_float2(0.f, 0.f);
+    m.me.x.x = m.me.x.y = m.me.x.z = m.me.v.x = m.me.v.y = m.me.v.z = z2;
+    m.w1 = m.me;
+    m.k1.x = m.k1.y = m.k1.z = z2; m.k2a = m.k1; m.k2b = m.k1;
+    m.kDa = m.kAb = make_f3(0.f, 0.f, 0.f);
+
+    // benign content for the pad columns / pad thread slots (never written by a particle)
+    {
+        OcSmem2<WC>& s = *m.sm;
+        constexpr int T = WC / 2;
+        for (int e = i; e < 6 * OC_RING * 4; e += T) {
+            const int comp = e / (OC_RING * 4), slot = (e / 4) % OC_RING, pc = e % 4;
+            const int col = pc < 2 ? pc : WC + pc;
+            s.X[comp][slot][col] = comp < 3 ? 1.0e3f + 8.0f * (float)col : 0.0f;
+            if (comp < 3) {
+                s.Dd[comp][slot][col] = 0.0f;
+                if (slot < 2) s.FH2[comp][slot][col] = 0.0f;
+                if (pc == 0 || pc == 3) {
+                    const int ti = pc == 0 ? 0 : T + 1;
+                    s.FDb[comp][slot][ti] = 0.0f; s.FAa[comp][slot][ti] = 0.0f;
+                    if (slot < 2) s.FH1[comp][slot][ti] = 0.0f;
+                }
+            }
+        }
+    }
+
+    // steady range: interior rows, all activities on, multiple of 4 iterations starting at row & 3 == 0
+    int st_lo = lo > plo + 1 ? lo : plo + 1; if (st_lo < 2) st_lo = 2;
+    int st_hi = hi < V - 3 ? hi : V - 3;
+    if (st_hi > in_hi - OC_MARCH_LAG) st_hi = in_hi - OC_MARCH_LAG;
+    int it_lo = st_lo - row0, it_hi = st_hi - row0;
+    if (it_lo < 0) it_lo = 0;
+    if (it_hi > n_it) it_hi = n_it;
+    while (it_lo < it_hi && ((row0 + it_lo) & (OC_RING - 1)) != 0) ++it_lo;
+    it_hi = it_lo + ((it_hi - it_lo) & ~(OC_RING - 1));
+    if (it_hi <= it_lo) it_lo = it_hi = n_it;
+    const bool interior = cx0 >= 2 && cx0 + WC + 2 <= U;          // CTA-uniform
+
+    int it = 0;
+    for (int phase = 0; phase < 2; ++phase) {
+        const int end = phase == 0 ? it_lo : n_it;
+        for (; it < end; ++it) m.template iter<false, false, -1>(it);
+        if (phase == 0) {
+            if (interior) {
+                for (; it < it_hi; ++it) m.template iter<true, true, -1>(it);
+            } else {
+                for (; it < it_hi; ++it) m.template iter<true, false, -1>(it);
+            }
+        }
+    }
+}
+
+#ifdef __CUDACC__
+#ifndef OC_CTAS_M2
+#define OC_CTAS_M2 4
+#endif
+template <class M, int WC>
+__global__ void __launch_bounds__(WC / 2, OC_CTAS_M2)
+oc_k_march2(OcConst c, const float4* __restrict__ A, const float4* __restrict__ B, float4* __restrict__ C,
+            int ra, int rb, int RS, int x_halo)
+{
+    OcDevCtx ctx;
+    oc_march2_body<M, WC, OcDevCtx>(ctx, c, A, B, C, ra, rb, RS, x_halo);
+}
+#endif
+
+// ---- host side (oc_march.cu) -------------------------------------------------------------------
+int  oc_march2_configure(int device);
+int  oc_march2_plan(const OcConst& c, int ra, int rb, int sm_count, int occ_hint, OcMarchPlan* plan);
+#ifdef __CUDACC__
+cudaError_t oc_march2_launch(const OcConst& c, bool exact, int ra, int rb, int sm_count,
+                             const float4* A, const float4* B, float4* C, cudaStream_t stream, int* n_launches);
+#endif

@@ -14,6 +14,7 @@
 #include "../../opencloth_b200/csrc/oc_host.h"
 #include "../../opencloth_b200/csrc/oc_gather.cuh"
 #include "../../opencloth_b200/csrc/oc_march.cuh"
+#include "../../opencloth_b200/csrc/oc_march2.cuh"
 
 #include <ucontext.h>
 #include <cstdlib>
@@ -188,6 +189,40 @@ static int emu_march_dispatch(EmuCloth* e, const OcLaunch& L, int TW, int RS)
     return -2;
 }
 
+template <class M, int WC>
+static int emu_march2(EmuCloth* e, const OcLaunch& L, int RS)
+{
+    const OcConst& k = e->k;
+    const int x_halo = (k.U <= WC) ? 0 : 2;
+    const int W_out = WC - 2 * x_halo;
+    const int nstrips = (k.U + W_out - 1) / W_out;
+    const int rows = L.rb - L.ra;
+    if (RS <= 0 || RS > rows) RS = rows;
+    const int nseg = (rows + RS - 1) / RS;
+    const float4* A = e->buf[L.src_a].data();
+    const float4* B = e->buf[L.src_b].data();
+    float4* C = e->buf[L.dst].data();
+    int rc = 0;
+    for (int bz = 0; bz < k.batch; ++bz)
+        for (int by = 0; by < nseg; ++by)
+            for (int bx = 0; bx < nstrips; ++bx) {
+                int ra = L.ra, rb = L.rb;
+                rc |= run_cta(WC / 2, bx, by, bz, sizeof(OcSmem2<WC>), [&](EmuCtx& ctx) {
+                    oc_march2_body<M, WC, EmuCtx>(ctx, k, A, B, C, ra, rb, RS, x_halo);
+                });
+            }
+    return rc;
+}
+template <class M>
+static int emu_march2_dispatch(EmuCloth* e, const OcLaunch& L, int WC, int RS)
+{
+    if (WC == 16)  return emu_march2<M, 16>(e, L, RS);
+    if (WC == 32)  return emu_march2<M, 32>(e, L, RS);
+    if (WC == 64)  return emu_march2<M, 64>(e, L, RS);
+    if (WC == 128) return emu_march2<M, 128>(e, L, RS);
+    return -2;
+}
+
 template <class M>
 static void emu_gather(EmuCloth* e, const OcLaunch& L)
 {
@@ -272,7 +307,7 @@ int emu_download(void* h, float* X, float* XL)
     return 0;
 }
 
-// kernel: 1 = gather, 2 = march.  k = substeps per launch, TW = column window, RS = rows per segment
+// kernel: 1 = gather, 2 = march, 3 = march2 (TW = window columns).  k = substeps per launch, TW = column window, RS = rows per segment
 // (0 = one segment).  Returns 0, -1 on a barrier-count mismatch, -2 unsupported variant, -3 halo exhausted.
 int emu_step(void* h, int n, int kernel, int exact, int k, int TW, int RS)
 {
@@ -285,7 +320,11 @@ int emu_step(void* h, int n, int kernel, int exact, int k, int TW, int RS)
         int kk = 1;
         if (kernel == 2) { int w = n < k ? n : k; kk = (TW == 16 && w <= 3) ? w : oc_host_pick_stages(w); }
         oc_host_next_launch(e->q, n, kk, L);
-        if (kernel == 2) {
+        if (kernel == 3) {
+            int r = exact ? emu_march2_dispatch<MathExact>(e, L, TW, RS) : emu_march2_dispatch<MathFast>(e, L, TW, RS);
+            if (r == -2) return -2;
+            rc |= r;
+        } else if (kernel == 2) {
             int r = exact ? emu_march_dispatch<MathExact>(e, L, TW, RS) : emu_march_dispatch<MathFast>(e, L, TW, RS);
             if (r == -2) return -2;
             rc |= r;

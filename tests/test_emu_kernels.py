@@ -11,7 +11,7 @@ import pytest
 import helpers
 from helpers import Emu, Oracle, bitwise_equal
 
-GATHER, MARCH = 1, 2
+GATHER, MARCH, MARCH2 = 1, 2, 3
 
 
 def run_pair(nx, ny, pre, steps, **kw):
@@ -50,6 +50,30 @@ MARCH_CASES = [
 @pytest.mark.parametrize("nx,ny,pre,steps,k,TW,RS", MARCH_CASES)
 def test_march_kernel_body(nx, ny, pre, steps, k, TW, RS):
     run_pair(nx, ny, pre, steps, kernel=MARCH, k=k, TW=TW, RS=RS)
+
+
+# two-columns-per-thread kernel: (nx, ny, pre, steps, window columns WC, rows per segment)
+MARCH2_CASES = [
+    (21, 21, 0, 20, 32, 0), (21, 21, 1800, 60, 32, 7), (21, 21, 1800, 30, 16, 5), (37, 23, 1900, 12, 16, 5), (37, 23, 1900, 12, 64, 0),
+    (64, 64, 2000, 8, 32, 10), (64, 64, 2000, 8, 64, 9), (70, 40, 1500, 8, 64, 13), (130, 20, 500, 4, 128, 7), (128, 24, 500, 4, 128, 0),
+    (3, 3, 5, 40, 16, 0), (5, 4, 5, 40, 16, 2), (4, 9, 5, 23, 16, 3), (33, 30, 1700, 10, 32, 11),
+]
+
+
+@pytest.mark.parametrize("nx,ny,pre,steps,WC,RS", MARCH2_CASES)
+def test_march2_kernel_body(nx, ny, pre, steps, WC, RS):
+    run_pair(nx, ny, pre, steps, kernel=MARCH2, k=1, TW=WC, RS=RS)
+
+
+@pytest.mark.parametrize("order", [1, 2])
+def test_march2_is_independent_of_thread_schedule(order):
+    L = helpers.emu_lib()
+    L.emu_set_order(order)
+    try:
+        run_pair(37, 23, 1900, 9, kernel=MARCH2, k=1, TW=16, RS=4)
+        run_pair(70, 40, 1500, 6, kernel=MARCH2, k=1, TW=64, RS=11)
+    finally:
+        L.emu_set_order(0)
 
 
 @pytest.mark.parametrize("order", [1, 2])

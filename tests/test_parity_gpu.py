@@ -30,6 +30,10 @@ def golden(name):
     return g, json.loads(bytes(g["meta"]).decode())
 
 
+def kid(m, kernel):
+    return {"march": m.OC_KERNEL_MARCH, "gather": m.OC_KERNEL_GATHER, "march2": m.OC_KERNEL_MARCH2}[kernel]
+
+
 def nbad(a, b):
     return int((helpers.bits(a) != helpers.bits(b)).any(1).sum())
 
@@ -38,12 +42,12 @@ def nbad(a, b):
 # golden vectors of the verbatim reference
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("name", ["grid_21x21.npz", "grid_37x23.npz", "grid_64x64.npz", "grid_256x256.npz"])
-@pytest.mark.parametrize("kernel,k", [("march", 1), ("march", 4), ("gather", 1)])
+@pytest.mark.parametrize("kernel,k", [("march", 1), ("march", 4), ("gather", 1), ("march2", 1)])
 def test_cuda_matches_reference_golden(name, kernel, k):
     g, meta = golden(name)
     nx, ny = meta["nx"], meta["ny"]
     m = oc()
-    c = m.Cloth(nx, ny, kernel=m.OC_KERNEL_MARCH if kernel == "march" else m.OC_KERNEL_GATHER, substeps_per_launch=k)
+    c = m.Cloth(nx, ny, kernel=kid(m, kernel), substeps_per_launch=k)
     step = 0
     for cp in meta["checkpoints"]:
         c.step(cp - step)
@@ -74,12 +78,12 @@ def test_energy_trajectory_matches_reference():
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("nx,ny,pre,steps", [(3, 3, 0, 300), (4, 7, 0, 300), (21, 21, 1650, 400), (37, 23, 1800, 300),
                                              (100, 61, 1500, 200), (129, 40, 800, 100), (300, 200, 600, 100), (1000, 37, 300, 50)])
-@pytest.mark.parametrize("kernel,k", [("march", 1), ("march", 2), ("march", 8), ("gather", 1)])
+@pytest.mark.parametrize("kernel,k", [("march", 1), ("march", 2), ("march", 8), ("gather", 1), ("march2", 1)])
 def test_cuda_matches_oracle_bitwise(nx, ny, pre, steps, kernel, k):
     m = oc()
     x0, xl0 = helpers.developed_state(nx, ny, pre)
     o = Oracle(nx, ny); o.set_state(x0, xl0); o.step(steps)
-    c = m.Cloth(nx, ny, kernel=m.OC_KERNEL_MARCH if kernel == "march" else m.OC_KERNEL_GATHER, substeps_per_launch=k)
+    c = m.Cloth(nx, ny, kernel=kid(m, kernel), substeps_per_launch=k)
     c.upload(x0, xl0)
     c.step(steps)
     x, xl = c.download()
@@ -111,8 +115,8 @@ def test_large_grid_matches_oracle_2048():
     n = 2048
     o = Oracle(n, n); o.step(20)
     ox, oxl = o.state()
-    for k in (1, 4):
-        c = m.Cloth(n, n, substeps_per_launch=k)
+    for k, kern in ((1, m.OC_KERNEL_MARCH), (4, m.OC_KERNEL_MARCH), (1, m.OC_KERNEL_MARCH2)):
+        c = m.Cloth(n, n, substeps_per_launch=k, kernel=kern)
         c.step(20)
         x, xl = c.download()
         assert bitwise_equal(x, ox) and bitwise_equal(xl, oxl), f"k={k}: {nbad(x, ox)} particles differ"
@@ -181,13 +185,17 @@ def test_floor_clamp_and_collider_are_exercised():
     m = oc()
     nx, ny = 48, 48
     kw = dict(gravity=(0.0, -0.5, 0.0))
-    o = Oracle(nx, ny, **kw); c = m.Cloth(nx, ny, substeps_per_launch=4, **kw)
-    o.step(1200); c.step(1200)
-    x, xl = c.download(); ox, oxl = o.state()
+    o = Oracle(nx, ny, **kw)
+    o.step(1200)
+    ox, oxl = o.state()
     assert (ox[:, 1] == 0.0).sum() > 0, "test does not reach the floor"
     assert int((ox == oxl).all(1).sum()) > 10, "test does not reach the collider"
-    assert bitwise_equal(x, ox) and bitwise_equal(xl, oxl)
-    c.close()
+    for kern, k in ((m.OC_KERNEL_MARCH, 4), (m.OC_KERNEL_MARCH2, 1)):
+        c = m.Cloth(nx, ny, substeps_per_launch=k, kernel=kern, **kw)
+        c.step(1200)
+        x, xl = c.download()
+        assert bitwise_equal(x, ox) and bitwise_equal(xl, oxl), f"kernel {kern}"
+        c.close()
 
 
 def test_batched_cloths_match_per_cloth_oracle():
@@ -202,8 +210,8 @@ def test_batched_cloths_match_per_cloth_oracle():
         rng = np.random.RandomState(1234 + b)
         X0[b] = base
         X0[b, :, 1] += (1e-3 * rng.uniform(-1, 1, nx * ny)).astype(np.float32)
-    for k in (1, 4):
-        c = m.Cloth(nx, ny, batch=B, substeps_per_launch=k)
+    for k, kern in ((1, m.OC_KERNEL_MARCH), (4, m.OC_KERNEL_MARCH), (1, m.OC_KERNEL_MARCH2)):
+        c = m.Cloth(nx, ny, batch=B, substeps_per_launch=k, kernel=kern)
         c.upload(X0.reshape(-1, 3), X0.reshape(-1, 3))
         c.step(60)
         x, xl = c.download()
@@ -215,8 +223,8 @@ def test_batched_cloths_match_per_cloth_oracle():
         c.close()
 
 
-@pytest.mark.parametrize("nbands,halo,k", [(2, 4, 1), (4, 8, 4), (3, 16, 8), (8, 8, 2)])
-def test_row_bands_single_process_equal_whole_cloth(nbands, halo, k):
+@pytest.mark.parametrize("nbands,halo,k,kern", [(2, 4, 1, 2), (4, 8, 4, 2), (3, 16, 8, 2), (8, 8, 2, 2), (4, 8, 1, 3)])
+def test_row_bands_single_process_equal_whole_cloth(nbands, halo, k, kern):
     """SURVEY.md 8(e) on one device: g band handles exchanging halos with oc_halo_exchange
     (device-to-device copies ordered by events) must equal the undivided cloth bitwise."""
     import ctypes
@@ -228,7 +236,7 @@ def test_row_bands_single_process_equal_whole_cloth(nbands, halo, k):
     cuts = [round(ny * b / nbands) for b in range(nbands + 1)]
     bands = []
     for b in range(nbands):
-        c = m.Cloth(nx, ny, row_begin=cuts[b], row_end=cuts[b + 1], halo_rows=halo, substeps_per_launch=k)
+        c = m.Cloth(nx, ny, row_begin=cuts[b], row_end=cuts[b + 1], halo_rows=halo, substeps_per_launch=k, kernel=kern)
         sl = slice(cuts[b] * nx, cuts[b + 1] * nx)
         c.upload(x0[sl], xl0[sl])
         assert c.halo_budget == 0
