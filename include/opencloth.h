@@ -43,7 +43,7 @@ typedef enum oc_status {
 } oc_status;
 
 typedef enum oc_kernel {
-    OC_KERNEL_AUTO = 0,      /* marching stencil kernel where the grid allows, else gather */
+    OC_KERNEL_AUTO = 0,      /* march2 for one substep per launch, march for k > 1 */
     OC_KERNEL_GATHER = 1,    /* one thread per particle, 12-neighbour gather from global memory */
     OC_KERNEL_MARCH = 2,     /* fused shared-memory marching stencil, one column per thread, k substeps per launch */
     OC_KERNEL_MARCH2 = 3     /* the same with two columns per thread (one substep per launch) */

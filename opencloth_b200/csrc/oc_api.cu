@@ -409,7 +409,8 @@ extern "C" int oc_set_particle(oc_cloth* c, int cloth, int idx, const float xyz[
 static int pick_kernel(const oc_cloth* c)
 {
     if (c->p.kernel != OC_KERNEL_AUTO) return c->p.kernel;
-    return OC_KERNEL_MARCH;
+    // one substep per launch: the two-columns-per-thread kernel (fastest); k > 1: the staged one-column kernel
+    return c->p.substeps_per_launch <= 1 ? OC_KERNEL_MARCH2 : OC_KERNEL_MARCH;
 }
 
 extern "C" int oc_step(oc_cloth* c, int n)

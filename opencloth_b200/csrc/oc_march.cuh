@@ -43,6 +43,7 @@ struct OcStageSmem {
     float4 D[OC_RING][TW + 4];      // X - X_last (w unused), read by the owning column only
     float  FH[6][2][TW + 4];        // f(+1,0).xyz, f(+2,0).xyz of row (row & 1): force ON the publishing
     float  FD[6][OC_RING][TW + 4];  // f(+1,+1).xyz, f(-1,+1).xyz of row (row & 3)   particle; the partner SUBTRACTS it
+    float4 stage[2][TW];            // landing zone of stage 0's asynchronous row loads: A[col], B[col] per thread
 };
 
 #ifdef __CUDA_ARCH__
@@ -175,19 +176,21 @@ struct OcMarch {
         Smem& in = rings[s];
         const int row = row0 + it;                                // row this stage works on
         const int lrow = first + it;                              // row stage 0 loads
-        // ---- stage 0: issue the global loads of row lrow early -------------------------------------
+        // ---- stage 0: request row lrow asynchronously (LDGSTS into the thread's landing zone) ---------
         // (columns of the window that lie outside the cloth publish a benign far-away particle at rest, so
         // that the lanes next to them stay inside the operand range of the branch-free sequences)
-        float4 la, lq;
         const bool doL = (s == 0) && (kSteady || (lrow >= in_lo && lrow < in_hi));
         if (doL) {
+            Smem& st = rings[0];
+            const int li = ci - 2;
             if (col_ok) {
                 const long long o = goff + (long long)lrow * U;
-                la = A[o]; lq = B[o];
+                oc_cp_async16(&st.stage[0][li], A + o); oc_cp_async16(&st.stage[1][li], B + o);
             } else {
                 // distinct per column and row: the springs between two such particles must not be degenerate
-                la = lq = make_float4(1.0e3f + 8.0f * (float)ci, 1.0e3f, 1.0e3f + 8.0f * (float)(lrow & 63), oc_u2f(OC_W_PLAIN));
+                st.stage[0][li] = st.stage[1][li] = make_float4(1.0e3f + 8.0f * (float)ci, 1.0e3f, 1.0e3f + 8.0f * (float)(lrow & 63), oc_u2f(OC_W_PLAIN));
             }
+            oc_cp_async_commit();
         }
         const float rv1_j = rv1_n, rv2_j = rv2_n, dz2_j = dz2_n;
         {
@@ -308,9 +311,9 @@ struct OcMarch {
         }
 
         // ---- stage 0: publish the loaded row into its own ring --------------------------------------
-        // (the register fence sits here, not right after the barrier: the loads get the whole iteration to land)
         if (doL) {
-            OC_KEEP4(la); OC_KEEP4(lq);
+            oc_cp_async_wait();
+            const float4 la = rings[0].stage[0][ci - 2], lq = rings[0].stage[1][ci - 2];
             float2 dxy = p_sub(make_float2(la.x, la.y), make_float2(lq.x, lq.y));
             float dz = M::sub(la.z, lq.z);
             if (oc_hit(la.w)) { dxy = p_bc(0.0f); dz = 0.0f; }                   // X_last == X (V:530)

@@ -472,8 +472,13 @@ OC_HD void oc_march2_body(Ctx& ctx, const OcConst& c, const float4* __restrict__
 #ifndef OC_CTAS_M2
 #define OC_CTAS_M2 4
 #endif
+#ifdef OC_M2_MAXNREG
+#define OC_M2_BOUNDS __maxnreg__(OC_M2_MAXNREG)
+#else
+#define OC_M2_BOUNDS __launch_bounds__(WC / 2, OC_CTAS_M2)
+#endif
 template <class M, int WC>
-__global__ void __launch_bounds__(WC / 2, OC_CTAS_M2)
+__global__ void OC_M2_BOUNDS
 oc_k_march2(OcConst c, const float4* __restrict__ A, const float4* __restrict__ B, float4* __restrict__ C,
             int ra, int rb, int RS, int x_halo)
 {
