@@ -268,7 +268,7 @@ def run_ours(args):
                 "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic (closed-form flat sheet of InitGL V:254-260, reference parameters; state larger than L2)",
                 "config": {"workload": workload_name(args), "mode": args.mode + (" (bit-identical to the reference CPU path)" if exact else " (FMA/rsqrt, within 1e-5 / 1e-3 of extent)"),
-                           "substeps_per_launch": args.k, "kernel": "oc_k_march (fused stencil, packed FP32x2)",
+                           "substeps_per_launch": args.k, "kernel": "oc_k_march2 (fused marching stencil, 2 columns/thread, packed FP32x2)" if args.k <= 1 else "oc_k_march (staged, k substeps per launch)",
                            "l2": "state 48 B x particles per step > 126 MB L2 (no flush needed)" if particles_total * 48 > 126e6 else "state fits L2",
                            "halo_rows": args.halo_rows if band is not None else 0},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -409,6 +409,8 @@ extern "C" int oc_set_particle(oc_cloth* c, int cloth, int idx, const float xyz[
 static int pick_kernel(const oc_cloth* c)
 {
     if (c->p.kernel != OC_KERNEL_AUTO) return c->p.kernel;
+    // tiny problems are latency bound by the row march (one barrier per row): the gather kernel is quicker
+    if ((long long)c->p.nx * c->p.ny * c->p.batch <= 2048 && c->p.substeps_per_launch <= 1) return OC_KERNEL_GATHER;
     // one substep per launch: the two-columns-per-thread kernel (fastest); k > 1: the staged one-column kernel
     return c->p.substeps_per_launch <= 1 ? OC_KERNEL_MARCH2 : OC_KERNEL_MARCH;
 }
