@@ -153,6 +153,51 @@ struct OcMarch2 {
         return r;
     }
 
+    // One loaded row (both columns) -> position, velocity (X - X_last)/dt and X - X_last, once, into ring slot sl
+    OC_HD void publish(int sl, const float4 laa, const float4 lqa, const float4 lab, const float4 lqb)
+    {
+        Smem& s = *sm;
+        OcPair3 d;
+        d.x = make_float2(M::sub(laa.x, lqa.x), M::sub(lab.x, lqb.x));
+        d.y = make_float2(M::sub(laa.y, lqa.y), M::sub(lab.y, lqb.y));
+        d.z = make_float2(M::sub(laa.z, lqa.z), M::sub(lab.z, lqb.z));
+        if (oc_hit(laa.w)) { d.x.x = 0.0f; d.y.x = 0.0f; d.z.x = 0.0f; }       // X_last == X (V:530)
+        if (oc_hit(lab.w)) { d.x.y = 0.0f; d.y.y = 0.0f; d.z.y = 0.0f; }
+        OcPair3 v;
+#ifdef __CUDA_ARCH__
+        if (M::kExact) {
+            bool badv = (c.dt_bf == 0) | oc_bad_vel(d.x.x, OC_VEL_LO_BITS, OC_VEL_HI_BITS) | oc_bad_vel(d.x.y, OC_VEL_LO_BITS, OC_VEL_HI_BITS) |
+                        oc_bad_vel(d.y.x, OC_VEL_LO_BITS, OC_VEL_HI_BITS) | oc_bad_vel(d.y.y, OC_VEL_LO_BITS, OC_VEL_HI_BITS) |
+                        oc_bad_vel(d.z.x, OC_VEL_LO_BITS, OC_VEL_HI_BITS) | oc_bad_vel(d.z.y, OC_VEL_LO_BITS, OC_VEL_HI_BITS);
+            const float2 y = p_bc(ydt), nd = p_bc(-c.dt);
+            float2 q0 = p_mul(d.x, y); v.x = p_fma(y, p_fma(q0, nd, d.x), q0);
+            q0 = p_mul(d.y, y);        v.y = p_fma(y, p_fma(q0, nd, d.y), q0);
+            q0 = p_mul(d.z, y);        v.z = p_fma(y, p_fma(q0, nd, d.z), q0);
+            if (badv) {
+                v.x = make_float2(M::div(d.x.x, c.dt), M::div(d.x.y, c.dt));
+                v.y = make_float2(M::div(d.y.x, c.dt), M::div(d.y.y, c.dt));
+                v.z = make_float2(M::div(d.z.x, c.dt), M::div(d.z.y, c.dt));
+            }
+        } else
+#endif
+        {
+            if (M::kExact) {
+                v.x = make_float2(d.x.x / c.dt, d.x.y / c.dt); v.y = make_float2(d.y.x / c.dt, d.y.y / c.dt); v.z = make_float2(d.z.x / c.dt, d.z.y / c.dt);
+            } else {
+                v.x = p_mul(d.x, p_bc(c.inv_dt)); v.y = p_mul(d.y, p_bc(c.inv_dt)); v.z = p_mul(d.z, p_bc(c.inv_dt));
+            }
+        }
+        *reinterpret_cast<float2*>(&s.X[0][sl][pa]) = make_float2(laa.x, lab.x);          // lrow = row + 4: same slot
+        *reinterpret_cast<float2*>(&s.X[1][sl][pa]) = make_float2(laa.y, lab.y);
+        *reinterpret_cast<float2*>(&s.X[2][sl][pa]) = make_float2(laa.z, lab.z);
+        *reinterpret_cast<float2*>(&s.X[3][sl][pa]) = v.x;
+        *reinterpret_cast<float2*>(&s.X[4][sl][pa]) = v.y;
+        *reinterpret_cast<float2*>(&s.X[5][sl][pa]) = v.z;
+        *reinterpret_cast<float2*>(&s.Dd[0][sl][pa]) = d.x;
+        *reinterpret_cast<float2*>(&s.Dd[1][sl][pa]) = d.y;
+        *reinterpret_cast<float2*>(&s.Dd[2][sl][pa]) = d.z;
+    }
+
     template <bool kSteady, bool kInterior, int kSlot>
     OC_HD void iter(int it)
     {
@@ -336,46 +381,7 @@ struct OcMarch2 {
         // ---- publish the loaded row ------------------------------------------------------------------
         if (doL) {
             oc_cp_async_wait();
-            const float4 laa = s.stage[0][i], lqa = s.stage[1][i], lab = s.stage[2][i], lqb = s.stage[3][i];
-            OcPair3 d;
-            d.x = make_float2(M::sub(laa.x, lqa.x), M::sub(lab.x, lqb.x));
-            d.y = make_float2(M::sub(laa.y, lqa.y), M::sub(lab.y, lqb.y));
-            d.z = make_float2(M::sub(laa.z, lqa.z), M::sub(lab.z, lqb.z));
-            if (oc_hit(laa.w)) { d.x.x = 0.0f; d.y.x = 0.0f; d.z.x = 0.0f; }       // X_last == X (V:530)
-            if (oc_hit(lab.w)) { d.x.y = 0.0f; d.y.y = 0.0f; d.z.y = 0.0f; }
-            OcPair3 v;
-#ifdef __CUDA_ARCH__
-            if (M::kExact) {
-                bool badv = (c.dt_bf == 0) | oc_bad_vel(d.x.x, OC_VEL_LO_BITS, OC_VEL_HI_BITS) | oc_bad_vel(d.x.y, OC_VEL_LO_BITS, OC_VEL_HI_BITS) |
-                            oc_bad_vel(d.y.x, OC_VEL_LO_BITS, OC_VEL_HI_BITS) | oc_bad_vel(d.y.y, OC_VEL_LO_BITS, OC_VEL_HI_BITS) |
-                            oc_bad_vel(d.z.x, OC_VEL_LO_BITS, OC_VEL_HI_BITS) | oc_bad_vel(d.z.y, OC_VEL_LO_BITS, OC_VEL_HI_BITS);
-                const float2 y = p_bc(ydt), nd = p_bc(-c.dt);
-                float2 q0 = p_mul(d.x, y); v.x = p_fma(y, p_fma(q0, nd, d.x), q0);
-                q0 = p_mul(d.y, y);        v.y = p_fma(y, p_fma(q0, nd, d.y), q0);
-                q0 = p_mul(d.z, y);        v.z = p_fma(y, p_fma(q0, nd, d.z), q0);
-                if (badv) {
-                    v.x = make_float2(M::div(d.x.x, c.dt), M::div(d.x.y, c.dt));
-                    v.y = make_float2(M::div(d.y.x, c.dt), M::div(d.y.y, c.dt));
-                    v.z = make_float2(M::div(d.z.x, c.dt), M::div(d.z.y, c.dt));
-                }
-            } else
-#endif
-            {
-                if (M::kExact) {
-                    v.x = make_float2(d.x.x / c.dt, d.x.y / c.dt); v.y = make_float2(d.y.x / c.dt, d.y.y / c.dt); v.z = make_float2(d.z.x / c.dt, d.z.y / c.dt);
-                } else {
-                    v.x = p_mul(d.x, p_bc(c.inv_dt)); v.y = p_mul(d.y, p_bc(c.inv_dt)); v.z = p_mul(d.z, p_bc(c.inv_dt));
-                }
-            }
-            *reinterpret_cast<float2*>(&s.X[0][sl][pa]) = make_float2(laa.x, lab.x);          // lrow = row + 4: same slot
-            *reinterpret_cast<float2*>(&s.X[1][sl][pa]) = make_float2(laa.y, lab.y);
-            *reinterpret_cast<float2*>(&s.X[2][sl][pa]) = make_float2(laa.z, lab.z);
-            *reinterpret_cast<float2*>(&s.X[3][sl][pa]) = v.x;
-            *reinterpret_cast<float2*>(&s.X[4][sl][pa]) = v.y;
-            *reinterpret_cast<float2*>(&s.X[5][sl][pa]) = v.z;
-            *reinterpret_cast<float2*>(&s.Dd[0][sl][pa]) = d.x;
-            *reinterpret_cast<float2*>(&s.Dd[1][sl][pa]) = d.y;
-            *reinterpret_cast<float2*>(&s.Dd[2][sl][pa]) = d.z;
+            publish(sl, s.stage[0][i], s.stage[1][i], s.stage[2][i], s.stage[3][i]);      // lrow = row + 4: same slot
         }
     }
 };
