@@ -145,6 +145,12 @@ int oc_halo_recv_region(oc_cloth* c, int side, int which, void** dev_ptr, size_t
 int oc_halo_refreshed(oc_cloth* c);
 /* substeps that can still be taken before the next exchange is required */
 int oc_halo_budget(const oc_cloth* c);
+/* Like oc_step, for overlapping the halo exchange with compute.  If the n-th substep exhausts the halo budget
+ * (it then covers exactly the owned rows), it is issued as: the first and last halo_rows owned rows — the rows
+ * the neighbours are waiting for —, an event, then the interior; `exchange_stream` (cudaStream_t) is made to wait
+ * for that event, so an exchange enqueued on it runs concurrently with the interior launch.  *did_split tells
+ * whether the split happened (it does not for k > 1 launches or very small bands). */
+int oc_step_split(oc_cloth* c, int n, void* exchange_stream, int* did_split);
 /* Single-process exchange: bands[0..n) are the bands of ONE cloth in row order (same process, same
  * or different devices).  Copies every send region into the neighbour's halo (cudaMemcpyPeerAsync
  * across devices, i.e. NVLink on an HGX box), ordered after each band's queued work and before its

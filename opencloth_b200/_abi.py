@@ -70,6 +70,7 @@ SYMBOLS = {
     "oc_halo_recv_region": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, _P(ctypes.c_void_p), _P(ctypes.c_size_t)]),
     "oc_halo_refreshed": (ctypes.c_int, [ctypes.c_void_p]),
     "oc_halo_budget": (ctypes.c_int, [ctypes.c_void_p]),
+    "oc_step_split": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, _P(ctypes.c_int)]),
     "oc_halo_exchange": (ctypes.c_int, [_P(ctypes.c_void_p), ctypes.c_int]),
     "oc_debug_counters": (ctypes.c_int, [ctypes.c_void_p, _P(ctypes.c_ulonglong)]),
     "oc_sizeof_params": (ctypes.c_size_t, []),

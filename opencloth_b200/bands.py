@@ -59,6 +59,11 @@ class CudaBand:
     def step(self, n):
         self.cloth.step(n)
 
+    def step_split(self, n, side_stream):
+        """Advance n substeps; when this uses up the halo budget the last substep publishes its boundary rows
+        first and `side_stream` is made to wait for exactly those — returns True in that case."""
+        return self.cloth.step_split(n, side_stream.cuda_stream)
+
     def refreshed(self):
         self.cloth.halo_refreshed()
 
@@ -77,14 +82,21 @@ class BandDriver:
     exchange(): post the receives of both halos and the sends of the owned boundary rows as one
     batch of point-to-point operations (NCCL groups them; over gloo they are plain isend/irecv), wait,
     mark the halo current.  step(n): as many groups of `halo_rows/2` substeps as needed, one exchange
-    before each group.
+    before each group.  With overlap=True the exchange that follows a full group is started on a side
+    stream as soon as the group's last substep has produced its boundary rows (oc_step_split) and runs
+    concurrently with the interior of that substep; call finish() before reading the state.
     """
 
-    def __init__(self, band, rank, world, group=None):
+    def __init__(self, band, rank, world, group=None, overlap=False):
         self.band, self.rank, self.world, self.group = band, rank, world, group
         self.exchanges = 0
+        # overlap: start the exchange as soon as the boundary rows of the last substep of a group exist, on a
+        # side stream, while the interior of that substep is still being computed (CUDA bands only)
+        self.overlap = overlap and hasattr(band, "step_split") and torch.cuda.is_available()
+        self.side = torch.cuda.Stream(band.device) if self.overlap else None
+        self.pending = None
 
-    def exchange(self):
+    def _ops(self):
         ops = []
         for side, peer in ((0, self.rank - 1), (1, self.rank + 1)):
             if peer < 0 or peer >= self.world:
@@ -93,6 +105,20 @@ class BandDriver:
                 ops.append(dist.P2POp(dist.irecv, t, peer, self.group))
             for t in self.band.regions(side, send=True):
                 ops.append(dist.P2POp(dist.isend, t, peer, self.group))
+        return ops
+
+    def _finish_pending(self):
+        if self.pending is not None:
+            for w in self.pending:
+                w.wait()                      # the current (compute) stream waits for the exchange
+            self.pending = None
+            self.band.refreshed()
+            self.exchanges += 1
+
+    def exchange(self):
+        if self.pending is not None:
+            return self._finish_pending()
+        ops = self._ops()
         if ops:
             for w in dist.batch_isend_irecv(ops):
                 w.wait()
@@ -104,8 +130,22 @@ class BandDriver:
             if self.band.budget == 0:
                 self.exchange()
             m = min(n, self.band.budget)
-            self.band.step(m)
+            if self.overlap and m == self.band.budget:
+                # this group ends at an exchange point: boundary rows first, exchange on the side stream
+                if self.band.step_split(m, self.side):
+                    ops = self._ops()
+                    if ops:
+                        with torch.cuda.stream(self.side):
+                            self.pending = dist.batch_isend_irecv(ops)
+                    else:
+                        self.pending = []
+            else:
+                self.band.step(m)
             n -= m
+
+    def finish(self):
+        """Complete an exchange that is still in flight (call before reading the state)."""
+        self._finish_pending()
 
 
 def gather_rows(local_x, ny, nx, world, rank, group=None):

@@ -58,6 +58,12 @@ class Cloth:
         """n x StepPhysics(dt) (V:557-562). Asynchronous."""
         check(self._lib.oc_step(self._h, int(n)))
 
+    def step_split(self, n, exchange_stream_ptr):
+        """oc_step_split: the last substep's boundary rows first; returns True if `exchange_stream` now waits for them."""
+        did = ctypes.c_int(0)
+        check(self._lib.oc_step_split(self._h, int(n), ctypes.c_void_p(exchange_stream_ptr), ctypes.byref(did)))
+        return bool(did.value)
+
     def step_timed(self, n=1):
         """n substeps timed with CUDA events on the handle's stream; returns milliseconds."""
         ms = ctypes.c_float()

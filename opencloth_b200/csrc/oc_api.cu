@@ -415,8 +415,38 @@ static int pick_kernel(const oc_cloth* c)
     return c->p.substeps_per_launch <= 1 ? OC_KERNEL_MARCH2 : OC_KERNEL_MARCH;
 }
 
-extern "C" int oc_step(oc_cloth* c, int n)
+// one launch: rows [ra, rb) of the launch descriptor's destination, S substeps
+static int launch_rows(oc_cloth* c, int kern, const OcLaunch& L, int ra, int rb)
 {
+    if (rb <= ra) return OC_OK;
+    if (kern == OC_KERNEL_MARCH2) {
+        int nl = 0;
+        cudaError_t e = oc_march2_launch(c->k, c->p.exact != 0, ra, rb, c->sm_count,
+                                         c->buf[L.src_a], c->buf[L.src_b], c->buf[L.dst], c->stream, &nl);
+        c->launches += nl;
+        if (e != cudaSuccess) return oc_fail(OC_ERR_CUDA, "march2 kernel launch failed: %s", cudaGetErrorString(e));
+    } else if (kern == OC_KERNEL_MARCH) {
+        int nl = 0;
+        cudaError_t e = oc_march_launch(c->k, c->p.exact != 0, L.S, ra, rb, c->sm_count,
+                                        c->buf[L.src_a], c->buf[L.src_b], c->buf[L.dst], c->buf[L.dst_prev], c->stream, &nl);
+        c->launches += nl;
+        if (e != cudaSuccess) return oc_fail(OC_ERR_CUDA, "march kernel launch failed: %s", cudaGetErrorString(e));
+    } else {
+        dim3 blk(128, 1, 1), grd((c->p.nx + 127) / 128, rb - ra, c->p.batch);
+        if (c->p.exact) oc_k_gather<MathExact><<<grd, blk, 0, c->stream>>>(c->k, c->buf[L.src_a], c->buf[L.src_b], c->buf[L.dst], ra);
+        else            oc_k_gather<MathFast><<<grd, blk, 0, c->stream>>>(c->k, c->buf[L.src_a], c->buf[L.src_b], c->buf[L.dst], ra);
+        c->launches++;
+        OC_CUDA(cudaGetLastError());
+    }
+    return OC_OK;
+}
+
+// n substeps; if split_stream != nullptr and the last substep is a single-substep launch over exactly the
+// owned rows of a band, that launch is issued as boundary rows first (the rows the neighbours need), an
+// event, then the interior, and split_stream is made to wait for the event.
+static int step_impl(oc_cloth* c, int n, cudaStream_t split_stream, bool want_split, int* did_split)
+{
+    if (did_split) *did_split = 0;
     if (!c) return oc_fail(OC_ERR_INVALID, "oc_step: null");
     if (n < 0) return oc_fail(OC_ERR_INVALID, "oc_step: n < 0");
     if (c->q.band && c->q.fresh + n > c->q.kmax)
@@ -429,27 +459,30 @@ extern "C" int oc_step(oc_cloth* c, int n)
         const int kmaxS = (kern == OC_KERNEL_MARCH) ? oc_host_pick_stages(n < kdef ? n : kdef) : 1;
         OcLaunch L;
         oc_host_next_launch(c->q, n, kmaxS, L);
-        if (kern == OC_KERNEL_MARCH2) {
-            int nl = 0;
-            cudaError_t e = oc_march2_launch(c->k, c->p.exact != 0, L.ra, L.rb, c->sm_count,
-                                             c->buf[L.src_a], c->buf[L.src_b], c->buf[L.dst], c->stream, &nl);
-            c->launches += nl;
-            if (e != cudaSuccess) return oc_fail(OC_ERR_CUDA, "march2 kernel launch failed: %s", cudaGetErrorString(e));
-        } else if (kern == OC_KERNEL_MARCH) {
-            int nl = 0;
-            cudaError_t e = oc_march_launch(c->k, c->p.exact != 0, L.S, L.ra, L.rb, c->sm_count,
-                                            c->buf[L.src_a], c->buf[L.src_b], c->buf[L.dst], c->buf[L.dst_prev], c->stream, &nl);
-            c->launches += nl;
-            if (e != cudaSuccess) return oc_fail(OC_ERR_CUDA, "march kernel launch failed: %s", cudaGetErrorString(e));
+        const int H = c->p.halo_rows;
+        const bool split = want_split && n == 0 && c->q.band && L.S == 1 && L.ra == c->p.row_begin && L.rb == c->p.row_end &&
+                           (L.rb - L.ra) > 2 * H + 8;
+        int rc;
+        if (!split) {
+            rc = launch_rows(c, kern, L, L.ra, L.rb);
+            if (rc) return rc;
         } else {
-            dim3 blk(128, 1, 1), grd((c->p.nx + 127) / 128, L.rb - L.ra, c->p.batch);
-            if (c->p.exact) oc_k_gather<MathExact><<<grd, blk, 0, c->stream>>>(c->k, c->buf[L.src_a], c->buf[L.src_b], c->buf[L.dst], L.ra);
-            else            oc_k_gather<MathFast><<<grd, blk, 0, c->stream>>>(c->k, c->buf[L.src_a], c->buf[L.src_b], c->buf[L.dst], L.ra);
-            c->launches++;
-            OC_CUDA(cudaGetLastError());
+            rc = launch_rows(c, kern, L, L.ra, L.ra + H);          if (rc) return rc;
+            rc = launch_rows(c, kern, L, L.rb - H, L.rb);          if (rc) return rc;
+            OC_CUDA(cudaEventRecord(c->ev_ready, c->stream));
+            if (split_stream) OC_CUDA(cudaStreamWaitEvent(split_stream, c->ev_ready, 0));
+            rc = launch_rows(c, kern, L, L.ra + H, L.rb - H);      if (rc) return rc;
+            if (did_split) *did_split = 1;
         }
     }
     return OC_OK;
+}
+
+extern "C" int oc_step(oc_cloth* c, int n) { return step_impl(c, n, nullptr, false, nullptr); }
+
+extern "C" int oc_step_split(oc_cloth* c, int n, void* exchange_stream, int* did_split)
+{
+    return step_impl(c, n, (cudaStream_t)exchange_stream, true, did_split);
 }
 
 extern "C" int oc_step_timed(oc_cloth* c, int n, float* ms)

@@ -17,6 +17,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--nx", type=int, default=1024); ap.add_argument("--ny", type=int, default=1024)
 ap.add_argument("--steps", type=int, default=50); ap.add_argument("--halo", type=int, default=8)
 ap.add_argument("--k", type=int, default=2); ap.add_argument("--exact", type=int, default=1)
+ap.add_argument("--overlap", type=int, default=0)
 a = ap.parse_args()
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
@@ -26,7 +27,7 @@ stream = torch.cuda.Stream(dev)
 torch.cuda.set_stream(stream)
 band = B.CudaBand(a.nx, a.ny, world, rank, a.halo, local, exact=a.exact, substeps_per_launch=a.k)
 band.cloth.set_stream(stream.cuda_stream)
-drv = B.BandDriver(band, rank, world)
+drv = B.BandDriver(band, rank, world, overlap=bool(a.overlap))
 # non-trivial start: whole cloth advanced on every rank's own GPU first (deterministic), then cut
 whole = oc.Cloth(a.nx, a.ny, device=local, exact=a.exact, substeps_per_launch=4)
 whole.step(300)
@@ -34,6 +35,7 @@ x0, xl0 = whole.download()
 sl = slice(band.begin * a.nx, band.end * a.nx)
 band.cloth.upload(x0[sl], xl0[sl])
 drv.step(a.steps)
+drv.finish()
 x, xl = band.cloth.download()
 whole.step(a.steps)
 wx, wxl = whole.download()
@@ -41,7 +43,7 @@ ok = bool((x.view(np.uint32) == wx[sl].view(np.uint32)).all() and (xl.view(np.ui
 t = torch.tensor([1 if ok else 0], device=dev)
 dist.all_reduce(t, op=dist.ReduceOp.MIN)
 if rank == 0:
-    print("BAND_CHECK", "OK" if int(t.item()) == 1 else "MISMATCH", f"world={world} grid={a.nx}x{a.ny} steps={a.steps} halo={a.halo} k={a.k} exchanges={drv.exchanges}")
+    print("BAND_CHECK", "OK" if int(t.item()) == 1 else "MISMATCH", f"world={world} grid={a.nx}x{a.ny} steps={a.steps} halo={a.halo} k={a.k} overlap={a.overlap} exchanges={drv.exchanges}")
 dist.barrier()
 dist.destroy_process_group()
 sys.exit(0 if int(t.item()) == 1 else 1)
