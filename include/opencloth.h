@@ -169,6 +169,10 @@ int oc_selftest_math(unsigned long long n, unsigned int seed, unsigned long long
 /* Development counters (only counted when the environment has OC_DEBUG=4 at oc_create): lanes and warps
  * that took the IEEE-intrinsic fallback of the exact-mode spring phase, velocity fallbacks; reset on read. */
 int oc_debug_counters(oc_cloth* c, unsigned long long out[4]);
+/* Development CTA time line of the last oc_k_march2 launch (only recorded with OC_DEBUG=8 at oc_create): 8 words
+ * per CTA (linear index x + gridDim.x * (y + gridDim.y * z), first 4096 CTAs): %globaltimer at entry, set-up
+ * done, lead-in done, steady loop done, exit; SM id; 2 unused.  Copies min(n_words, 8*4096) words. */
+int oc_debug_timeline(oc_cloth* c, unsigned long long* out, size_t n_words);
 /* sizeof(oc_params) as the library was compiled, so that FFI bindings can verify their mirror */
 size_t oc_sizeof_params(void);
 /* library / device info string: "opencloth_b200 abi=1 sm=100 device=NVIDIA B200 ..." */

@@ -259,8 +259,8 @@ extern "C" int oc_create(oc_cloth** out, const oc_params* p)
 
     for (int b = 0; b < 4; ++b) OC_CREATE_CUDA(cudaMalloc(&c->buf[b], (size_t)c->stored * sizeof(float4)));
     OC_CREATE_CUDA(cudaMalloc(&c->d_energy, sizeof(double)));
-    OC_CREATE_CUDA(cudaMalloc(&c->d_dbg, 4 * sizeof(unsigned long long)));
-    OC_CREATE_CUDA(cudaMemset(c->d_dbg, 0, 4 * sizeof(unsigned long long)));
+    OC_CREATE_CUDA(cudaMalloc(&c->d_dbg, OC_DBG_WORDS * sizeof(unsigned long long)));
+    OC_CREATE_CUDA(cudaMemset(c->d_dbg, 0, OC_DBG_WORDS * sizeof(unsigned long long)));
     k.dbg_cnt = c->d_dbg;
     OC_CREATE_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
@@ -604,7 +604,7 @@ __device__ __forceinline__ float oc_rand_float(unsigned long long& st, int elo, 
     if (neg_ok && (r & 0x80000000u)) bits |= 0x80000000u;
     return __uint_as_float(bits);
 }
-__global__ void oc_k_selftest(unsigned long long per_thread, unsigned seed, float dt, unsigned long long* out)
+__global__ void oc_k_selftest(unsigned long long per_thread, unsigned seed, float dt, unsigned long long* out, float one)
 {
     unsigned long long st = ((unsigned long long)seed << 32) ^ (0x9E3779B97F4A7C15ULL * (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x + 1));
     unsigned long long bad_count = 0;
@@ -673,7 +673,7 @@ __global__ void oc_k_selftest(unsigned long long per_thread, unsigned seed, floa
             qv.x = make_float2(av.x, bv.x); qv.y = make_float2(av.y, bv.y); qv.z = make_float2(av.z, bv.z);
             const float ra = jitter(0.2828f, 1e-4f), rb = jitter(0.2828f, 1e-4f);
             bool b4 = false;
-            const OcPair3 g = oc_spring2<MathExact>(mx, mv, qx, qv, make_float2(ra, rb), p_bc(-50.75f), p_bc(-0.25f), b4);
+            const OcPair3 g = oc_spring2<MathExact>(mx, mv, qx, qv, make_float2(ra, rb), p_bc(-50.75f), p_bc(-0.25f), one, b4);
             const f3 fa = oc_spring<MathExact>(mx, mv, ax, av, ra, -50.75f, -0.25f);
             const f3 fb = oc_spring<MathExact>(mx, mv, bx, bv, rb, -50.75f, -0.25f);
             if (!b4) {
@@ -694,7 +694,7 @@ extern "C" int oc_selftest_math(unsigned long long n, unsigned int seed, unsigne
     unsigned long long per = (n + (unsigned long long)blocks * threads - 1) / ((unsigned long long)blocks * threads);
     const float dts[4] = { 1 / 60.0f, 1 / 90.0f, 0.001f, 0.37f };
     for (int t = 0; t < 4; ++t) {
-        oc_k_selftest<<<blocks, threads>>>((per + 3) / 4, seed + t, dts[t], d);
+        oc_k_selftest<<<blocks, threads>>>((per + 3) / 4, seed + t, dts[t], d, 1.0f);
         OC_CUDA(cudaGetLastError());
     }
     OC_CUDA(cudaMemcpy(mismatches, d, sizeof(*d), cudaMemcpyDeviceToHost));
@@ -709,6 +709,16 @@ extern "C" int oc_debug_counters(oc_cloth* c, unsigned long long out[4])
     OC_CUDA(cudaStreamSynchronize(c->stream));
     OC_CUDA(cudaMemcpy(out, c->d_dbg, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     OC_CUDA(cudaMemset(c->d_dbg, 0, 4 * sizeof(unsigned long long)));
+    return OC_OK;
+}
+
+extern "C" int oc_debug_timeline(oc_cloth* c, unsigned long long* out, size_t n_words)
+{
+    if (!c || !out) return oc_fail(OC_ERR_INVALID, "oc_debug_timeline: null");
+    if (n_words > (size_t)8 * OC_DBG_TL_CTAS) n_words = (size_t)8 * OC_DBG_TL_CTAS;
+    OC_CUDA(cudaSetDevice(c->dev));
+    OC_CUDA(cudaStreamSynchronize(c->stream));
+    OC_CUDA(cudaMemcpy(out, c->d_dbg + OC_DBG_TL_BASE, n_words * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     return OC_OK;
 }
 

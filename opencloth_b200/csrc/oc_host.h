@@ -52,6 +52,7 @@ static inline void oc_host_derive_scalars(const oc_params& p, OcConst& k)
 {
     k.dt = p.dt;
     k.inv_dt = 1.0f / p.dt;
+    k.one = 1.0f;
     k.dt_bf = (p.dt >= 0x1.0p-20f && p.dt <= 0x1.0p+20f) ? 1 : 0;
     { const char* e = getenv("OC_DEBUG"); k.dbg = e ? atoi(e) : 0; }
     k.dt2m = (p.dt * p.dt) / p.mass;                                  // V:429

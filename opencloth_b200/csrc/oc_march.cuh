@@ -222,9 +222,9 @@ struct OcMarch {
             const float2 nksS = p_bc(c.nks_shear), kdS = p_bc(c.kd_shear);
             if (!M::kExact) { rH = p_mul(rH, nksHV); rV = p_mul(rV, nksHV); rS = p_mul(rS, nksS); }
             unsigned cls = 0;
-            gH = oc_spring2<M>(mx, mv, nH.x, nH.v, rH, nksHV, kdHV, bad, &cls);
-            gV = oc_spring2<M>(mx, mv, nV.x, nV.v, rV, nksHV, kdHV, bad, &cls);
-            gS = oc_spring2<M>(mx, mv, nS.x, nS.v, rS, nksS,  kdS,  bad, &cls);
+            gH = oc_spring2<M>(mx, mv, nH.x, nH.v, rH, nksHV, kdHV, c.one, bad, &cls);
+            gV = oc_spring2<M>(mx, mv, nV.x, nV.v, rV, nksHV, kdHV, c.one, bad, &cls);
+            gS = oc_spring2<M>(mx, mv, nS.x, nS.v, rS, nksS,  kdS,  c.one, bad, &cls);
 #if defined(OC_CLASSIFY) && defined(__CUDA_ARCH__)
             if (M::kExact && (c.dbg & 4) && col_store && row >= lo_s && row < hi_s) {
                 if (cls & 1u) atomicAdd(c.dbg_cnt + 3, 1ull);                       // -0 numerator
@@ -258,7 +258,7 @@ struct OcMarch {
             OcF F;
             F.xy = pinned ? p_bc(0.0f) : make_float2(c.f0[0], c.f0[1]);
             F.z  = pinned ? 0.0f : c.f0[2];
-            F.xy = p_add(F.xy, p_mulm<M>(p_bc(c.damping), make_float2(mv.x, mv.y)));
+            F.xy = p_sump<M>(p_mul(p_bc(c.damping), make_float2(mv.x, mv.y)), F.xy, c.one);
             F.z  = M::add(F.z, M::mul(c.damping, mv.z));
             if (!pinned) {
                 const bool up1 = kSteady || row - 1 >= 0, up2 = kSteady || row - 2 >= 0;

@@ -35,29 +35,29 @@ struct OcSmem2 {
 // ---- spring pair with a pair-valued first end (particles a and b of the thread) ----------------------
 template <class M>
 OC_HD OcPair3 oc_spring2v(const OcPair3& px, const OcPair3& pv, const OcPair3& qx, const OcPair3& qv,
-                          float2 rest, float2 nks, float2 kd, bool& bad)
+                          float2 rest, float2 nks, float2 kd, float one, bool& bad)
 {
     OcPair3 dp, dv, f;
     dp.x = p_sub(px.x, qx.x); dp.y = p_sub(px.y, qx.y); dp.z = p_sub(px.z, qx.z);                     // V:471
     dv.x = p_sub(pv.x, qv.x); dv.y = p_sub(pv.y, qv.y); dv.z = p_sub(pv.z, qv.z);                     // V:472
     if (M::kExact) {
-        const float2 sqr  = p_add(p_add(p_mulx(dp.x, dp.x), p_mulx(dp.y, dp.y)), p_mulx(dp.z, dp.z));
+        const float2 sqr  = p_sump<M>(p_mul(dp.z, dp.z), p_sump<M>(p_mul(dp.y, dp.y), p_mul(dp.x, dp.x), one), one);
         const float2 dist = oc_sqrt2<M>(sqr, bad);                                                   // V:473
 #ifdef __CUDA_ARCH__
         const float2 y0  = p_rcp(dist);
         const float2 inv = p_fma(y0, p_fma(y0, p_neg(dist), p_bc(1.0f)), y0);
-        const float2 a   = p_add(p_add(p_mulx(dv.x, dp.x), p_mulx(dv.y, dp.y)), p_mulx(dv.z, dp.z));
+        const float2 a   = p_sump<M>(p_mul(dv.z, dp.z), p_sump<M>(p_mul(dv.y, dp.y), p_mul(dv.x, dp.x), one), one);
         bad |= oc_bad_num(a.x, OC_NUM_LO_BITS, OC_NUM_HI_BITS) | oc_bad_num(a.y, OC_NUM_LO_BITS, OC_NUM_HI_BITS);
         const float2 q0  = p_mul(a, inv);
         const float2 q   = p_fma(inv, p_fma(q0, p_neg(dist), a), q0);
 #else
         const float2 inv = make_float2(1.0f / dist.x, 1.0f / dist.y);
-        const float2 a   = p_add(p_add(p_mulx(dv.x, dp.x), p_mulx(dv.y, dp.y)), p_mulx(dv.z, dp.z));
+        const float2 a   = p_sump<M>(p_mul(dv.z, dp.z), p_sump<M>(p_mul(dv.y, dp.y), p_mul(dv.x, dp.x), one), one);
         const float2 q   = make_float2(a.x / dist.x, a.y / dist.y);
 #endif
-        const float2 left  = p_mulx(nks, p_sub(dist, rest));                                         // V:475
-        const float2 right = p_mulx(kd, q);                                                          // V:476
-        const float2 s = p_add(left, right);
+        const float2 left  = p_mul(nks, p_sub(dist, rest));                                          // V:475
+        const float2 right = p_mul(kd, q);                                                           // V:476
+        const float2 s = p_sump<M>(right, left, one);
         f.x = p_mul(s, p_mul(dp.x, inv)); f.y = p_mul(s, p_mul(dp.y, inv)); f.z = p_mul(s, p_mul(dp.z, inv));   // V:477
     } else {
         const float2 sqr  = p_fma(dp.z, dp.z, p_fma(dp.y, dp.y, p_mul(dp.x, dp.x)));
@@ -105,11 +105,12 @@ OcPair3 oc_march2_redo(const OcSmem2<WC>* s, int kind, int sl, int pa, float res
 }
 
 // F (+|-)= g for both particles, or per half under predicates
-template <class M, bool kAll> OC_HD void oc_acc2(OcPair3& F, const OcPair3& g, bool pa, bool pb, bool sub)
+// (g is a packed product s * n: p_sump / p_subp keep ptxas from contracting it into the accumulation)
+template <class M, bool kAll> OC_HD void oc_acc2(OcPair3& F, const OcPair3& g, bool pa, bool pb, bool sub, float one)
 {
     if (kAll) {
-        if (sub) { F.x = p_sub(F.x, g.x); F.y = p_sub(F.y, g.y); F.z = p_sub(F.z, g.z); }
-        else     { F.x = p_add(F.x, g.x); F.y = p_add(F.y, g.y); F.z = p_add(F.z, g.z); }
+        if (sub) { F.x = p_subp<M>(F.x, g.x, one); F.y = p_subp<M>(F.y, g.y, one); F.z = p_subp<M>(F.z, g.z, one); }
+        else     { F.x = p_sump<M>(g.x, F.x, one); F.y = p_sump<M>(g.y, F.y, one); F.z = p_sump<M>(g.z, F.z, one); }
     } else {
         if (pa) {
             if (sub) { F.x.x = M::sub(F.x.x, g.x.x); F.y.x = M::sub(F.y.x, g.y.x); F.z.x = M::sub(F.z.x, g.z.x); }
@@ -138,8 +139,9 @@ struct OcMarch2 {
     float ydt;
     float rv1_n, rv2_n, dz2_n;
     long long goff;                          // element offset of (cloth, ga, row 0)
-    OcPV2 me, w1;                            // own columns, rows row and row+1
-    OcPair3 k1, k2a, k2b;                    // carried (0,+1) of row-1, (0,+2) of row-1 and row-2
+    // carried from iteration to iteration as 64-bit pairs (see oc_q2):
+    OcPair3q me_x, me_v, w1_x, w1_v;         // own columns, rows row and row+1
+    OcPair3q k1_q, k2a_q, k2b_q;             // carried (0,+1) of row-1, (0,+2) of row-1 and row-2
     f3 kDa, kAb;                             // carried internal shear forces of row-1: f(a->b'), f(b->a')
 
     OC_HD OcMarch2(Ctx& ctx_, const OcConst& c_) : ctx(ctx_), c(c_) {}
@@ -204,6 +206,9 @@ struct OcMarch2 {
         Smem& s = *sm;
         const int row = row0 + it;
         const int lrow = first + it;
+        OcPV2 me, w1;
+        me.x = p_unpack3(me_x); me.v = p_unpack3(me_v); w1.x = p_unpack3(w1_x); w1.v = p_unpack3(w1_v);
+        const OcPair3 k1 = p_unpack3(k1_q), k2b = p_unpack3(k2b_q);
         // ---- asynchronous global loads of row lrow (both columns) into the thread's landing zone ------
         // (columns of the window outside the cloth get a benign far-away particle at rest)
         const bool doL = kSteady || (lrow >= in_lo && lrow < in_hi);
@@ -257,12 +262,12 @@ struct OcMarch2 {
             const float2 nSh = p_bc(c.nks_shear), kSh = p_bc(c.kd_shear);
             if (!M::kExact) { rH1 = p_mul(rH1, nS); rH2 = p_mul(rH2, nB); rV1 = p_mul(rV1, nS); rV2 = p_mul(rV2, nB); rD = p_mul(rD, nSh); rA = p_mul(rA, nSh); }
             bool b1 = false, b2 = false, b3 = false, b4 = false, b5 = false, b6 = false;
-            gH1 = oc_spring2v<M>(me.x, me.v, qH1.x, qH1.v, rH1, nS, kS, b1);
-            gH2 = oc_spring2v<M>(me.x, me.v, n0.x,  n0.v,  rH2, nB, kB, b2);
-            gV1 = oc_spring2v<M>(me.x, me.v, w1.x,  w1.v,  rV1, nS, kS, b3);
-            gV2 = oc_spring2v<M>(me.x, me.v, w2.x,  w2.v,  rV2, nB, kB, b4);
-            gD  = oc_spring2v<M>(me.x, me.v, qD.x,  qD.v,  rD,  nSh, kSh, b5);
-            gA  = oc_spring2v<M>(me.x, me.v, qA.x,  qA.v,  rA,  nSh, kSh, b6);
+            gH1 = oc_spring2v<M>(me.x, me.v, qH1.x, qH1.v, rH1, nS, kS, c.one, b1);
+            gH2 = oc_spring2v<M>(me.x, me.v, n0.x,  n0.v,  rH2, nB, kB, c.one, b2);
+            gV1 = oc_spring2v<M>(me.x, me.v, w1.x,  w1.v,  rV1, nS, kS, c.one, b3);
+            gV2 = oc_spring2v<M>(me.x, me.v, w2.x,  w2.v,  rV2, nB, kB, c.one, b4);
+            gD  = oc_spring2v<M>(me.x, me.v, qD.x,  qD.v,  rD,  nSh, kSh, c.one, b5);
+            gA  = oc_spring2v<M>(me.x, me.v, qA.x,  qA.v,  rA,  nSh, kSh, c.one, b6);
             if (M::kExact && (bad | b1 | b2 | b3 | b4 | b5 | b6)) {
                 // rare: an operand left the exact range of the branch-free sequences -> IEEE intrinsics
                 if (bad | b1) gH1 = oc_march2_redo<M, WC>(sm, 0, sl, pa, rh1.x, rh1.y, c.nks_struct, c.kd_struct);
@@ -271,6 +276,20 @@ struct OcMarch2 {
                 if (bad | b4) gV2 = oc_march2_redo<M, WC>(sm, 3, sl, pa, rv2_j, rv2_j, c.nks_bend, c.kd_bend);
                 if (bad | b5) gD  = oc_march2_redo<M, WC>(sm, 4, sl, pa, M::sqrt(M::add(dx2ab.x, dz2_j)), M::sqrt(M::add(dx2ab.y, dz2_j)), c.nks_shear, c.kd_shear);
                 if (bad | b6) gA  = oc_march2_redo<M, WC>(sm, 5, sl, pa, M::sqrt(M::add(dx2ma.x, dz2_j)), M::sqrt(M::add(dx2ma.y, dz2_j)), c.nks_shear, c.kd_shear);
+            }
+            if (!kInterior || !kSteady) {
+                // Window columns at a cloth edge: a spring to (or from) a column that does not exist is multiplied
+                // by 0, every other one by 1 (exact).  The zero force then flows through the unpredicated packed
+                // accumulation of the steady loop unchanged: F + (+-0) == F because an accumulator is never -0
+                // (oc_core.cuh).  The ghost ends are finite far-away particles, so 0 * f is a zero, not a NaN.
+                const int gb_ = ga + 1;
+                const float2 mH1 = make_float2(oka && okb ? 1.0f : 0.0f, okb && gb_ + 1 < U ? 1.0f : 0.0f);   // a-b, b-a_next (also (+1,+1))
+                const float2 mH2 = make_float2(oka && ga + 2 < U ? 1.0f : 0.0f, okb && gb_ + 2 < U ? 1.0f : 0.0f);
+                const float2 mA  = make_float2(oka && ga - 1 >= 0 ? 1.0f : 0.0f, oka && okb ? 1.0f : 0.0f);    // a-b_prev', b-a'
+                gH1.x = p_mul(gH1.x, mH1); gH1.y = p_mul(gH1.y, mH1); gH1.z = p_mul(gH1.z, mH1);
+                gH2.x = p_mul(gH2.x, mH2); gH2.y = p_mul(gH2.y, mH2); gH2.z = p_mul(gH2.z, mH2);
+                gD.x  = p_mul(gD.x,  mH1); gD.y  = p_mul(gD.y,  mH1); gD.z  = p_mul(gD.z,  mH1);
+                gA.x  = p_mul(gA.x,  mA);  gA.y  = p_mul(gA.y,  mA);  gA.z  = p_mul(gA.z,  mA);
             }
             // publish the forces whose partner lives in another thread
             s.FH1[0][h][i + 1] = gH1.x.y; s.FH1[1][h][i + 1] = gH1.y.y; s.FH1[2][h][i + 1] = gH1.z.y;
@@ -284,7 +303,7 @@ struct OcMarch2 {
         // ---- G phase ---------------------------------------------------------------------------------
         const bool doG = kSteady || (row >= lo && row < hi);
         if (doG) {
-            constexpr bool kAll = kSteady && kInterior;
+            constexpr bool kAll = kSteady;           // no predicates: edge columns are handled by the zero masks above
             const int gb = ga + 1;
             const bool pin_a = !kSteady && oc_pinned(c, ga, row), pin_b = !kSteady && oc_pinned(c, gb, row);
             const bool ea = !pin_a, eb = !pin_b;                                  // springs act on the particle
@@ -297,18 +316,18 @@ struct OcMarch2 {
             F.x = make_float2(pin_a ? 0.0f : c.f0[0], pin_b ? 0.0f : c.f0[0]);
             F.y = make_float2(pin_a ? 0.0f : c.f0[1], pin_b ? 0.0f : c.f0[1]);
             F.z = make_float2(pin_a ? 0.0f : c.f0[2], pin_b ? 0.0f : c.f0[2]);
-            F.x = p_add(F.x, p_mulm<M>(p_bc(c.damping), me.v.x));
-            F.y = p_add(F.y, p_mulm<M>(p_bc(c.damping), me.v.y));
-            F.z = p_add(F.z, p_mulm<M>(p_bc(c.damping), me.v.z));
+            F.x = p_sump<M>(p_mul(p_bc(c.damping), me.v.x), F.x, c.one);
+            F.y = p_sump<M>(p_mul(p_bc(c.damping), me.v.y), F.y, c.one);
+            F.z = p_sump<M>(p_mul(p_bc(c.damping), me.v.z), F.z, c.one);
             // 1  (i-1, j): a <- b of the previous thread (shared), b <- a (own pair, first half)
             {
                 const bool p = ea && al1, q = eb && bl1;
                 if (kAll || p) { F.x.x = M::sub(F.x.x, s.FH1[0][h][i]); F.y.x = M::sub(F.y.x, s.FH1[1][h][i]); F.z.x = M::sub(F.z.x, s.FH1[2][h][i]); }
                 if (kAll || q) { F.x.y = M::sub(F.x.y, gH1.x.x); F.y.y = M::sub(F.y.y, gH1.y.x); F.z.y = M::sub(F.z.y, gH1.z.x); }
             }
-            oc_acc2<M, kAll>(F, gH1, ea && ar1, eb && br1, false);                                  // 2  (i+1, j)
-            oc_acc2<M, kAll>(F, k1,  ea && up1, eb && up1, true);                                   // 3  (i, j-1)
-            oc_acc2<M, kAll>(F, gV1, ea && dn1, eb && dn1, false);                                  // 4  (i, j+1)
+            oc_acc2<M, kAll>(F, gH1, ea && ar1, eb && br1, false, c.one);                                  // 2  (i+1, j)
+            oc_acc2<M, kAll>(F, k1,  ea && up1, eb && up1, true, c.one);                                   // 3  (i, j-1)
+            oc_acc2<M, kAll>(F, gV1, ea && dn1, eb && dn1, false, c.one);                                  // 4  (i, j+1)
             // 5  (i-1, j-1): a <- b_prev at row-1 (shared), b <- a at row-1 (carried)
             {
                 const bool p = ea && al1 && up1, q = eb && bl1 && up1;
@@ -321,36 +340,41 @@ struct OcMarch2 {
                 if (kAll || p) { F.x.x = M::sub(F.x.x, kAb.x); F.y.x = M::sub(F.y.x, kAb.y); F.z.x = M::sub(F.z.x, kAb.z); }
                 if (kAll || q) { F.x.y = M::sub(F.x.y, s.FAa[0][s3][i + 2]); F.y.y = M::sub(F.y.y, s.FAa[1][s3][i + 2]); F.z.y = M::sub(F.z.y, s.FAa[2][s3][i + 2]); }
             }
-            oc_acc2<M, kAll>(F, gA, ea && al1 && dn1, eb && bl1 && dn1, false);                     // 7  (i-1, j+1)
-            oc_acc2<M, kAll>(F, gD, ea && ar1 && dn1, eb && br1 && dn1, false);                     // 8  (i+1, j+1)
+            oc_acc2<M, kAll>(F, gA, ea && al1 && dn1, eb && bl1 && dn1, false, c.one);                     // 7  (i-1, j+1)
+            oc_acc2<M, kAll>(F, gD, ea && ar1 && dn1, eb && br1 && dn1, false, c.one);                     // 8  (i+1, j+1)
             OcPair3 r2;                                                                             // 9  (i-2, j)
             r2.x = *reinterpret_cast<const float2*>(&s.FH2[0][h][pa - 2]);
             r2.y = *reinterpret_cast<const float2*>(&s.FH2[1][h][pa - 2]);
             r2.z = *reinterpret_cast<const float2*>(&s.FH2[2][h][pa - 2]);
-            oc_acc2<M, kAll>(F, r2,  ea && al2, eb && bl2, true);
-            oc_acc2<M, kAll>(F, gH2, ea && ar2, eb && br2, false);                                  // 10 (i+2, j)
+            oc_acc2<M, kAll>(F, r2,  ea && al2, eb && bl2, true, c.one);
+            oc_acc2<M, kAll>(F, gH2, ea && ar2, eb && br2, false, c.one);                                  // 10 (i+2, j)
             if (!kAll) {                                                                            // 11 duplicated last bend spring of the row (V:313)
-                oc_acc2<M, false>(F, gH2, ea && ga == U - 3, eb && gb == U - 3, false);
-                oc_acc2<M, false>(F, r2,  ea && ga == U - 1, eb && gb == U - 1, true);
+                oc_acc2<M, false>(F, gH2, ea && ga == U - 3, eb && gb == U - 3, false, c.one);
+                oc_acc2<M, false>(F, r2,  ea && ga == U - 1, eb && gb == U - 1, true, c.one);
+            } else if (!kInterior) {                                                                // same, as 0/1 multipliers
+                const float2 dA = make_float2(ga == U - 3 ? 1.0f : 0.0f, gb == U - 3 ? 1.0f : 0.0f);
+                const float2 dB = make_float2(ga == U - 1 ? 1.0f : 0.0f, gb == U - 1 ? 1.0f : 0.0f);
+                F.x = p_sump<M>(p_mul(gH2.x, dA), F.x, c.one); F.y = p_sump<M>(p_mul(gH2.y, dA), F.y, c.one); F.z = p_sump<M>(p_mul(gH2.z, dA), F.z, c.one);
+                F.x = p_subp<M>(F.x, p_mul(r2.x, dB), c.one);  F.y = p_subp<M>(F.y, p_mul(r2.y, dB), c.one);  F.z = p_subp<M>(F.z, p_mul(r2.z, dB), c.one);
             }
-            oc_acc2<M, kAll>(F, k2b, ea && up2, eb && up2, true);                                   // 12 (i, j-2)
-            oc_acc2<M, kAll>(F, gV2, ea && dn2, eb && dn2, false);                                  // 13 (i, j+2)
+            oc_acc2<M, kAll>(F, k2b, ea && up2, eb && up2, true, c.one);                                   // 12 (i, j-2)
+            oc_acc2<M, kAll>(F, gV2, ea && dn2, eb && dn2, false, c.one);                                  // 13 (i, j+2)
             if (!kSteady) {                                                                         // 14 duplicated last bend spring of the column (V:319)
-                oc_acc2<M, false>(F, gV2, ea && row == V - 3, eb && row == V - 3, false);
-                oc_acc2<M, false>(F, k2b, ea && row == V - 1, eb && row == V - 1, true);
+                oc_acc2<M, false>(F, gV2, ea && row == V - 3, eb && row == V - 3, false, c.one);
+                oc_acc2<M, false>(F, k2b, ea && row == V - 1, eb && row == V - 1, true, c.one);
             }
             // ---- IntegrateVerlet (V:428-444) + EllipsoidCollision (V:509-533), both particles ----------
             OcPair3 n;
-            n.x = p_add(p_add(me.x.x, dme.x), p_mulm<M>(p_bc(c.dt2m), F.x));
-            n.y = p_add(p_add(me.x.y, dme.y), p_mulm<M>(p_bc(c.dt2m), F.y));
-            n.z = p_add(p_add(me.x.z, dme.z), p_mulm<M>(p_bc(c.dt2m), F.z));
+            n.x = p_sump<M>(p_mul(p_bc(c.dt2m), F.x), p_add(me.x.x, dme.x), c.one);
+            n.y = p_sump<M>(p_mul(p_bc(c.dt2m), F.y), p_add(me.x.y, dme.y), c.one);
+            n.z = p_sump<M>(p_mul(p_bc(c.dt2m), F.z), p_add(me.x.z, dme.z), c.one);
             if (n.y.x < 0.0f) n.y.x = 0.0f;
             if (n.y.y < 0.0f) n.y.y = 0.0f;
             OcPair3 p0;         // X_0 = inverse_ellipsoid * vec4(X,1) - center, rows x, y, z for (a, b)
-            p0.x = p_sub(p_add(p_add(p_add(p_mulm<M>(p_bc(c.im[0][0]), n.x), p_mulm<M>(p_bc(c.im[0][1]), n.y)), p_mulm<M>(p_bc(c.im[0][2]), n.z)), p_bc(c.im[0][3])), p_bc(c.center[0]));
-            p0.y = p_sub(p_add(p_add(p_add(p_mulm<M>(p_bc(c.im[1][0]), n.x), p_mulm<M>(p_bc(c.im[1][1]), n.y)), p_mulm<M>(p_bc(c.im[1][2]), n.z)), p_bc(c.im[1][3])), p_bc(c.center[1]));
-            p0.z = p_sub(p_add(p_add(p_add(p_mulm<M>(p_bc(c.im[2][0]), n.x), p_mulm<M>(p_bc(c.im[2][1]), n.y)), p_mulm<M>(p_bc(c.im[2][2]), n.z)), p_bc(c.im[2][3])), p_bc(c.center[2]));
-            const float2 sq = p_add(p_add(p_mulm<M>(p0.x, p0.x), p_mulm<M>(p0.y, p0.y)), p_mulm<M>(p0.z, p0.z));
+            p0.x = p_sub(p_add(p_sump<M>(p_mul(p_bc(c.im[0][2]), n.z), p_sump<M>(p_mul(p_bc(c.im[0][1]), n.y), p_mul(p_bc(c.im[0][0]), n.x), c.one), c.one), p_bc(c.im[0][3])), p_bc(c.center[0]));
+            p0.y = p_sub(p_add(p_sump<M>(p_mul(p_bc(c.im[1][2]), n.z), p_sump<M>(p_mul(p_bc(c.im[1][1]), n.y), p_mul(p_bc(c.im[1][0]), n.x), c.one), c.one), p_bc(c.im[1][3])), p_bc(c.center[1]));
+            p0.z = p_sub(p_add(p_sump<M>(p_mul(p_bc(c.im[2][2]), n.z), p_sump<M>(p_mul(p_bc(c.im[2][1]), n.y), p_mul(p_bc(c.im[2][0]), n.x), c.one), c.one), p_bc(c.im[2][3])), p_bc(c.center[2]));
+            const float2 sq = p_sump<M>(p_mul(p0.z, p0.z), p_sump<M>(p_mul(p0.y, p0.y), p_mul(p0.x, p0.x), c.one), c.one);
             bool hit_a = sq.x < 1.0f, hit_b = sq.y < 1.0f;                                           // V:513-514 (see oc_core.cuh)
             if (hit_a | hit_b) {
                 for (int hh = 0; hh < 2; ++hh) {
@@ -372,10 +396,10 @@ struct OcMarch2 {
             if (stb) C[o + 1] = make_float4(n.x.y, n.y.y, n.z.y, oc_u2f(hit_b ? OC_W_HIT : OC_W_PLAIN));
         }
         if (doP) {
-            k2b = k2a; k2a = gV2; k1 = gV1;
+            k2b_q = k2a_q; k2a_q = p_pack3(gV2); k1_q = p_pack3(gV1);
             kDa = make_f3(gD.x.x, gD.y.x, gD.z.x);
             kAb = make_f3(gA.x.y, gA.y.y, gA.z.y);
-            me = w1; w1 = w2;
+            me_x = p_pack3(w1.x); me_v = p_pack3(w1.v); w1_x = p_pack3(w2.x); w1_v = p_pack3(w2.v);
         }
 
         // ---- publish the loaded row ------------------------------------------------------------------
@@ -385,6 +409,19 @@ struct OcMarch2 {
         }
     }
 };
+
+#ifdef __CUDACC__
+// development aid (OC_DEBUG=8): per-CTA time stamps  [0] entry  [1] set-up done  [2] lead-in done  [3] steady loop
+// done  [4] exit, and [5] = SM id, at dbg_cnt[OC_DBG_TL_BASE + 8 * linear CTA index + k]
+__device__ __forceinline__ void oc_timeline_mark(const OcConst& c, int k)
+{
+    const unsigned lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+    if (lin >= OC_DBG_TL_CTAS) return;
+    unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    c.dbg_cnt[OC_DBG_TL_BASE + 8 * lin + k] = t;
+    if (k == 0) { unsigned sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); c.dbg_cnt[OC_DBG_TL_BASE + 8 * lin + 5] = sm; }
+}
+#endif
 
 template <class M, int WC, class Ctx>
 OC_HD void oc_march2_body(Ctx& ctx, const OcConst& c, const float4* __restrict__ A, const float4* __restrict__ B,
@@ -423,9 +460,8 @@ OC_HD void oc_march2_body(Ctx& ctx, const OcConst& c, const float4* __restrict__
         m.rv1_n = OC_LDG(c.rv1 + r); m.rv2_n = OC_LDG(c.rv2 + r); m.dz2_n = OC_LDG(c.dz2 + r);
     }
     const float2 z2 = make_float2(0.f, 0.f);
-    m.me.x.x = m.me.x.y = m.me.x.z = m.me.v.x = m.me.v.y = m.me.v.z = z2;
-    m.w1 = m.me;
-    m.k1.x = m.k1.y = m.k1.z = z2; m.k2a = m.k1; m.k2b = m.k1;
+    m.me_x.x = m.me_x.y = m.me_x.z = p_pack(z2);
+    m.me_v = m.w1_x = m.w1_v = m.k1_q = m.k2a_q = m.k2b_q = m.me_x;
     m.kDa = m.kAb = make_f3(0.f, 0.f, 0.f);
 
     // benign content for the pad columns / pad thread slots (never written by a particle)
@@ -448,28 +484,35 @@ OC_HD void oc_march2_body(Ctx& ctx, const OcConst& c, const float4* __restrict__
         }
     }
 
-    // steady range: interior rows, all activities on, multiple of 4 iterations starting at row & 3 == 0
+    // steady range: interior rows, all activities on
     int st_lo = lo > plo + 1 ? lo : plo + 1; if (st_lo < 2) st_lo = 2;
     int st_hi = hi < V - 3 ? hi : V - 3;
     if (st_hi > in_hi - OC_MARCH_LAG) st_hi = in_hi - OC_MARCH_LAG;
     int it_lo = st_lo - row0, it_hi = st_hi - row0;
     if (it_lo < 0) it_lo = 0;
     if (it_hi > n_it) it_hi = n_it;
-    while (it_lo < it_hi && ((row0 + it_lo) & (OC_RING - 1)) != 0) ++it_lo;
-    it_hi = it_lo + ((it_hi - it_lo) & ~(OC_RING - 1));
     if (it_hi <= it_lo) it_lo = it_hi = n_it;
     const bool interior = cx0 >= 2 && cx0 + WC + 2 <= U;          // CTA-uniform
 
+#ifdef __CUDA_ARCH__
+    if ((c.dbg & 8) && i == 0) oc_timeline_mark(c, 1);       // development: CTA timeline (OC_DEBUG=8)
+#endif
     int it = 0;
     for (int phase = 0; phase < 2; ++phase) {
         const int end = phase == 0 ? it_lo : n_it;
         for (; it < end; ++it) m.template iter<false, false, -1>(it);
+#ifdef __CUDA_ARCH__
+        if ((c.dbg & 8) && i == 0) oc_timeline_mark(c, phase == 0 ? 2 : 4);
+#endif
         if (phase == 0) {
             if (interior) {
                 for (; it < it_hi; ++it) m.template iter<true, true, -1>(it);
             } else {
                 for (; it < it_hi; ++it) m.template iter<true, false, -1>(it);
             }
+#ifdef __CUDA_ARCH__
+            if ((c.dbg & 8) && i == 0) oc_timeline_mark(c, 3);
+#endif
         }
     }
 }
@@ -488,6 +531,7 @@ __global__ void OC_M2_BOUNDS
 oc_k_march2(OcConst c, const float4* __restrict__ A, const float4* __restrict__ B, float4* __restrict__ C,
             int ra, int rb, int RS, int x_halo)
 {
+    if ((c.dbg & 8) && threadIdx.x == 0) oc_timeline_mark(c, 0);
     OcDevCtx ctx;
     oc_march2_body<M, WC, OcDevCtx>(ctx, c, A, B, C, ra, rb, RS, x_halo);
 }
