@@ -136,6 +136,9 @@ cudaError_t oc_march_launch(const OcConst& c, bool exact, int S, int ra, int rb,
 extern "C" const void* oc_march2_fn_exact(int WC);
 extern "C" const void* oc_march2_fn_fast(int WC);
 static int g_occ2[2][2];      // [exact][WC == 128]
+// tile-height ratios of the speed classes (percent), measured on B200 (profiles/ time line)
+#define OC_MARCH2_EDGE_EXACT 24
+#define OC_MARCH2_EDGE_FAST  10
 
 static size_t smem2(int WC) { return WC == 64 ? sizeof(OcSmem2<64>) : sizeof(OcSmem2<128>); }
 static int pick_wc(int nx)
@@ -162,7 +165,7 @@ int oc_march2_configure(int device)
     return 0;
 }
 
-int oc_march2_plan(const OcConst& c, int ra, int rb, int sm_count, int occ_hint, OcMarchPlan* pl)
+int oc_march2_plan(const OcConst& c, bool exact, int ra, int rb, int sm_count, int occ_hint, OcMarchPlan* pl, OcSeg2* seg)
 {
     const int U = c.U;
     const int WC = pick_wc(U);
@@ -187,6 +190,22 @@ int oc_march2_plan(const OcConst& c, int ra, int rb, int sm_count, int occ_hint,
     }
     pl->TW = WC; pl->S = 1; pl->x_halo = x_halo; pl->W_out = W_out; pl->nstrips = nstrips;
     pl->RS = best_rs; pl->nseg = (rows + best_rs - 1) / best_rs; pl->threads = WC / 2; pl->smem = smem2(WC);
+    seg->rs = seg->rs_e = best_rs; seg->nstrips = nstrips; seg->nseg_all = pl->nseg; seg->n_extra = 0;
+    // Single-wave launch of one cloth: shorter segments for the two edge strips (OcSeg2).
+    //   OC_MARCH2_EDGE = interior / edge rows per segment - 1 in percent (0 = off).
+    const char* ee = getenv("OC_MARCH2_EDGE");
+    const int edge = ee ? atoi(ee) : (exact ? OC_MARCH2_EDGE_EXACT : OC_MARCH2_EDGE_FAST);
+    const long long tiles = (long long)nstrips * pl->nseg;
+    if (!(env && atoi(env) > 0) && edge > 0 && c.batch == 1 && nstrips >= 3 && tiles <= slots) {
+        for (int e = edge; e >= 4; e -= 2) {                          // the largest ratio whose extra edge tiles fit the same wave
+            OcSeg2 g = *seg;
+            g.rs_e = (int)((100.0 * g.rs) / (100.0 + e) + 0.5);
+            if (g.rs_e < 8) continue;
+            oc_seg2_finish(g, rows);
+            if (oc_seg2_tiles(g) <= slots) { *seg = g; break; }
+        }
+    }
+    pl->nseg = seg->nseg_all;
     return 0;
 }
 
@@ -196,14 +215,23 @@ cudaError_t oc_march2_launch(const OcConst& c, bool exact, int ra, int rb, int s
     *n_launches = 0;
     OcMarchPlan pl;
     const int WC = pick_wc(c.U);
-    if (oc_march2_plan(c, ra, rb, sm_count, g_occ2[exact ? 1 : 0][WC == 128], &pl) != 0) return cudaErrorInvalidValue;
+    OcSeg2 seg;
+    if (oc_march2_plan(c, exact, ra, rb, sm_count, g_occ2[exact ? 1 : 0][WC == 128], &pl, &seg) != 0) return cudaErrorInvalidValue;
     const void* fn = exact ? oc_march2_fn_exact(WC) : oc_march2_fn_fast(WC);
     if (!fn) return cudaErrorInvalidDeviceFunction;
-    if (pl.nseg > 65535 || c.batch > 65535) return cudaErrorInvalidConfiguration;
-    dim3 grid(pl.nstrips, pl.nseg, c.batch), block(pl.threads, 1, 1);
+    if (c.batch > 65535) return cudaErrorInvalidConfiguration;
+    if (c.dbg & 16) {        // development: print the segmentation once per distinct row range
+        static int last_ra = -1, last_rb = -1;
+        if (last_ra != ra || last_rb != rb) {
+            last_ra = ra; last_rb = rb;
+            fprintf(stderr, "[oc] march2 plan rows [%d,%d): strips %d x segs %d + %d extra; rows/segment %d, edge strips %d; exact %d\n",
+                    ra, rb, seg.nstrips, seg.nseg_all, seg.n_extra, seg.rs, seg.rs_e, (int)exact);
+        }
+    }
+    dim3 grid(oc_seg2_tiles(seg), 1, c.batch), block(pl.threads, 1, 1);
     OcConst cc = c;
-    int RS = pl.RS, xh = pl.x_halo;
-    void* args[] = { &cc, (void*)&A, (void*)&B, (void*)&C, &ra, &rb, &RS, &xh };
+    int xh = pl.x_halo;
+    void* args[] = { &cc, (void*)&A, (void*)&B, (void*)&C, &ra, &rb, &seg, &xh };
     cudaError_t e = cudaLaunchKernel(fn, grid, block, args, pl.smem, stream);
     if (e == cudaSuccess) *n_launches = 1;
     return e;

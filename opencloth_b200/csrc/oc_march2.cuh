@@ -176,6 +176,7 @@ struct OcMarch2 {
             q0 = p_mul(d.y, y);        v.y = p_fma(y, p_fma(q0, nd, d.y), q0);
             q0 = p_mul(d.z, y);        v.z = p_fma(y, p_fma(q0, nd, d.z), q0);
             if (badv) {
+                if (c.dbg & 4) atomicAdd(c.dbg_cnt + 2, 1ull);
                 v.x = make_float2(M::div(d.x.x, c.dt), M::div(d.x.y, c.dt));
                 v.y = make_float2(M::div(d.y.x, c.dt), M::div(d.y.y, c.dt));
                 v.z = make_float2(M::div(d.z.x, c.dt), M::div(d.z.y, c.dt));
@@ -268,6 +269,12 @@ struct OcMarch2 {
             gV2 = oc_spring2v<M>(me.x, me.v, w2.x,  w2.v,  rV2, nB, kB, c.one, b4);
             gD  = oc_spring2v<M>(me.x, me.v, qD.x,  qD.v,  rD,  nSh, kSh, c.one, b5);
             gA  = oc_spring2v<M>(me.x, me.v, qA.x,  qA.v,  rA,  nSh, kSh, c.one, b6);
+#ifdef __CUDA_ARCH__
+            if (M::kExact && (c.dbg & 4) && (bad | b1 | b2 | b3 | b4 | b5 | b6)) {      // development counters (OC_DEBUG=4)
+                atomicAdd(c.dbg_cnt, 1ull);
+                if ((threadIdx.x & 31) == __ffs(__activemask()) - 1) atomicAdd(c.dbg_cnt + 1, 1ull);
+            }
+#endif
             if (M::kExact && (bad | b1 | b2 | b3 | b4 | b5 | b6)) {
                 // rare: an operand left the exact range of the branch-free sequences -> IEEE intrinsics
                 if (bad | b1) gH1 = oc_march2_redo<M, WC>(sm, 0, sl, pa, rh1.x, rh1.y, c.nks_struct, c.kd_struct);
@@ -377,6 +384,9 @@ struct OcMarch2 {
             const float2 sq = p_sump<M>(p_mul(p0.z, p0.z), p_sump<M>(p_mul(p0.y, p0.y), p_mul(p0.x, p0.x), c.one), c.one);
             bool hit_a = sq.x < 1.0f, hit_b = sq.y < 1.0f;                                           // V:513-514 (see oc_core.cuh)
             if (hit_a | hit_b) {
+#ifdef __CUDA_ARCH__
+                if (c.dbg & 4) { atomicAdd(c.dbg_cnt + 3, 1ull); if ((threadIdx.x & 31) == __ffs(__activemask()) - 1) atomicAdd(c.dbg_cnt + 3, 1ull << 32); }
+#endif
                 for (int hh = 0; hh < 2; ++hh) {
                     if (!(hh ? hit_b : hit_a)) continue;
                     f3 d0 = hh ? make_f3(p0.x.y, p0.y.y, p0.z.y) : make_f3(p0.x.x, p0.y.x, p0.z.x);
@@ -423,9 +433,44 @@ __device__ __forceinline__ void oc_timeline_mark(const OcConst& c, int k)
 }
 #endif
 
+// Row segmentation of a launch: tile t of the 1-D grid -> (strip, segment) -> rows.  Uniform segments (rs_e = rs,
+// n_extra = 0) are always valid.  In a SINGLE-WAVE launch the kernel ends when its slowest CTA does, and the CTAs
+// of the first and last strip (masked edge path, half-empty last window) are the slow ones (time line in
+// profiles/): the planner then gives the edge strips shorter segments (rs_e < rs) and a few more of them, so that
+// all CTAs finish together.  The result does not depend on the segmentation: each row of a strip is computed by
+// exactly one tile, from the same inputs.
+struct OcSeg2 {
+    int rs, rs_e;       // rows per segment: interior strips, edge strips
+    int nstrips;
+    int nseg_all;       // segments every strip has: tiles t < nstrips * nseg_all are (t % nstrips, t / nstrips)
+    int n_extra;        // further tiles, alternately of the first and the last strip (the edge strips' additional segments)
+};
+OC_HD int oc_seg2_tiles(const OcSeg2& g) { return g.nstrips * g.nseg_all + g.n_extra; }
+OC_HD void oc_seg2_tile(const OcSeg2& g, int t, int& bx, int& by)
+{
+    const int body = g.nstrips * g.nseg_all;
+    if (t < body) { bx = t % g.nstrips; by = t / g.nstrips; }
+    else { const int e = t - body; bx = (e & 1) ? g.nstrips - 1 : 0; by = g.nseg_all + (e >> 1); }
+}
+OC_HD void oc_seg2_rows(const OcSeg2& g, int bx, int by, int ra, int rb, int& r0, int& r1)
+{
+    const int h = (bx == 0 || bx == g.nstrips - 1) ? g.rs_e : g.rs;
+    r0 = ra + by * h;
+    r1 = r0 + h;
+    if (r0 > rb) r0 = rb;
+    if (r1 > rb) r1 = rb;
+}
+// Completes g (rs, rs_e, nstrips given) so that every strip is covered.
+inline void oc_seg2_finish(OcSeg2& g, int rows)
+{
+    const int ni = (rows + g.rs - 1) / g.rs, ne = (rows + g.rs_e - 1) / g.rs_e;
+    if (g.nstrips <= 2 || ne <= ni) { g.nseg_all = g.nstrips <= 2 ? ne : ni; g.n_extra = 0; if (ne < ni) g.rs_e = g.rs; return; }
+    g.nseg_all = ni; g.n_extra = 2 * (ne - ni);
+}
+
 template <class M, int WC, class Ctx>
 OC_HD void oc_march2_body(Ctx& ctx, const OcConst& c, const float4* __restrict__ A, const float4* __restrict__ B,
-                          float4* __restrict__ C, int ra, int rb, int RS, int x_halo)
+                          float4* __restrict__ C, int ra, int rb, OcSeg2 seg, int x_halo)
 {
     OcMarch2<M, WC, Ctx> m(ctx, c);
     m.A = A; m.B = B; m.C = C;
@@ -435,8 +480,9 @@ OC_HD void oc_march2_body(Ctx& ctx, const OcConst& c, const float4* __restrict__
     const int W_out = WC - 2 * x_halo;
     const int cx0 = ctx.bx() * W_out - x_halo;
     const int ga = cx0 + 2 * i, gb = ga + 1;
-    const int r0 = ra + ctx.by() * RS;
-    const int r1 = (r0 + RS < rb) ? r0 + RS : rb;
+    int r0, r1;
+    oc_seg2_rows(seg, ctx.bx(), ctx.by(), ra, rb, r0, r1);
+    if (r0 >= r1) return;                           // CTA-uniform: no rows left for this tile
     m.i = i; m.pa = 2 * i + 2; m.ga = ga; m.U = U; m.V = V;
     int lo = r0, hi = r1;
     int plo = lo - 2; if (plo < 0) plo = 0;
@@ -526,20 +572,30 @@ OC_HD void oc_march2_body(Ctx& ctx, const OcConst& c, const float4* __restrict__
 #else
 #define OC_M2_BOUNDS __launch_bounds__(WC / 2, OC_CTAS_M2)
 #endif
+struct OcDevCtx2 {          // grid = (tiles, 1, batch): the tile -> (strip, segment) map is OcSeg2's
+    int x, y;
+    __device__ __forceinline__ int tid() const { return threadIdx.x; }
+    __device__ __forceinline__ int bx() const { return x; }
+    __device__ __forceinline__ int by() const { return y; }
+    __device__ __forceinline__ int bz() const { return blockIdx.z; }
+    __device__ __forceinline__ void sync() const { __syncthreads(); }
+    __device__ __forceinline__ unsigned char* smem() const { extern __shared__ __align__(16) unsigned char oc_dyn_smem[]; return oc_dyn_smem; }
+};
 template <class M, int WC>
 __global__ void OC_M2_BOUNDS
 oc_k_march2(OcConst c, const float4* __restrict__ A, const float4* __restrict__ B, float4* __restrict__ C,
-            int ra, int rb, int RS, int x_halo)
+            int ra, int rb, OcSeg2 seg, int x_halo)
 {
     if ((c.dbg & 8) && threadIdx.x == 0) oc_timeline_mark(c, 0);
-    OcDevCtx ctx;
-    oc_march2_body<M, WC, OcDevCtx>(ctx, c, A, B, C, ra, rb, RS, x_halo);
+    OcDevCtx2 ctx;
+    oc_seg2_tile(seg, blockIdx.x, ctx.x, ctx.y);
+    oc_march2_body<M, WC, OcDevCtx2>(ctx, c, A, B, C, ra, rb, seg, x_halo);
 }
 #endif
 
 // ---- host side (oc_march.cu) -------------------------------------------------------------------
 int  oc_march2_configure(int device);
-int  oc_march2_plan(const OcConst& c, int ra, int rb, int sm_count, int occ_hint, OcMarchPlan* plan);
+int  oc_march2_plan(const OcConst& c, bool exact, int ra, int rb, int sm_count, int occ_hint, OcMarchPlan* plan, OcSeg2* seg);
 #ifdef __CUDACC__
 cudaError_t oc_march2_launch(const OcConst& c, bool exact, int ra, int rb, int sm_count,
                              const float4* A, const float4* B, float4* C, cudaStream_t stream, int* n_launches);

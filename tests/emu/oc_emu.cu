@@ -197,20 +197,25 @@ static int emu_march2(EmuCloth* e, const OcLaunch& L, int RS)
     const int W_out = WC - 2 * x_halo;
     const int nstrips = (k.U + W_out - 1) / W_out;
     const int rows = L.rb - L.ra;
-    if (RS <= 0 || RS > rows) RS = rows;
-    const int nseg = (rows + RS - 1) / RS;
+    // RS = rows per segment | (rows per segment of the edge strips) << 8   (0: same; see OcSeg2)
+    OcSeg2 seg;
+    seg.rs = RS & 0xff; seg.rs_e = (RS >> 8) & 0xff; seg.nstrips = nstrips;
+    if (seg.rs <= 0 || seg.rs > rows) seg.rs = rows;
+    if (seg.rs_e <= 0) seg.rs_e = seg.rs;
+    oc_seg2_finish(seg, rows);
     const float4* A = e->buf[L.src_a].data();
     const float4* B = e->buf[L.src_b].data();
     float4* C = e->buf[L.dst].data();
     int rc = 0;
     for (int bz = 0; bz < k.batch; ++bz)
-        for (int by = 0; by < nseg; ++by)
-            for (int bx = 0; bx < nstrips; ++bx) {
-                int ra = L.ra, rb = L.rb;
-                rc |= run_cta(WC / 2, bx, by, bz, sizeof(OcSmem2<WC>), [&](EmuCtx& ctx) {
-                    oc_march2_body<M, WC, EmuCtx>(ctx, k, A, B, C, ra, rb, RS, x_halo);
-                });
-            }
+        for (int t = 0; t < oc_seg2_tiles(seg); ++t) {
+            int bx, by;
+            oc_seg2_tile(seg, t, bx, by);
+            int ra = L.ra, rb = L.rb;
+            rc |= run_cta(WC / 2, bx, by, bz, sizeof(OcSmem2<WC>), [&](EmuCtx& ctx) {
+                oc_march2_body<M, WC, EmuCtx>(ctx, k, A, B, C, ra, rb, seg, x_halo);
+            });
+        }
     return rc;
 }
 template <class M>

@@ -57,6 +57,8 @@ MARCH2_CASES = [
     (21, 21, 0, 20, 32, 0), (21, 21, 1800, 60, 32, 7), (21, 21, 1800, 30, 16, 5), (37, 23, 1900, 12, 16, 5), (37, 23, 1900, 12, 64, 0),
     (64, 64, 2000, 8, 32, 10), (64, 64, 2000, 8, 64, 9), (70, 40, 1500, 8, 64, 13), (130, 20, 500, 4, 128, 7), (128, 24, 500, 4, 128, 0),
     (3, 3, 5, 40, 16, 0), (5, 4, 5, 40, 16, 2), (4, 9, 5, 23, 16, 3), (33, 30, 1700, 10, 32, 11),
+    # shorter segments in the edge strips (OcSeg2): RS = rows per segment | edge rows per segment << 8
+    (70, 40, 1500, 8, 64, 9), (70, 40, 1500, 8, 32, 12 | 9 << 8), (37, 23, 1900, 12, 16, 7 | 4 << 8), (37, 23, 1900, 12, 16, 6 | 5 << 8),
 ]
 
 

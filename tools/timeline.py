@@ -50,7 +50,7 @@ for cnt in np.unique(per):
 wout = 124 if a.nx > 128 else a.nx
 nstrips = (a.nx + wout - 1) // wout
 if n % nstrips == 0:
-    dur = d[:, 2].reshape(n // nstrips, nstrips)
-    print("  steady-loop duration map (us), one line per row segment:")
+    dur = rel[:, 4].reshape(n // nstrips, nstrips)
+    print("  exit time map (us after the first CTA entry), one line per row segment:")
     for r in range(dur.shape[0]):
         print("   ", " ".join(f"{int(v):3d}" for v in dur[r]), f"  | SMs {' '.join(str(int(x)) for x in sm[r * nstrips:(r + 1) * nstrips][:6])} ...")
