@@ -634,6 +634,31 @@ __global__ void oc_k_selftest(unsigned long long per_thread, unsigned seed, floa
         float v = oc_div_bf(d, dt, ydt, OC_VEL_LO, OC_VEL_HI, bad);
         if (__float_as_uint(v) != __float_as_uint(__fdiv_rn(d, dt))) bad_count++;
         if (bad || bad2) bad_count += 1000000;      // operands were generated inside the accepted ranges
+        // accumulated range tests (OcRange / OcRangeVel) against the per-operand tests, on arbitrary bit patterns
+        // biased towards the interval ends, the zeros and NaN / Inf
+        {
+            auto pattern = [&](unsigned lo, unsigned hi) -> float {
+                const unsigned r = oc_rng(st), k = r & 15u;
+                unsigned b;
+                if (k == 0) b = 0u; else if (k == 1) b = 0x80000000u;
+                else if (k == 2) b = lo + ((r >> 8) & 3u) - 2u; else if (k == 3) b = hi + ((r >> 8) & 3u) - 2u;
+                else if (k == 4) b = 0x7f800000u | ((r >> 8) & 0x400001u);
+                else if (k < 8) b = oc_rng(st);
+                else b = lo + (unsigned)(((unsigned long long)(hi - lo) * (oc_rng(st) >> 4)) >> 28);
+                if ((r & 0x100000u) && k >= 2) b ^= 0x80000000u;
+                return __uint_as_float(b);
+            };
+            OcRange rg; rg.init(); OcRangeVel rv; rv.init();
+            bool ref_sq = false, ref_num = false, ref_vel = false;
+            const int n_ops = 1 + (int)(oc_rng(st) & 3u);
+            for (int k = 0; k < n_ops; ++k) {
+                const float fs = pattern(0x10800000u, 0x6e800000u), fn = pattern(OC_NUM_LO_BITS, OC_NUM_HI_BITS), fv = pattern(OC_VEL_LO_BITS, OC_VEL_HI_BITS);
+                rg.sqr(fs); rg.num(fn); rv.add(fv);
+                ref_sq |= oc_bad_sqr(fs); ref_num |= oc_bad_num(fn, OC_NUM_LO_BITS, OC_NUM_HI_BITS); ref_vel |= oc_bad_vel(fv, OC_VEL_LO_BITS, OC_VEL_HI_BITS);
+            }
+            if (rg.bad() != (ref_sq | ref_num)) bad_count += 1ull << 48;
+            if (rv.bad() != ref_vel) bad_count += 1ull << 48;
+        }
         // packed FP32x2 forms: primitive ops and the pair sequences of the marching kernel
         {
             const float u0 = oc_rand_float(st, -30, 30, true), u1 = oc_rand_float(st, -30, 30, true);

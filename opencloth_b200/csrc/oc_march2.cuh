@@ -35,19 +35,19 @@ struct OcSmem2 {
 // ---- spring pair with a pair-valued first end (particles a and b of the thread) ----------------------
 template <class M>
 OC_HD OcPair3 oc_spring2v(const OcPair3& px, const OcPair3& pv, const OcPair3& qx, const OcPair3& qv,
-                          float2 rest, float2 nks, float2 kd, float one, bool& bad)
+                          float2 rest, float2 nks, float2 kd, float one, OcRange& rg)
 {
     OcPair3 dp, dv, f;
     dp.x = p_sub(px.x, qx.x); dp.y = p_sub(px.y, qx.y); dp.z = p_sub(px.z, qx.z);                     // V:471
     dv.x = p_sub(pv.x, qv.x); dv.y = p_sub(pv.y, qv.y); dv.z = p_sub(pv.z, qv.z);                     // V:472
     if (M::kExact) {
         const float2 sqr  = p_sump<M>(p_mul(dp.z, dp.z), p_sump<M>(p_mul(dp.y, dp.y), p_mul(dp.x, dp.x), one), one);
-        const float2 dist = oc_sqrt2<M>(sqr, bad);                                                   // V:473
+        const float2 dist = oc_sqrt2<M>(sqr, rg);                                                    // V:473
 #ifdef __CUDA_ARCH__
         const float2 y0  = p_rcp(dist);
         const float2 inv = p_fma(y0, p_fma(y0, p_neg(dist), p_bc(1.0f)), y0);
         const float2 a   = p_sump<M>(p_mul(dv.z, dp.z), p_sump<M>(p_mul(dv.y, dp.y), p_mul(dv.x, dp.x), one), one);
-        bad |= oc_bad_num(a.x, OC_NUM_LO_BITS, OC_NUM_HI_BITS) | oc_bad_num(a.y, OC_NUM_LO_BITS, OC_NUM_HI_BITS);
+        rg.num(a.x); rg.num(a.y);
         const float2 q0  = p_mul(a, inv);
         const float2 q   = p_fma(inv, p_fma(q0, p_neg(dist), a), q0);
 #else
@@ -168,14 +168,14 @@ struct OcMarch2 {
         OcPair3 v;
 #ifdef __CUDA_ARCH__
         if (M::kExact) {
-            bool badv = (c.dt_bf == 0) | oc_bad_vel(d.x.x, OC_VEL_LO_BITS, OC_VEL_HI_BITS) | oc_bad_vel(d.x.y, OC_VEL_LO_BITS, OC_VEL_HI_BITS) |
-                        oc_bad_vel(d.y.x, OC_VEL_LO_BITS, OC_VEL_HI_BITS) | oc_bad_vel(d.y.y, OC_VEL_LO_BITS, OC_VEL_HI_BITS) |
-                        oc_bad_vel(d.z.x, OC_VEL_LO_BITS, OC_VEL_HI_BITS) | oc_bad_vel(d.z.y, OC_VEL_LO_BITS, OC_VEL_HI_BITS);
+            OcRangeVel rv; rv.init();
+            rv.add(d.x.x); rv.add(d.x.y); rv.add(d.y.x); rv.add(d.y.y); rv.add(d.z.x); rv.add(d.z.y);
+            const bool badv = (c.dt_bf == 0) | rv.bad();
             const float2 y = p_bc(ydt), nd = p_bc(-c.dt);
             float2 q0 = p_mul(d.x, y); v.x = p_fma(y, p_fma(q0, nd, d.x), q0);
             q0 = p_mul(d.y, y);        v.y = p_fma(y, p_fma(q0, nd, d.y), q0);
             q0 = p_mul(d.z, y);        v.z = p_fma(y, p_fma(q0, nd, d.z), q0);
-            if (badv) {
+            if (__builtin_expect(badv, 0)) {
                 if (c.dbg & 4) atomicAdd(c.dbg_cnt + 2, 1ull);
                 v.x = make_float2(M::div(d.x.x, c.dt), M::div(d.x.y, c.dt));
                 v.y = make_float2(M::div(d.y.x, c.dt), M::div(d.y.y, c.dt));
@@ -255,34 +255,36 @@ struct OcMarch2 {
             qA.x.x = make_float2(s.X[0][s1][pa - 1], w1.x.x.x); qA.x.y = make_float2(s.X[1][s1][pa - 1], w1.x.y.x); qA.x.z = make_float2(s.X[2][s1][pa - 1], w1.x.z.x);
             qA.v.x = make_float2(s.X[3][s1][pa - 1], w1.v.x.x); qA.v.y = make_float2(s.X[4][s1][pa - 1], w1.v.y.x); qA.v.z = make_float2(s.X[5][s1][pa - 1], w1.v.z.x);
 
-            bool bad = false;
-            float2 rD = oc_sqrt2<M>(p_add(dx2ab, p_bc(dz2_j)), bad);        // cells (ga, row), (gb, row)
-            float2 rA = oc_sqrt2<M>(p_add(dx2ma, p_bc(dz2_j)), bad);        // cells (ga-1, row), (ga, row)
+            // exact mode: the operand ranges of the branch-free sqrt / division sequences, accumulated over the
+            // six spring pairs and the two shear rest lengths (OcRange); one test for the whole iteration
+            OcRange rg; rg.init();
+            float2 rD = oc_sqrt2<M>(p_add(dx2ab, p_bc(dz2_j)), rg);         // cells (ga, row), (gb, row)
+            float2 rA = oc_sqrt2<M>(p_add(dx2ma, p_bc(dz2_j)), rg);         // cells (ga-1, row), (ga, row)
             float2 rH1 = rh1, rH2 = rh2, rV1 = p_bc(rv1_j), rV2 = p_bc(rv2_j);
             const float2 nS = p_bc(c.nks_struct), kS = p_bc(c.kd_struct), nB = p_bc(c.nks_bend), kB = p_bc(c.kd_bend);
             const float2 nSh = p_bc(c.nks_shear), kSh = p_bc(c.kd_shear);
             if (!M::kExact) { rH1 = p_mul(rH1, nS); rH2 = p_mul(rH2, nB); rV1 = p_mul(rV1, nS); rV2 = p_mul(rV2, nB); rD = p_mul(rD, nSh); rA = p_mul(rA, nSh); }
-            bool b1 = false, b2 = false, b3 = false, b4 = false, b5 = false, b6 = false;
-            gH1 = oc_spring2v<M>(me.x, me.v, qH1.x, qH1.v, rH1, nS, kS, c.one, b1);
-            gH2 = oc_spring2v<M>(me.x, me.v, n0.x,  n0.v,  rH2, nB, kB, c.one, b2);
-            gV1 = oc_spring2v<M>(me.x, me.v, w1.x,  w1.v,  rV1, nS, kS, c.one, b3);
-            gV2 = oc_spring2v<M>(me.x, me.v, w2.x,  w2.v,  rV2, nB, kB, c.one, b4);
-            gD  = oc_spring2v<M>(me.x, me.v, qD.x,  qD.v,  rD,  nSh, kSh, c.one, b5);
-            gA  = oc_spring2v<M>(me.x, me.v, qA.x,  qA.v,  rA,  nSh, kSh, c.one, b6);
+            gH1 = oc_spring2v<M>(me.x, me.v, qH1.x, qH1.v, rH1, nS, kS, c.one, rg);
+            gH2 = oc_spring2v<M>(me.x, me.v, n0.x,  n0.v,  rH2, nB, kB, c.one, rg);
+            gV1 = oc_spring2v<M>(me.x, me.v, w1.x,  w1.v,  rV1, nS, kS, c.one, rg);
+            gV2 = oc_spring2v<M>(me.x, me.v, w2.x,  w2.v,  rV2, nB, kB, c.one, rg);
+            gD  = oc_spring2v<M>(me.x, me.v, qD.x,  qD.v,  rD,  nSh, kSh, c.one, rg);
+            gA  = oc_spring2v<M>(me.x, me.v, qA.x,  qA.v,  rA,  nSh, kSh, c.one, rg);
+            if (__builtin_expect(M::kExact && rg.bad(), 0)) {
+                // rare: an operand left the exact range of the branch-free sequences -> all six pairs again with the
+                // IEEE intrinsics (cold, out of line; operands re-read from shared memory)
 #ifdef __CUDA_ARCH__
-            if (M::kExact && (c.dbg & 4) && (bad | b1 | b2 | b3 | b4 | b5 | b6)) {      // development counters (OC_DEBUG=4)
-                atomicAdd(c.dbg_cnt, 1ull);
-                if ((threadIdx.x & 31) == __ffs(__activemask()) - 1) atomicAdd(c.dbg_cnt + 1, 1ull);
-            }
+                if (c.dbg & 4) {                                            // development counters (OC_DEBUG=4)
+                    atomicAdd(c.dbg_cnt, 1ull);
+                    if ((threadIdx.x & 31) == __ffs(__activemask()) - 1) atomicAdd(c.dbg_cnt + 1, 1ull);
+                }
 #endif
-            if (M::kExact && (bad | b1 | b2 | b3 | b4 | b5 | b6)) {
-                // rare: an operand left the exact range of the branch-free sequences -> IEEE intrinsics
-                if (bad | b1) gH1 = oc_march2_redo<M, WC>(sm, 0, sl, pa, rh1.x, rh1.y, c.nks_struct, c.kd_struct);
-                if (bad | b2) gH2 = oc_march2_redo<M, WC>(sm, 1, sl, pa, rh2.x, rh2.y, c.nks_bend, c.kd_bend);
-                if (bad | b3) gV1 = oc_march2_redo<M, WC>(sm, 2, sl, pa, rv1_j, rv1_j, c.nks_struct, c.kd_struct);
-                if (bad | b4) gV2 = oc_march2_redo<M, WC>(sm, 3, sl, pa, rv2_j, rv2_j, c.nks_bend, c.kd_bend);
-                if (bad | b5) gD  = oc_march2_redo<M, WC>(sm, 4, sl, pa, M::sqrt(M::add(dx2ab.x, dz2_j)), M::sqrt(M::add(dx2ab.y, dz2_j)), c.nks_shear, c.kd_shear);
-                if (bad | b6) gA  = oc_march2_redo<M, WC>(sm, 5, sl, pa, M::sqrt(M::add(dx2ma.x, dz2_j)), M::sqrt(M::add(dx2ma.y, dz2_j)), c.nks_shear, c.kd_shear);
+                gH1 = oc_march2_redo<M, WC>(sm, 0, sl, pa, rh1.x, rh1.y, c.nks_struct, c.kd_struct);
+                gH2 = oc_march2_redo<M, WC>(sm, 1, sl, pa, rh2.x, rh2.y, c.nks_bend, c.kd_bend);
+                gV1 = oc_march2_redo<M, WC>(sm, 2, sl, pa, rv1_j, rv1_j, c.nks_struct, c.kd_struct);
+                gV2 = oc_march2_redo<M, WC>(sm, 3, sl, pa, rv2_j, rv2_j, c.nks_bend, c.kd_bend);
+                gD  = oc_march2_redo<M, WC>(sm, 4, sl, pa, M::sqrt(M::add(dx2ab.x, dz2_j)), M::sqrt(M::add(dx2ab.y, dz2_j)), c.nks_shear, c.kd_shear);
+                gA  = oc_march2_redo<M, WC>(sm, 5, sl, pa, M::sqrt(M::add(dx2ma.x, dz2_j)), M::sqrt(M::add(dx2ma.y, dz2_j)), c.nks_shear, c.kd_shear);
             }
             if (!kInterior || !kSteady) {
                 // Window columns at a cloth edge: a spring to (or from) a column that does not exist is multiplied
@@ -383,7 +385,7 @@ struct OcMarch2 {
             p0.z = p_sub(p_add(p_sump<M>(p_mul(p_bc(c.im[2][2]), n.z), p_sump<M>(p_mul(p_bc(c.im[2][1]), n.y), p_mul(p_bc(c.im[2][0]), n.x), c.one), c.one), p_bc(c.im[2][3])), p_bc(c.center[2]));
             const float2 sq = p_sump<M>(p_mul(p0.z, p0.z), p_sump<M>(p_mul(p0.y, p0.y), p_mul(p0.x, p0.x), c.one), c.one);
             bool hit_a = sq.x < 1.0f, hit_b = sq.y < 1.0f;                                           // V:513-514 (see oc_core.cuh)
-            if (hit_a | hit_b) {
+            if (__builtin_expect(hit_a | hit_b, 0)) {
 #ifdef __CUDA_ARCH__
                 if (c.dbg & 4) { atomicAdd(c.dbg_cnt + 3, 1ull); if ((threadIdx.x & 31) == __ffs(__activemask()) - 1) atomicAdd(c.dbg_cnt + 3, 1ull << 32); }
 #endif
