@@ -21,6 +21,13 @@
 #include "oc_core.cuh"
 #include "oc_march.cuh"
 
+#ifndef OC_M2_UNROLL_EXACT
+#define OC_M2_UNROLL_EXACT 0
+#endif
+#ifndef OC_M2_UNROLL
+#define OC_M2_UNROLL 2      // copies of the fast-mode steady loop body (see oc_march2_body)
+#endif
+
 template <int WC>
 struct OcSmem2 {
     float X[6][OC_RING][WC + 4];        // x, y, z, vx, vy, vz     slot = row & 3, index = window column + 2
@@ -71,30 +78,35 @@ OC_HD OcPair3 oc_spring2v(const OcPair3& px, const OcPair3& pv, const OcPair3& q
     return f;
 }
 
-// Cold path of exact mode: one spring pair of the thread redone with the IEEE intrinsics.  The operands
-// are re-read from shared memory (nothing of the hot loop has its address taken) and the result comes
-// back by value.  kind: 0 (+1,0)  1 (+2,0)  2 (0,+1)  3 (0,+2)  4 (+1,+1)  5 (-1,+1)
-template <class M, int WC>
+// Cold paths.  They are kept OUT OF LINE (noinline, scalar arguments and results in registers, operands re-read from
+// shared memory, constants through a pointer to the __grid_constant__ kernel parameter): the steady loop of exact
+// mode is bound by instruction issue and instruction-cache reach, and inlined the three of them were 516 of its
+// 1183 instructions.
 #ifdef __CUDA_ARCH__
-__device__ __noinline__
+#define OC_COLD __device__ __noinline__
 #else
-inline
+#define OC_COLD inline
 #endif
-OcPair3 oc_march2_redo(const OcSmem2<WC>* s, int kind, int sl, int pa, float rest_a, float rest_b, float nks, float kd)
+// One spring pair of the thread redone with the IEEE intrinsics.
+// kind: 0 (+1,0)  1 (+2,0)  2 (0,+1)  3 (0,+2)  4 (+1,+1)  5 (-1,+1); for 4 and 5 rest_* are the SQUARED rest lengths.
+template <class M, int WC>
+OC_COLD OcPair3 oc_march2_redo(const OcConst* c, const OcSmem2<WC>* s, int kind, int sl, int pa, float rest_a, float rest_b)
 {
     const int s1 = (sl + 1) & (OC_RING - 1), s2 = (sl + 2) & (OC_RING - 1);
 #define OC_LDX(slot, col) make_f3(s->X[0][slot][col], s->X[1][slot][col], s->X[2][slot][col])
 #define OC_LDV(slot, col) make_f3(s->X[3][slot][col], s->X[4][slot][col], s->X[5][slot][col])
     // partner of a / of b: (slot, column)
     int sa = sl, ca = pa, sb = sl, cb = pa;
+    float nks = c->nks_struct, kd = c->kd_struct;
     switch (kind) {
     case 0: sa = sl; ca = pa + 1; sb = sl; cb = pa + 2; break;
-    case 1: sa = sl; ca = pa + 2; sb = sl; cb = pa + 3; break;
+    case 1: sa = sl; ca = pa + 2; sb = sl; cb = pa + 3; nks = c->nks_bend; kd = c->kd_bend; break;
     case 2: sa = s1; ca = pa;     sb = s1; cb = pa + 1; break;
-    case 3: sa = s2; ca = pa;     sb = s2; cb = pa + 1; break;
-    case 4: sa = s1; ca = pa + 1; sb = s1; cb = pa + 2; break;
-    default: sa = s1; ca = pa - 1; sb = s1; cb = pa;    break;
+    case 3: sa = s2; ca = pa;     sb = s2; cb = pa + 1; nks = c->nks_bend; kd = c->kd_bend; break;
+    case 4: sa = s1; ca = pa + 1; sb = s1; cb = pa + 2; nks = c->nks_shear; kd = c->kd_shear; break;
+    default: sa = s1; ca = pa - 1; sb = s1; cb = pa;    nks = c->nks_shear; kd = c->kd_shear; break;
     }
+    if (kind >= 4) { rest_a = M::sqrt(rest_a); rest_b = M::sqrt(rest_b); }
     const f3 fa = oc_spring<M>(OC_LDX(sl, pa),     OC_LDV(sl, pa),     OC_LDX(sa, ca), OC_LDV(sa, ca), rest_a, nks, kd);
     const f3 fb = oc_spring<M>(OC_LDX(sl, pa + 1), OC_LDV(sl, pa + 1), OC_LDX(sb, cb), OC_LDV(sb, cb), rest_b, nks, kd);
 #undef OC_LDX
@@ -102,6 +114,30 @@ OcPair3 oc_march2_redo(const OcSmem2<WC>* s, int kind, int sl, int pa, float res
     OcPair3 f;
     f.x = make_float2(fa.x, fb.x); f.y = make_float2(fa.y, fb.y); f.z = make_float2(fa.z, fb.z);
     return f;
+}
+// (X - X_last) / dt of both particles with the IEEE division (an operand left the range of the branch-free form)
+template <class M>
+OC_COLD OcPair3 oc_march2_vel_slow(OcPair3 d, float dt)
+{
+    OcPair3 v;
+    v.x = make_float2(M::div(d.x.x, dt), M::div(d.x.y, dt));
+    v.y = make_float2(M::div(d.y.x, dt), M::div(d.y.y, dt));
+    v.z = make_float2(M::div(d.z.x, dt), M::div(d.z.y, dt));
+    return v;
+}
+// EllipsoidCollision of one particle that is inside the collider (V:514-530): p0 = X_0 - center, sq = dot(p0, p0),
+// n = the integrated position; returns the projected position.
+template <class M>
+OC_COLD f3 oc_march2_collide(const OcConst* c, f3 d0, float sq, f3 n)
+{
+    const float distance = M::sqrt(sq);
+    const float sc = M::sub(c->radius, distance);                                    // V:515
+    if (M::kExact) d0 = make_f3(M::div(M::mul(sc, d0.x), distance), M::div(M::mul(sc, d0.y), distance), M::div(M::mul(sc, d0.z), distance));
+    else { const float q = M::div(sc, distance); d0 = make_f3(q * d0.x, q * d0.y, q * d0.z); }
+    const float ddx = M::dot(d0, make_f3(c->tinv[0][0], c->tinv[0][1], c->tinv[0][2]));     // V:520-528
+    const float ddy = M::dot(d0, make_f3(c->tinv[1][0], c->tinv[1][1], c->tinv[1][2]));
+    const float ddz = M::dot(d0, make_f3(c->tinv[2][0], c->tinv[2][1], c->tinv[2][2]));
+    return make_f3(M::add(n.x, ddx), M::add(n.y, ddy), M::add(n.z, ddz));
 }
 
 // F (+|-)= g for both particles, or per half under predicates
@@ -177,9 +213,7 @@ struct OcMarch2 {
             q0 = p_mul(d.z, y);        v.z = p_fma(y, p_fma(q0, nd, d.z), q0);
             if (__builtin_expect(badv, 0)) {
                 if (c.dbg & 4) atomicAdd(c.dbg_cnt + 2, 1ull);
-                v.x = make_float2(M::div(d.x.x, c.dt), M::div(d.x.y, c.dt));
-                v.y = make_float2(M::div(d.y.x, c.dt), M::div(d.y.y, c.dt));
-                v.z = make_float2(M::div(d.z.x, c.dt), M::div(d.z.y, c.dt));
+                v = oc_march2_vel_slow<M>(d, c.dt);
             }
         } else
 #endif
@@ -279,12 +313,12 @@ struct OcMarch2 {
                     if ((threadIdx.x & 31) == __ffs(__activemask()) - 1) atomicAdd(c.dbg_cnt + 1, 1ull);
                 }
 #endif
-                gH1 = oc_march2_redo<M, WC>(sm, 0, sl, pa, rh1.x, rh1.y, c.nks_struct, c.kd_struct);
-                gH2 = oc_march2_redo<M, WC>(sm, 1, sl, pa, rh2.x, rh2.y, c.nks_bend, c.kd_bend);
-                gV1 = oc_march2_redo<M, WC>(sm, 2, sl, pa, rv1_j, rv1_j, c.nks_struct, c.kd_struct);
-                gV2 = oc_march2_redo<M, WC>(sm, 3, sl, pa, rv2_j, rv2_j, c.nks_bend, c.kd_bend);
-                gD  = oc_march2_redo<M, WC>(sm, 4, sl, pa, M::sqrt(M::add(dx2ab.x, dz2_j)), M::sqrt(M::add(dx2ab.y, dz2_j)), c.nks_shear, c.kd_shear);
-                gA  = oc_march2_redo<M, WC>(sm, 5, sl, pa, M::sqrt(M::add(dx2ma.x, dz2_j)), M::sqrt(M::add(dx2ma.y, dz2_j)), c.nks_shear, c.kd_shear);
+                gH1 = oc_march2_redo<M, WC>(&c, sm, 0, sl, pa, rh1.x, rh1.y);
+                gH2 = oc_march2_redo<M, WC>(&c, sm, 1, sl, pa, rh2.x, rh2.y);
+                gV1 = oc_march2_redo<M, WC>(&c, sm, 2, sl, pa, rv1_j, rv1_j);
+                gV2 = oc_march2_redo<M, WC>(&c, sm, 3, sl, pa, rv2_j, rv2_j);
+                gD  = oc_march2_redo<M, WC>(&c, sm, 4, sl, pa, M::add(dx2ab.x, dz2_j), M::add(dx2ab.y, dz2_j));
+                gA  = oc_march2_redo<M, WC>(&c, sm, 5, sl, pa, M::add(dx2ma.x, dz2_j), M::add(dx2ma.y, dz2_j));
             }
             if (!kInterior || !kSteady) {
                 // Window columns at a cloth edge: a spring to (or from) a column that does not exist is multiplied
@@ -385,23 +419,16 @@ struct OcMarch2 {
             p0.z = p_sub(p_add(p_sump<M>(p_mul(p_bc(c.im[2][2]), n.z), p_sump<M>(p_mul(p_bc(c.im[2][1]), n.y), p_mul(p_bc(c.im[2][0]), n.x), c.one), c.one), p_bc(c.im[2][3])), p_bc(c.center[2]));
             const float2 sq = p_sump<M>(p_mul(p0.z, p0.z), p_sump<M>(p_mul(p0.y, p0.y), p_mul(p0.x, p0.x), c.one), c.one);
             bool hit_a = sq.x < 1.0f, hit_b = sq.y < 1.0f;                                           // V:513-514 (see oc_core.cuh)
-            if (__builtin_expect(hit_a | hit_b, 0)) {
 #ifdef __CUDA_ARCH__
-                if (c.dbg & 4) { atomicAdd(c.dbg_cnt + 3, 1ull); if ((threadIdx.x & 31) == __ffs(__activemask()) - 1) atomicAdd(c.dbg_cnt + 3, 1ull << 32); }
+            if ((c.dbg & 4) && (hit_a | hit_b)) { atomicAdd(c.dbg_cnt + 3, 1ull); if ((threadIdx.x & 31) == __ffs(__activemask()) - 1) atomicAdd(c.dbg_cnt + 3, 1ull << 32); }
 #endif
-                for (int hh = 0; hh < 2; ++hh) {
-                    if (!(hh ? hit_b : hit_a)) continue;
-                    f3 d0 = hh ? make_f3(p0.x.y, p0.y.y, p0.z.y) : make_f3(p0.x.x, p0.y.x, p0.z.x);
-                    const float distance = M::sqrt(hh ? sq.y : sq.x);
-                    const float sc = M::sub(c.radius, distance);                                    // V:515
-                    if (M::kExact) d0 = make_f3(M::div(M::mul(sc, d0.x), distance), M::div(M::mul(sc, d0.y), distance), M::div(M::mul(sc, d0.z), distance));
-                    else { const float q = M::div(sc, distance); d0 = make_f3(q * d0.x, q * d0.y, q * d0.z); }
-                    const float ddx = M::dot(d0, make_f3(c.tinv[0][0], c.tinv[0][1], c.tinv[0][2]));     // V:520-528
-                    const float ddy = M::dot(d0, make_f3(c.tinv[1][0], c.tinv[1][1], c.tinv[1][2]));
-                    const float ddz = M::dot(d0, make_f3(c.tinv[2][0], c.tinv[2][1], c.tinv[2][2]));
-                    if (hh) { n.x.y = M::add(n.x.y, ddx); n.y.y = M::add(n.y.y, ddy); n.z.y = M::add(n.z.y, ddz); }
-                    else    { n.x.x = M::add(n.x.x, ddx); n.y.x = M::add(n.y.x, ddy); n.z.x = M::add(n.z.x, ddz); }
-                }
+            if (__builtin_expect(hit_a, 0)) {
+                const f3 r = oc_march2_collide<M>(&c, make_f3(p0.x.x, p0.y.x, p0.z.x), sq.x, make_f3(n.x.x, n.y.x, n.z.x));
+                n.x.x = r.x; n.y.x = r.y; n.z.x = r.z;
+            }
+            if (__builtin_expect(hit_b, 0)) {
+                const f3 r = oc_march2_collide<M>(&c, make_f3(p0.x.y, p0.y.y, p0.z.y), sq.y, make_f3(n.x.y, n.y.y, n.z.y));
+                n.x.y = r.x; n.y.y = r.y; n.z.y = r.z;
             }
             const long long o = goff + (long long)row * U;
             if (sta) C[o]     = make_float4(n.x.x, n.y.x, n.z.x, oc_u2f(hit_a ? OC_W_HIT : OC_W_PLAIN));
@@ -554,6 +581,17 @@ OC_HD void oc_march2_body(Ctx& ctx, const OcConst& c, const float4* __restrict__
 #endif
         if (phase == 0) {
             if (interior) {
+                // fast mode: two copies of the body, which removes most of the register moves that rotate the
+                // loop-carried rows (measured +2.6 %; three copies are slower again).  Exact mode is not unrolled: its
+                // 2 x 11 KB of hot code, with the cold fallback blocks interleaved, misses in the instruction cache
+                // and loses 10 %.
+                if (!M::kExact || OC_M2_UNROLL_EXACT) {
+#if OC_M2_UNROLL == 3
+                    for (; it + 2 < it_hi; it += 3) { m.template iter<true, true, -1>(it); m.template iter<true, true, -1>(it + 1); m.template iter<true, true, -1>(it + 2); }
+#elif OC_M2_UNROLL == 2
+                    for (; it + 1 < it_hi; it += 2) { m.template iter<true, true, -1>(it); m.template iter<true, true, -1>(it + 1); }
+#endif
+                }
                 for (; it < it_hi; ++it) m.template iter<true, true, -1>(it);
             } else {
                 for (; it < it_hi; ++it) m.template iter<true, false, -1>(it);
@@ -569,6 +607,7 @@ OC_HD void oc_march2_body(Ctx& ctx, const OcConst& c, const float4* __restrict__
 #ifndef OC_CTAS_M2
 #define OC_CTAS_M2 4
 #endif
+
 #ifdef OC_M2_MAXNREG
 #define OC_M2_BOUNDS __maxnreg__(OC_M2_MAXNREG)
 #else
@@ -585,7 +624,7 @@ struct OcDevCtx2 {          // grid = (tiles, 1, batch): the tile -> (strip, seg
 };
 template <class M, int WC>
 __global__ void OC_M2_BOUNDS
-oc_k_march2(OcConst c, const float4* __restrict__ A, const float4* __restrict__ B, float4* __restrict__ C,
+oc_k_march2(const __grid_constant__ OcConst c, const float4* __restrict__ A, const float4* __restrict__ B, float4* __restrict__ C,
             int ra, int rb, OcSeg2 seg, int x_halo)
 {
     if ((c.dbg & 8) && threadIdx.x == 0) oc_timeline_mark(c, 0);
