@@ -280,6 +280,26 @@ def run_ours(args):
                 "clocks": clocks, "gpu_launches": launches}
         if e2e is not None:
             line["e2e"] = e2e
+        if world == 1 and args.workload == "cloth":
+            # the library's other arithmetic mode on the same workload (not the headline; CUDA events in oc_step_timed)
+            other = oc.Cloth(nx, ny, device=local, exact=0 if exact else 1, substeps_per_launch=args.k)
+            other.step(max(W, 3))
+            n_o = max(3, min(K, 500))
+            o_ms = other.step_timed(n_o)
+            o_val = nx * ny * n_o / (o_ms * 1e-3)
+            other.close()
+            line["other_mode"] = {"mode": "fast" if exact else "exact", "value": o_val, "unit": UNIT, "steps": n_o,
+                                  "roofline_frac": o_val * ALG_BYTES_PER_UPDATE / 1e9 / peak}
+        if world == 1 and args.workload == "cloth" and nx != 8192:
+            # N > 1 runs split the 8192^2 cloth of BASELINE config 4 (strong scaling): its 1-GPU rate, measured here, is
+            # the base a parallel efficiency has to be computed against (not this line's 2048^2 value)
+            big = oc.Cloth(8192, 8192, device=local, exact=exact, substeps_per_launch=args.k)
+            big.step(max(W, 3))
+            n_b = max(3, min(K, 300))
+            b_ms = big.step_timed(n_b)
+            big.close()
+            line["scaling_base"] = {"workload": "8192x8192 cloth, single B200 (the N>1 workload on one GPU)", "value": 8192 * 8192 * n_b / (b_ms * 1e-3),
+                                    "unit": UNIT, "steps": n_b, "mode": args.mode}
         if world == 1 and not args.no_cpu_baseline:
             base, _ = cpu_reference(nx, 3, 1, budget_s=15.0)
             line["cpu_baseline"] = base

@@ -1,0 +1,32 @@
+#!/usr/bin/env python
+"""Small runs of every kernel for compute-sanitizer (memcheck / racecheck / initcheck); development tool.
+  compute-sanitizer --tool racecheck python tools/sanitize_small.py"""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import opencloth_b200 as oc  # noqa: E402
+
+for kernel, k in ((1, 1), (2, 1), (2, 4), (3, 1)):
+    for exact in (1, 0):
+        for nx, ny, batch in ((150, 70, 1), (37, 23, 3), (260, 40, 1)):
+            c = oc.Cloth(nx, ny, batch=batch, kernel=kernel, exact=exact, substeps_per_launch=k)
+            c.step(12)
+            x, xl = c.download()
+            assert np.isfinite(x).all()
+            c.close()
+            print("ok", kernel, k, exact, nx, ny, batch, flush=True)
+# row bands in one process (halo exchange copies, band launches)
+import ctypes  # noqa: E402
+from opencloth_b200 import _abi  # noqa: E402
+bands = [oc.Cloth(150, 64, row_begin=0, row_end=32, halo_rows=8, kernel=3), oc.Cloth(150, 64, row_begin=32, row_end=64, halo_rows=8, kernel=3)]
+arr = (ctypes.c_void_p * 2)(*[b._h for b in bands])
+for _ in range(3):
+    _abi.check(_abi.load().oc_halo_exchange(arr, 2))
+    for b in bands:
+        b.step(4)
+for b in bands:
+    b.download()
+print("bands ok")
