@@ -648,7 +648,7 @@ __global__ void oc_k_selftest(unsigned long long per_thread, unsigned seed, floa
                 if ((r & 0x100000u) && k >= 2) b ^= 0x80000000u;
                 return __uint_as_float(b);
             };
-            OcRange rg; rg.init(); OcRangeVel rv; rv.init();
+            OcRange rg; rg.init(); OcRangeStrict rv; rv.init();
             bool ref_sq = false, ref_num = false, ref_vel = false;
             const int n_ops = 1 + (int)(oc_rng(st) & 3u);
             for (int k = 0; k < n_ops; ++k) {
@@ -657,7 +657,7 @@ __global__ void oc_k_selftest(unsigned long long per_thread, unsigned seed, floa
                 ref_sq |= oc_bad_sqr(fs); ref_num |= oc_bad_num(fn, OC_NUM_LO_BITS, OC_NUM_HI_BITS); ref_vel |= oc_bad_vel(fv, OC_VEL_LO_BITS, OC_VEL_HI_BITS);
             }
             if (rg.bad() != (ref_sq | ref_num)) bad_count += 1ull << 48;
-            if (rv.bad() != ref_vel) bad_count += 1ull << 48;
+            if (rv.bad(OC_VEL_LO_BITS, OC_VEL_HI_BITS) != ref_vel) bad_count += 1ull << 48;
         }
         // packed FP32x2 forms: primitive ops and the pair sequences of the marching kernel
         {
