@@ -66,7 +66,11 @@ struct oc_cloth {
     size_t    stage_bytes;
     double*   d_energy;
     unsigned long long* d_dbg;   // development counters (OC_DEBUG & 4)
+    OcChain2  chain;             // tile-level dependencies between consecutive oc_k_march2 launches (oc_march2.cuh)
 };
+#define OC_CHAIN_CAP (1 << 16)
+// anything that writes the state other than the chained kernel itself, or reorders the stream, breaks the chain
+static inline void chain_break(oc_cloth* c) { c->chain.valid = false; }
 
 static int free_handle(oc_cloth* c)
 {
@@ -77,6 +81,7 @@ static int free_handle(oc_cloth* c)
     if (c->stage[1]) cudaFree(c->stage[1]);
     if (c->d_energy) cudaFree(c->d_energy);
     if (c->d_dbg) cudaFree(c->d_dbg);
+    if (c->chain.flags) cudaFree(c->chain.flags);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->ev_ready) cudaEventDestroy(c->ev_ready);
@@ -262,6 +267,9 @@ extern "C" int oc_create(oc_cloth** out, const oc_params* p)
     OC_CREATE_CUDA(cudaMalloc(&c->d_dbg, OC_DBG_WORDS * sizeof(unsigned long long)));
     OC_CREATE_CUDA(cudaMemset(c->d_dbg, 0, OC_DBG_WORDS * sizeof(unsigned long long)));
     k.dbg_cnt = c->d_dbg;
+    OC_CREATE_CUDA(cudaMalloc(&c->chain.flags, OC_CHAIN_CAP * sizeof(unsigned)));
+    OC_CREATE_CUDA(cudaMemset(c->chain.flags, 0, OC_CHAIN_CAP * sizeof(unsigned)));
+    c->chain.cap = OC_CHAIN_CAP; c->chain.epoch = 0; c->chain.valid = false;
     OC_CREATE_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
     OC_CREATE_CUDA(cudaEventCreate(&c->ev0));
@@ -322,6 +330,7 @@ extern "C" int oc_set_stream(oc_cloth* c, void* s)
     OC_CUDA(cudaSetDevice(c->dev));
     OC_CUDA(cudaStreamSynchronize(c->stream));
     c->stream = s ? (cudaStream_t)s : c->own_stream;
+    chain_break(c);
     return OC_OK;
 }
 
@@ -355,6 +364,7 @@ extern "C" int oc_upload(oc_cloth* c, const float* X, const float* X_last, int s
     if (!c || !X || !X_last) return oc_fail(OC_ERR_INVALID, "oc_upload: null");
     if (stride != 3 && stride != 4) return oc_fail(OC_ERR_INVALID, "stride_floats must be 3 or 4");
     OC_CUDA(cudaSetDevice(c->dev));
+    chain_break(c);
     long long n = (long long)c->p.batch * c->rows_own * c->p.nx;
     size_t bytes = (size_t)n * stride * sizeof(float);
     int rc = ensure_stage(c, bytes);
@@ -394,6 +404,7 @@ extern "C" int oc_set_particle(oc_cloth* c, int cloth, int idx, const float xyz[
     if (!c || !xyz) return oc_fail(OC_ERR_INVALID, "oc_set_particle: null");
     if (cloth < 0 || cloth >= c->p.batch || idx < 0 || idx >= c->p.nx * c->p.ny)
         return oc_fail(OC_ERR_INVALID, "oc_set_particle: cloth %d / index %d out of range", cloth, idx);
+    chain_break(c);
     int j = idx / c->p.nx, i = idx % c->p.nx;
     if (j < c->k.row_lo || j >= c->k.row_lo + c->k.srows) return OC_OK;      // not stored by this band
     OC_CUDA(cudaSetDevice(c->dev));
@@ -422,16 +433,18 @@ static int launch_rows(oc_cloth* c, int kern, const OcLaunch& L, int ra, int rb)
     if (kern == OC_KERNEL_MARCH2) {
         int nl = 0;
         cudaError_t e = oc_march2_launch(c->k, c->p.exact != 0, ra, rb, c->sm_count,
-                                         c->buf[L.src_a], c->buf[L.src_b], c->buf[L.dst], c->stream, &nl);
+                                         c->buf[L.src_a], c->buf[L.src_b], c->buf[L.dst], c->stream, &nl, &c->chain);
         c->launches += nl;
         if (e != cudaSuccess) return oc_fail(OC_ERR_CUDA, "march2 kernel launch failed: %s", cudaGetErrorString(e));
     } else if (kern == OC_KERNEL_MARCH) {
+        chain_break(c);
         int nl = 0;
         cudaError_t e = oc_march_launch(c->k, c->p.exact != 0, L.S, ra, rb, c->sm_count,
                                         c->buf[L.src_a], c->buf[L.src_b], c->buf[L.dst], c->buf[L.dst_prev], c->stream, &nl);
         c->launches += nl;
         if (e != cudaSuccess) return oc_fail(OC_ERR_CUDA, "march kernel launch failed: %s", cudaGetErrorString(e));
     } else {
+        chain_break(c);
         dim3 blk(128, 1, 1), grd((c->p.nx + 127) / 128, rb - ra, c->p.batch);
         if (c->p.exact) oc_k_gather<MathExact><<<grd, blk, 0, c->stream>>>(c->k, c->buf[L.src_a], c->buf[L.src_b], c->buf[L.dst], ra);
         else            oc_k_gather<MathFast><<<grd, blk, 0, c->stream>>>(c->k, c->buf[L.src_a], c->buf[L.src_b], c->buf[L.dst], ra);
@@ -467,11 +480,16 @@ static int step_impl(oc_cloth* c, int n, cudaStream_t split_stream, bool want_sp
             rc = launch_rows(c, kern, L, L.ra, L.rb);
             if (rc) return rc;
         } else {
+            // three launches of ONE step over parts of the rows: each waits for the whole grid before it (no chaining)
+            chain_break(c);
             rc = launch_rows(c, kern, L, L.ra, L.ra + H);          if (rc) return rc;
+            chain_break(c);
             rc = launch_rows(c, kern, L, L.rb - H, L.rb);          if (rc) return rc;
             OC_CUDA(cudaEventRecord(c->ev_ready, c->stream));
             if (split_stream) OC_CUDA(cudaStreamWaitEvent(split_stream, c->ev_ready, 0));
+            chain_break(c);
             rc = launch_rows(c, kern, L, L.ra + H, L.rb - H);      if (rc) return rc;
+            chain_break(c);
             if (did_split) *did_split = 1;
         }
     }
@@ -520,6 +538,7 @@ extern "C" int oc_halo_recv_region(oc_cloth* c, int side, int which, void** p, s
 extern "C" int oc_halo_refreshed(oc_cloth* c)
 {
     if (!c) return oc_fail(OC_ERR_INVALID, "oc_halo_refreshed: null");
+    chain_break(c);              // the halo rows were written by something else (peer copy / NCCL receive)
     c->q.fresh = 0;
     return OC_OK;
 }
@@ -534,6 +553,7 @@ extern "C" int oc_halo_exchange(oc_cloth* const* bands, int n)
     if (!bands || n < 1) return oc_fail(OC_ERR_INVALID, "oc_halo_exchange: no bands");
     for (int b = 0; b < n; ++b) {
         if (!bands[b]) return oc_fail(OC_ERR_INVALID, "oc_halo_exchange: null band");
+        chain_break(bands[b]);
         if (b > 0 && (bands[b]->p.row_begin != bands[b - 1]->p.row_end || bands[b]->p.nx != bands[0]->p.nx ||
                       bands[b]->p.ny != bands[0]->p.ny || bands[b]->p.halo_rows != bands[0]->p.halo_rows))
             return oc_fail(OC_ERR_INVALID, "oc_halo_exchange: bands must be consecutive row bands of one cloth with equal halo_rows");

@@ -534,9 +534,34 @@ inline void oc_seg2_finish(OcSeg2& g, int rows)
     g.nseg_all = ni; g.n_extra = 2 * (ne - ni);
 }
 
+// tile index of (strip, segment) in the 1-D grid (inverse of oc_seg2_tile)
+OC_HD int oc_seg2_index(const OcSeg2& g, int bx, int by)
+{
+    return by < g.nseg_all ? bx + g.nstrips * by : g.nstrips * g.nseg_all + 2 * (by - g.nseg_all) + (bx == 0 ? 0 : 1);
+}
+
+// What a launch has to wait for before it touches the state.  Consecutive steps are consecutive kernels on one
+// stream, launched with programmatic stream serialization (the CTAs of step e+1 are placed while step e drains):
+//   mode 0: griddepcontrol.wait, i.e. the whole previous grid;
+//   mode 1: only the tiles of the previous launch that wrote what this tile reads: rows [r0-2, r1+2) of its own and
+//           the two neighbouring strips.  Every tile publishes flags[its index] = epoch (release, after its last
+//           store); a tile of the next launch polls the <= 12 flags it depends on (acquire).  This removes the
+//           barrier between steps: a tile starts as soon as its neighbourhood is done, so the slow tail of one
+//           launch overlaps the head of the next.  Older data (X(t-1), and the buffer being overwritten, last read
+//           two steps ago) is covered transitively: the tiles waited for have themselves waited for theirs.
+// The host only chains launches whose predecessor on the stream is the previous oc_k_march2 launch of the same handle
+// (anything else that writes the state resets the chain to mode 0).
+struct OcDep2 {
+    unsigned* flags;          // one word per tile; nullptr: do not publish
+    unsigned  epoch;          // this launch
+    int       mode;
+    int       pra, prb;       // previous launch: row range and segmentation
+    OcSeg2    pseg;
+};
+
 template <class M, int WC, class Ctx>
 OC_HD void oc_march2_body(Ctx& ctx, const OcConst& c, const float4* __restrict__ A, const float4* __restrict__ B,
-                          float4* __restrict__ C, int ra, int rb, OcSeg2 seg, int x_halo)
+                          float4* __restrict__ C, int ra, int rb, OcSeg2 seg, int x_halo, const OcDep2& dep)
 {
     OcMarch2<M, WC, Ctx> m(ctx, c);
     m.A = A; m.B = B; m.C = C;
@@ -548,7 +573,7 @@ OC_HD void oc_march2_body(Ctx& ctx, const OcConst& c, const float4* __restrict__
     const int ga = cx0 + 2 * i, gb = ga + 1;
     int r0, r1;
     oc_seg2_rows(seg, ctx.bx(), ctx.by(), ra, rb, r0, r1);
-    if (r0 >= r1) return;                           // CTA-uniform: no rows left for this tile
+    if (r0 >= r1) { ctx.wait_deps(dep, c, r0, r0); return; }      // CTA-uniform: no rows left for this tile (it still orders itself after its predecessors)
     m.i = i; m.pa = 2 * i + 2; m.ga = ga; m.U = U; m.V = V;
     int lo = r0, hi = r1;
     int plo = lo - 2; if (plo < 0) plo = 0;
@@ -609,6 +634,7 @@ OC_HD void oc_march2_body(Ctx& ctx, const OcConst& c, const float4* __restrict__
 #ifdef __CUDA_ARCH__
     if ((c.dbg & 8) && i == 0) oc_timeline_mark(c, 1);       // development: CTA timeline (OC_DEBUG=8)
 #endif
+    ctx.wait_deps(dep, c, r0, r1);
     int it = 0;
     for (int phase = 0; phase < 2; ++phase) {
         const int end = phase == 0 ? it_lo : n_it;
@@ -658,23 +684,71 @@ struct OcDevCtx2 {          // grid = (tiles, 1, batch): the tile -> (strip, seg
     __device__ __forceinline__ int bz() const { return blockIdx.z; }
     __device__ __forceinline__ void sync() const { __syncthreads(); }
     __device__ __forceinline__ unsigned char* smem() const { extern __shared__ __align__(16) unsigned char oc_dyn_smem[]; return oc_dyn_smem; }
+    // Programmatic dependent launch: everything before this point (set-up, table loads, shared-memory pads) may
+    // overlap the previous launch; the state buffers are only touched after it.  See OcDep2.
+    __device__ __forceinline__ void wait_deps(const OcDep2& d, const OcConst& c, int r0, int r1) const
+    {
+        if (d.mode == 0) { asm volatile("griddepcontrol.wait;" ::: "memory"); return; }
+        const int t = threadIdx.x;
+        if (t < 12) {
+            const int xs = x - 1 + t / 4, k = t % 4;
+            const int lo = r0 - 2 < d.pra ? d.pra : r0 - 2, hi = r1 + 2 > d.prb ? d.prb : r1 + 2;      // rows this tile reads
+            if (xs >= 0 && xs < d.pseg.nstrips && lo < hi) {
+                const int h = (xs == 0 || xs == d.pseg.nstrips - 1) ? d.pseg.rs_e : d.pseg.rs;
+                const int y = (lo - d.pra) / h + k, y_hi = (hi - 1 - d.pra) / h;
+                if (y <= y_hi) {
+                    const unsigned* p = d.flags + oc_seg2_index(d.pseg, xs, y);
+                    const unsigned want = d.epoch - 1u;
+                    unsigned v, spins = 0, ns = 200;
+                    for (;;) {
+                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+                        if ((int)(v - want) >= 0) break;
+                        __nanosleep(ns);                                   // back off: the polls go to L2
+                        if (ns < 1600) ns += ns;
+                        if (++spins > (1u << 21)) { atomicAdd(c.dbg_cnt + 2, 1ull << 40); break; }      // > 1 s: never in a correct chain
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    // after the tile's last store
+    __device__ __forceinline__ void publish(const OcDep2& d) const
+    {
+        if (!d.flags) return;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(d.flags + blockIdx.x), "r"(d.epoch) : "memory");
+        }
+    }
 };
 template <class M, int WC>
 __global__ void OC_M2_BOUNDS
 oc_k_march2(const __grid_constant__ OcConst c, const float4* __restrict__ A, const float4* __restrict__ B, float4* __restrict__ C,
-            int ra, int rb, OcSeg2 seg, int x_halo)
+            int ra, int rb, OcSeg2 seg, int x_halo, const __grid_constant__ OcDep2 dep)
 {
+    asm volatile("griddepcontrol.launch_dependents;");      // the next step may be placed as soon as CTA slots free up
     if ((c.dbg & 8) && threadIdx.x == 0) oc_timeline_mark(c, 0);
     OcDevCtx2 ctx;
     oc_seg2_tile(seg, blockIdx.x, ctx.x, ctx.y);
-    oc_march2_body<M, WC, OcDevCtx2>(ctx, c, A, B, C, ra, rb, seg, x_halo);
+    oc_march2_body<M, WC, OcDevCtx2>(ctx, c, A, B, C, ra, rb, seg, x_halo, dep);
+    ctx.publish(dep);
 }
 #endif
 
 // ---- host side (oc_march.cu) -------------------------------------------------------------------
 int  oc_march2_configure(int device);
 int  oc_march2_plan(const OcConst& c, bool exact, int ra, int rb, int sm_count, int occ_hint, OcMarchPlan* plan, OcSeg2* seg);
+// host side of OcDep2: the chain of launches of one handle
+struct OcChain2 {
+    unsigned* flags; int cap;      // device flag words
+    unsigned  epoch;
+    bool      valid;               // the previous stream operation of the handle was the launch described below
+    int       pra, prb;
+    OcSeg2    pseg;
+};
 #ifdef __CUDACC__
 cudaError_t oc_march2_launch(const OcConst& c, bool exact, int ra, int rb, int sm_count,
-                             const float4* A, const float4* B, float4* C, cudaStream_t stream, int* n_launches);
+                             const float4* A, const float4* B, float4* C, cudaStream_t stream, int* n_launches, OcChain2* chain);
 #endif

@@ -36,6 +36,7 @@ struct EmuCtx {
     int by() const { return by_; }
     int bz() const { return bz_; }
     unsigned char* smem() const { return smem_; }
+    void wait_deps(const OcDep2&, const OcConst&, int, int) const {}       // the emulator runs the tiles of a launch one after the other
     void sync();
 };
 
@@ -213,7 +214,7 @@ static int emu_march2(EmuCloth* e, const OcLaunch& L, int RS)
             oc_seg2_tile(seg, t, bx, by);
             int ra = L.ra, rb = L.rb;
             rc |= run_cta(WC / 2, bx, by, bz, sizeof(OcSmem2<WC>), [&](EmuCtx& ctx) {
-                oc_march2_body<M, WC, EmuCtx>(ctx, k, A, B, C, ra, rb, seg, x_halo);
+                oc_march2_body<M, WC, EmuCtx>(ctx, k, A, B, C, ra, rb, seg, x_halo, OcDep2());
             });
         }
     return rc;

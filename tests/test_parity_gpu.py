@@ -125,6 +125,44 @@ def test_large_grid_matches_oracle_2048():
         c.close()
 
 
+@pytest.mark.parametrize("nx,ny,steps", [(2048, 2048, 3000), (4096, 1200, 600), (1100, 5000, 600)])
+def test_chained_launches_match_gather_kernel_full_size(nx, ny, steps):
+    """Consecutive oc_k_march2 launches are chained by programmatic dependent launch and per-tile flags instead
+    of a barrier between steps (OcDep2; active for tiles of >= 32 rows, i.e. only at full size).  The gather
+    kernel (one thread per particle, plain launches) is the independent on-device reference: bitwise equal
+    after thousands of chained steps, across everything that breaks and restarts the chain (download,
+    oc_set_particle, upload, a change of time step), and no dependency wait may ever time out."""
+    import ctypes
+    m = oc()
+    a = m.Cloth(nx, ny, kernel=m.OC_KERNEL_MARCH2)
+    g = m.Cloth(nx, ny, kernel=m.OC_KERNEL_GATHER)
+    done = 0
+    plan = [1, 2, 7, 50, 3, 1, 1, 200]
+    i = 0
+    while done < steps:
+        n = min(plan[i % len(plan)] if i < 24 else 400, steps - done)
+        a.step(n); g.step(n); done += n
+        if i % 4 == 1:
+            xa, xla = a.download(); xg, xlg = g.download()
+            assert bitwise_equal(xa, xg) and bitwise_equal(xla, xlg), f"after {done} steps: {nbad(xa, xg)} particles differ"
+        if i == 5:
+            for c in (a, g):
+                c.set_particle((ny // 2) * nx + nx // 3, (0.25, 3.0, -0.5))
+        if i == 9:
+            xa, xla = a.download()
+            a.upload(xa, xla); g.upload(xa, xla)
+        if i == 13:
+            for c in (a, g):
+                c.set_params(dt=1.0 / 90.0)
+        i += 1
+    xa, xla = a.download(); xg, xlg = g.download()
+    assert bitwise_equal(xa, xg) and bitwise_equal(xla, xlg), f"{nbad(xa, xg)} particles differ"
+    out = (ctypes.c_ulonglong * 4)()
+    a._lib.oc_debug_counters(a._h, out)
+    assert (out[2] >> 40) == 0, "a tile-dependency wait timed out"
+    a.close(); g.close()
+
+
 def test_upload_download_round_trip_and_strides():
     m = oc()
     rng = np.random.RandomState(0)
