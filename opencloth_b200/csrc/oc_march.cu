@@ -165,7 +165,7 @@ int oc_march2_configure(int device)
     return 0;
 }
 
-int oc_march2_plan(const OcConst& c, bool exact, int ra, int rb, int sm_count, int occ_hint, OcMarchPlan* pl, OcSeg2* seg)
+int oc_march2_plan(const OcConst& c, bool exact, bool chained, int ra, int rb, int sm_count, int occ_hint, OcMarchPlan* pl, OcSeg2* seg)
 {
     const int U = c.U;
     const int WC = pick_wc(U);
@@ -188,6 +188,15 @@ int oc_march2_plan(const OcConst& c, bool exact, int ra, int rb, int sm_count, i
         double eff = (double)rows * nstrips * c.batch / ((double)waves * slots * (rs + fill));
         if (eff > best * 1.0001) { best = eff; best_rs = rs; }
     }
+    // Chained launches (OcDep2: the tiles of step e+1 start as those of step e finish) do not care about whole waves.
+    // What pays (measured at 2048^2, 4096^2, 8192^2, profiles/) is the tallest tile that still leaves ~15 % more tiles
+    // than CTA slots, so that a freed slot always finds a tile whose neighbourhood is done.
+    bool oversub = false;
+    if (chained && !(env && atoi(env) > 0) && c.batch == 1) {
+        const int nseg = (int)((slots * 115 / 100 + nstrips - 1) / nstrips);
+        const int rs = (rows + nseg - 1) / nseg;
+        if (nseg >= 1 && rs >= 32) { best_rs = rs; oversub = true; }
+    }
     pl->TW = WC; pl->S = 1; pl->x_halo = x_halo; pl->W_out = W_out; pl->nstrips = nstrips;
     pl->RS = best_rs; pl->nseg = (rows + best_rs - 1) / best_rs; pl->threads = WC / 2; pl->smem = smem2(WC);
     seg->rs = seg->rs_e = best_rs; seg->nstrips = nstrips; seg->nseg_all = pl->nseg; seg->n_extra = 0;
@@ -196,7 +205,7 @@ int oc_march2_plan(const OcConst& c, bool exact, int ra, int rb, int sm_count, i
     const char* ee = getenv("OC_MARCH2_EDGE");
     const int edge = ee ? atoi(ee) : (exact ? OC_MARCH2_EDGE_EXACT : OC_MARCH2_EDGE_FAST);
     const long long tiles = (long long)nstrips * pl->nseg;
-    if (!(env && atoi(env) > 0) && edge > 0 && c.batch == 1 && nstrips >= 3 && tiles <= slots) {
+    if (!oversub && !(env && atoi(env) > 0) && edge > 0 && c.batch == 1 && nstrips >= 3 && tiles <= slots) {
         for (int e = edge; e >= 4; e -= 2) {                          // the largest ratio whose extra edge tiles fit the same wave
             OcSeg2 g = *seg;
             g.rs_e = (int)((100.0 * g.rs) / (100.0 + e) + 0.5);
@@ -216,7 +225,10 @@ cudaError_t oc_march2_launch(const OcConst& c, bool exact, int ra, int rb, int s
     OcMarchPlan pl;
     const int WC = pick_wc(c.U);
     OcSeg2 seg;
-    if (oc_march2_plan(c, exact, ra, rb, sm_count, g_occ2[exact ? 1 : 0][WC == 128], &pl, &seg) != 0) return cudaErrorInvalidValue;
+    static const bool pdl = !(getenv("OC_PDL") && atoi(getenv("OC_PDL")) == 0);
+    static const bool tile_deps = !(getenv("OC_TILE_DEPS") && atoi(getenv("OC_TILE_DEPS")) == 0);
+    const bool chained = pdl && tile_deps && chain && chain->flags && c.batch == 1;
+    if (oc_march2_plan(c, exact, chained, ra, rb, sm_count, g_occ2[exact ? 1 : 0][WC == 128], &pl, &seg) != 0) return cudaErrorInvalidValue;
     const void* fn = exact ? oc_march2_fn_exact(WC) : oc_march2_fn_fast(WC);
     if (!fn) return cudaErrorInvalidDeviceFunction;
     if (c.batch > 65535) return cudaErrorInvalidConfiguration;
@@ -231,8 +243,6 @@ cudaError_t oc_march2_launch(const OcConst& c, bool exact, int ra, int rb, int s
     dim3 grid(oc_seg2_tiles(seg), 1, c.batch), block(pl.threads, 1, 1);
     OcConst cc = c;
     int xh = pl.x_halo;
-    static const bool pdl = !(getenv("OC_PDL") && atoi(getenv("OC_PDL")) == 0);
-    static const bool tile_deps = !(getenv("OC_TILE_DEPS") && atoi(getenv("OC_TILE_DEPS")) == 0);
     // dependencies on the previous launch (OcDep2)
     OcDep2 dep = {};
     const bool can_flag = chain && chain->flags && c.batch == 1 && oc_seg2_tiles(seg) <= chain->cap;

@@ -739,7 +739,7 @@ oc_k_march2(const __grid_constant__ OcConst c, const float4* __restrict__ A, con
 
 // ---- host side (oc_march.cu) -------------------------------------------------------------------
 int  oc_march2_configure(int device);
-int  oc_march2_plan(const OcConst& c, bool exact, int ra, int rb, int sm_count, int occ_hint, OcMarchPlan* plan, OcSeg2* seg);
+int  oc_march2_plan(const OcConst& c, bool exact, bool chained, int ra, int rb, int sm_count, int occ_hint, OcMarchPlan* plan, OcSeg2* seg);
 // host side of OcDep2: the chain of launches of one handle
 struct OcChain2 {
     unsigned* flags; int cap;      // device flag words
