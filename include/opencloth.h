@@ -157,6 +157,15 @@ int oc_step_split(oc_cloth* c, int n, void* exchange_stream, int* did_split);
  * next step, without blocking the host, then marks all bands refreshed. */
 int oc_halo_exchange(oc_cloth* const* bands, int n);
 
+/* ---- environment switches (development / measurement; read by the library, defaults in brackets) -------------
+ *   OC_PDL=0          launch oc_k_march2 without programmatic stream serialization              [on]
+ *   OC_TILE_DEPS=0    consecutive steps wait for the whole previous grid instead of per-tile flags [on]
+ *   OC_MARCH2_EDGE=p  un-chained single-wave launches: interior/edge rows per segment - 1, percent [24 exact, 10 fast]
+ *   OC_MARCH_RS=n, OC_MARCH_TW=n, OC_MARCH2_WC=n   force rows per segment / window width of the marching kernels
+ *   OC_DEBUG=bits     4: count fallbacks (oc_debug_counters)  8: CTA time line (oc_debug_timeline)
+ *                     16: print the launch plan to stderr  (1, 2: force / suppress the fallback of oc_k_march)
+ * None of them changes a result. */
+
 /* ---- diagnostics ----------------------------------------------------------------------------- */
 /* Spring energy  sum 1/2 Ks (|p1-p2| - rest)^2  over the reference's spring list (duplicated edge
  * bend springs included), reduced in double on the device; whole-cloth handles only. */
@@ -169,6 +178,9 @@ int oc_selftest_math(unsigned long long n, unsigned int seed, unsigned long long
 /* Development counters (only counted when the environment has OC_DEBUG=4 at oc_create): lanes and warps
  * that took the IEEE-intrinsic fallback of the exact-mode spring phase, velocity fallbacks; reset on read. */
 int oc_debug_counters(oc_cloth* c, unsigned long long out[4]);
+/* out[0], out[1]: lanes / warps that redid their springs with the IEEE intrinsics; out[2]: low 40 bits velocity
+ * fallbacks, bits 40..: tile-dependency waits that timed out (must be 0); out[3]: low 32 bits threads, high 32 bits
+ * warps that resolved a collider contact (oc_k_march2) */
 /* Development CTA time line of the last oc_k_march2 launch (only recorded with OC_DEBUG=8 at oc_create): 8 words
  * per CTA (linear index x + gridDim.x * (y + gridDim.y * z), first 4096 CTAs): %globaltimer at entry, set-up
  * done, lead-in done, steady loop done, exit; SM id; 2 unused.  Copies min(n_words, 8*4096) words. */
