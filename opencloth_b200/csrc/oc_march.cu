@@ -192,8 +192,9 @@ int oc_march2_plan(const OcConst& c, bool exact, bool chained, int ra, int rb, i
     // What pays (measured at 2048^2, 4096^2, 8192^2, profiles/) is the tallest tile that still leaves ~15 % more tiles
     // than CTA slots, so that a freed slot always finds a tile whose neighbourhood is done.
     bool oversub = false;
-    if (chained && !(env && atoi(env) > 0) && c.batch == 1) {
-        const int nseg = (int)((slots * 115 / 100 + nstrips - 1) / nstrips);
+    if (chained && !(env && atoi(env) > 0)) {
+        const long long per_seg = (long long)nstrips * c.batch;            // tiles per segment index (batched cloths: every cloth)
+        const int nseg = (int)((slots * 115 / 100 + per_seg - 1) / per_seg);
         const int rs = (rows + nseg - 1) / nseg;
         if (nseg >= 1 && rs >= 32) { best_rs = rs; oversub = true; }
     }
@@ -227,7 +228,7 @@ cudaError_t oc_march2_launch(const OcConst& c, bool exact, int ra, int rb, int s
     OcSeg2 seg;
     static const bool pdl = !(getenv("OC_PDL") && atoi(getenv("OC_PDL")) == 0);
     static const bool tile_deps = !(getenv("OC_TILE_DEPS") && atoi(getenv("OC_TILE_DEPS")) == 0);
-    const bool chained = pdl && tile_deps && chain && chain->flags && c.batch == 1;
+    const bool chained = pdl && tile_deps && chain && chain->flags;
     if (oc_march2_plan(c, exact, chained, ra, rb, sm_count, g_occ2[exact ? 1 : 0][WC == 128], &pl, &seg) != 0) return cudaErrorInvalidValue;
     const void* fn = exact ? oc_march2_fn_exact(WC) : oc_march2_fn_fast(WC);
     if (!fn) return cudaErrorInvalidDeviceFunction;
@@ -245,7 +246,7 @@ cudaError_t oc_march2_launch(const OcConst& c, bool exact, int ra, int rb, int s
     int xh = pl.x_halo;
     // dependencies on the previous launch (OcDep2)
     OcDep2 dep = {};
-    const bool can_flag = chain && chain->flags && c.batch == 1 && oc_seg2_tiles(seg) <= chain->cap;
+    const bool can_flag = chain && chain->flags && (long long)oc_seg2_tiles(seg) * c.batch <= chain->cap;      // one flag per tile and cloth
     if (can_flag) {
         dep.flags = chain->flags; dep.epoch = ++chain->epoch;
         const int h_max = seg.rs > seg.rs_e ? seg.rs : seg.rs_e;

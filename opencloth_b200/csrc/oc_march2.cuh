@@ -697,7 +697,7 @@ struct OcDevCtx2 {          // grid = (tiles, 1, batch): the tile -> (strip, seg
                 const int h = (xs == 0 || xs == d.pseg.nstrips - 1) ? d.pseg.rs_e : d.pseg.rs;
                 const int y = (lo - d.pra) / h + k, y_hi = (hi - 1 - d.pra) / h;
                 if (y <= y_hi) {
-                    const unsigned* p = d.flags + oc_seg2_index(d.pseg, xs, y);
+                    const unsigned* p = d.flags + (size_t)blockIdx.z * oc_seg2_tiles(d.pseg) + oc_seg2_index(d.pseg, xs, y);   // same cloth
                     const unsigned want = d.epoch - 1u;
                     unsigned v, spins = 0, ns = 200;
                     for (;;) {
@@ -719,7 +719,7 @@ struct OcDevCtx2 {          // grid = (tiles, 1, batch): the tile -> (strip, seg
         __syncthreads();
         if (threadIdx.x == 0) {
             __threadfence();
-            asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(d.flags + blockIdx.x), "r"(d.epoch) : "memory");
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(d.flags + (size_t)blockIdx.z * gridDim.x + blockIdx.x), "r"(d.epoch) : "memory");
         }
     }
 };
