@@ -43,10 +43,12 @@ typedef enum oc_status {
 } oc_status;
 
 typedef enum oc_kernel {
-    OC_KERNEL_AUTO = 0,      /* march2 for one substep per launch, march for k > 1 */
+    OC_KERNEL_AUTO = 0,      /* resident for small whole cloths, else march2 for one substep per launch, march for k > 1 */
     OC_KERNEL_GATHER = 1,    /* one thread per particle, 12-neighbour gather from global memory */
     OC_KERNEL_MARCH = 2,     /* fused shared-memory marching stencil, one column per thread, k substeps per launch */
-    OC_KERNEL_MARCH2 = 3     /* the same with two columns per thread (one substep per launch) */
+    OC_KERNEL_MARCH2 = 3,    /* the same with two columns per thread (one substep per launch) */
+    OC_KERNEL_RESIDENT = 4   /* small whole cloths (<= 1536 particles): one CTA per cloth keeps the state in shared memory
+                                and takes all the substeps of an oc_step call in one launch */
 } oc_kernel;
 
 typedef struct oc_cloth oc_cloth;      /* opaque; owns all device memory of one simulation */

@@ -21,6 +21,7 @@ OC_KERNEL_AUTO = 0
 OC_KERNEL_GATHER = 1
 OC_KERNEL_MARCH = 2
 OC_KERNEL_MARCH2 = 3
+OC_KERNEL_RESIDENT = 4
 
 
 class OcParams(ctypes.Structure):

@@ -9,6 +9,7 @@
 #include "oc_core.cuh"
 #include "oc_host.h"
 #include "oc_gather.cuh"
+#include "oc_resident.cuh"
 #include "oc_march.cuh"
 #include "oc_march2.cuh"
 
@@ -221,7 +222,7 @@ static int validate(const oc_params* p)
     if (!(p->dt > 0.0f) || !(p->mass > 0.0f)) return oc_fail(OC_ERR_INVALID, "dt and mass must be positive");
     if (p->substeps_per_launch < 0 || p->substeps_per_launch > OC_MARCH_MAX_STAGES)
         return oc_fail(OC_ERR_INVALID, "substeps_per_launch must be 0..%d", OC_MARCH_MAX_STAGES);
-    if (p->kernel < OC_KERNEL_AUTO || p->kernel > OC_KERNEL_MARCH2) return oc_fail(OC_ERR_INVALID, "bad kernel id");
+    if (p->kernel < OC_KERNEL_AUTO || p->kernel > OC_KERNEL_RESIDENT) return oc_fail(OC_ERR_INVALID, "bad kernel id");
     return OC_OK;
 }
 
@@ -419,9 +420,13 @@ extern "C" int oc_set_particle(oc_cloth* c, int cloth, int idx, const float xyz[
 // ------------------------------------------------------------------------------------------------
 static int pick_kernel(const oc_cloth* c)
 {
+    const bool can_reside = !c->q.band && (long long)c->p.nx * c->p.ny <= OC_RESIDENT_MAX_PARTICLES;
+    if (c->p.kernel == OC_KERNEL_RESIDENT) return can_reside ? OC_KERNEL_RESIDENT : OC_KERNEL_GATHER;
     if (c->p.kernel != OC_KERNEL_AUTO) return c->p.kernel;
-    // tiny problems are latency bound by the row march (one barrier per row): the gather kernel is quicker
-    if ((long long)c->p.nx * c->p.ny * c->p.batch <= 2048 && c->p.substeps_per_launch <= 1) return OC_KERNEL_GATHER;
+    // small whole cloths (the reference's own 21 x 21): state resident in shared memory, all substeps in one launch.
+    // One CTA per cloth: worth it while the CTA's 1024 threads cover the cloth's springs in a few passes (beyond that
+    // the gather kernel, which spreads one cloth over many SMs, or the marching kernel is quicker).
+    if (can_reside && c->p.substeps_per_launch <= 1 && (long long)c->p.nx * c->p.ny <= 1024) return OC_KERNEL_RESIDENT;
     // one substep per launch: the two-columns-per-thread kernel (fastest); k > 1: the staged one-column kernel
     return c->p.substeps_per_launch <= 1 ? OC_KERNEL_MARCH2 : OC_KERNEL_MARCH;
 }
@@ -436,6 +441,21 @@ static int launch_rows(oc_cloth* c, int kern, const OcLaunch& L, int ra, int rb)
                                          c->buf[L.src_a], c->buf[L.src_b], c->buf[L.dst], c->stream, &nl, &c->chain);
         c->launches += nl;
         if (e != cudaSuccess) return oc_fail(OC_ERR_CUDA, "march2 kernel launch failed: %s", cudaGetErrorString(e));
+    } else if (kern == OC_KERNEL_RESIDENT) {
+        chain_break(c);
+        const int N = c->p.nx * c->p.ny;
+        const size_t smem = OcResidentSmem::bytes(N);
+        int threads = (6 * N + 31) / 32 * 32; if (threads > OC_RESIDENT_THREADS) threads = OC_RESIDENT_THREADS;
+        static bool configured[2] = { false, false };
+        const void* fn = c->p.exact ? (const void*)&oc_k_resident<MathExact> : (const void*)&oc_k_resident<MathFast>;
+        if (!configured[c->p.exact ? 1 : 0]) {
+            OC_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OcResidentSmem::bytes(OC_RESIDENT_MAX_PARTICLES)));
+            configured[c->p.exact ? 1 : 0] = true;
+        }
+        if (c->p.exact) oc_k_resident<MathExact><<<c->p.batch, threads, smem, c->stream>>>(c->k, c->buf[L.src_a], c->buf[L.src_b], c->buf[L.dst], c->buf[L.dst_prev], L.S);
+        else            oc_k_resident<MathFast><<<c->p.batch, threads, smem, c->stream>>>(c->k, c->buf[L.src_a], c->buf[L.src_b], c->buf[L.dst], c->buf[L.dst_prev], L.S);
+        c->launches++;
+        OC_CUDA(cudaGetLastError());
     } else if (kern == OC_KERNEL_MARCH) {
         chain_break(c);
         int nl = 0;
@@ -469,7 +489,7 @@ static int step_impl(oc_cloth* c, int n, cudaStream_t split_stream, bool want_sp
     const int kern = pick_kernel(c);
     const int kdef = c->p.substeps_per_launch > 0 ? c->p.substeps_per_launch : 1;
     while (n > 0) {
-        const int kmaxS = (kern == OC_KERNEL_MARCH) ? oc_host_pick_stages(n < kdef ? n : kdef) : 1;
+        const int kmaxS = (kern == OC_KERNEL_MARCH) ? oc_host_pick_stages(n < kdef ? n : kdef) : (kern == OC_KERNEL_RESIDENT ? OC_RESIDENT_MAX_STEPS : 1);
         OcLaunch L;
         oc_host_next_launch(c->q, n, kmaxS, L);
         const int H = c->p.halo_rows;

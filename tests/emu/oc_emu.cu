@@ -15,6 +15,7 @@
 #include "../../opencloth_b200/csrc/oc_gather.cuh"
 #include "../../opencloth_b200/csrc/oc_march.cuh"
 #include "../../opencloth_b200/csrc/oc_march2.cuh"
+#include "../../opencloth_b200/csrc/oc_resident.cuh"
 
 #include <ucontext.h>
 #include <cstdlib>
@@ -28,10 +29,11 @@
 // ------------------------------------------------------------------------------------------------
 struct EmuCta;
 struct EmuCtx {
-    int tid_, bx_, by_, bz_;
+    int tid_, bx_, by_, bz_, nthreads_;
     unsigned char* smem_;
     EmuCta* cta;
     int tid() const { return tid_; }
+    int nthreads() const { return nthreads_; }
     int bx() const { return bx_; }
     int by() const { return by_; }
     int bz() const { return bz_; }
@@ -91,7 +93,7 @@ static int run_cta(int nthreads, int bx, int by, int bz, size_t smem_bytes, cons
     unsigned char* smem = (unsigned char*)aligned_alloc(128, (smem_bytes + 127) / 128 * 128 + 128);
     memset(smem, 0xCD, smem_bytes);            // garbage, like real shared memory
     for (int t = 0; t < nthreads; ++t) {
-        c->ctx[t].tid_ = t; c->ctx[t].bx_ = bx; c->ctx[t].by_ = by; c->ctx[t].bz_ = bz;
+        c->ctx[t].tid_ = t; c->ctx[t].bx_ = bx; c->ctx[t].by_ = by; c->ctx[t].bz_ = bz; c->ctx[t].nthreads_ = nthreads;
         c->ctx[t].smem_ = smem; c->ctx[t].cta = c;
         getcontext(&c->fib[t]);
         c->fib[t].uc_stack.ss_sp = c->stacks[t];
@@ -229,6 +231,26 @@ static int emu_march2_dispatch(EmuCloth* e, const OcLaunch& L, int WC, int RS)
     return -2;
 }
 
+// kernel 4: one CTA per cloth, all the substeps of the launch inside; TW = threads of the CTA (0: like the library)
+template <class M>
+static int emu_resident(EmuCloth* e, const OcLaunch& L, int threads)
+{
+    const OcConst& k = e->k;
+    const int N = k.U * k.V;
+    if (e->q.band || N > OC_RESIDENT_MAX_PARTICLES) return -2;
+    if (threads <= 0) { threads = (6 * N + 31) / 32 * 32; if (threads > OC_RESIDENT_THREADS) threads = OC_RESIDENT_THREADS; }
+    const float4* A = e->buf[L.src_a].data();
+    const float4* B = e->buf[L.src_b].data();
+    float4* D = e->buf[L.dst].data();
+    float4* Dp = e->buf[L.dst_prev].data();
+    int rc = 0, S = L.S;
+    for (int b = 0; b < k.batch; ++b)
+        rc |= run_cta(threads, b, 0, 0, OcResidentSmem::bytes(N), [&](EmuCtx& ctx) {
+            oc_resident_body<M, EmuCtx>(ctx, k, A, B, D, Dp, S);
+        });
+    return rc;
+}
+
 template <class M>
 static void emu_gather(EmuCloth* e, const OcLaunch& L)
 {
@@ -325,8 +347,13 @@ int emu_step(void* h, int n, int kernel, int exact, int k, int TW, int RS)
         // same stage-count choice as oc_step (TW = 16 exists only here and also has a 3-stage build)
         int kk = 1;
         if (kernel == 2) { int w = n < k ? n : k; kk = (TW == 16 && w <= 3) ? w : oc_host_pick_stages(w); }
+        if (kernel == 4) kk = OC_RESIDENT_MAX_STEPS;
         oc_host_next_launch(e->q, n, kk, L);
-        if (kernel == 3) {
+        if (kernel == 4) {
+            int r = exact ? emu_resident<MathExact>(e, L, TW) : emu_resident<MathFast>(e, L, TW);
+            if (r == -2) return -2;
+            rc |= r;
+        } else if (kernel == 3) {
             int r = exact ? emu_march2_dispatch<MathExact>(e, L, TW, RS) : emu_march2_dispatch<MathFast>(e, L, TW, RS);
             if (r == -2) return -2;
             rc |= r;

@@ -11,7 +11,7 @@ import pytest
 import helpers
 from helpers import Emu, Oracle, bitwise_equal
 
-GATHER, MARCH, MARCH2 = 1, 2, 3
+GATHER, MARCH, MARCH2, RESIDENT = 1, 2, 3, 4
 
 
 def run_pair(nx, ny, pre, steps, **kw):
@@ -33,6 +33,36 @@ def test_gather_kernel_body(nx, ny, pre, steps):
     hits = run_pair(nx, ny, pre, steps, kernel=GATHER)
     if pre >= 1800:
         assert hits > 2          # the collider is active in this window
+
+
+# resident small-cloth kernel: (nx, ny, pre, steps, threads of the CTA); every case also split into several calls
+@pytest.mark.parametrize("nx,ny,pre,steps,threads", [(21, 21, 0, 40, 0), (21, 21, 1800, 120, 0), (21, 21, 1800, 60, 96), (37, 23, 1900, 30, 0),
+                                                     (3, 3, 3, 60, 0), (5, 4, 3, 60, 32), (39, 39, 1200, 12, 256)])
+def test_resident_kernel_body(nx, ny, pre, steps, threads):
+    hits = run_pair(nx, ny, pre, steps, kernel=RESIDENT, TW=threads)
+    if pre >= 1800:
+        assert hits > 2
+    # the same in calls of 1, 2, 1, rest substeps (one substep per launch writes one buffer, more write two)
+    x0, xl0 = helpers.developed_state(nx, ny, pre) if pre else Oracle(nx, ny).state()
+    o = Oracle(nx, ny); o.set_state(x0, xl0); o.step(steps)
+    e = Emu(nx, ny)
+    if pre:
+        e.upload(x0, xl0)
+    for n in (1, 2, 1, steps - 4):
+        e.step(n, kernel=RESIDENT, TW=threads)
+    ex, exl = e.download(); ox, oxl = o.state()
+    assert bitwise_equal(ex, ox) and bitwise_equal(exl, oxl)
+
+
+@pytest.mark.parametrize("order", [1, 2])
+def test_resident_kernel_is_independent_of_thread_schedule(order):
+    L = helpers.emu_lib()
+    L.emu_set_order(order)
+    try:
+        run_pair(21, 21, 1800, 40, kernel=RESIDENT, TW=0)
+        run_pair(37, 23, 1900, 10, kernel=RESIDENT, TW=160)
+    finally:
+        L.emu_set_order(0)
 
 
 # (nx, ny, pre-steps, steps, k, TW, RS): single strip / multi strip, one / many segments, every k

@@ -31,7 +31,7 @@ def golden(name):
 
 
 def kid(m, kernel):
-    return {"march": m.OC_KERNEL_MARCH, "gather": m.OC_KERNEL_GATHER, "march2": m.OC_KERNEL_MARCH2}[kernel]
+    return {"march": m.OC_KERNEL_MARCH, "gather": m.OC_KERNEL_GATHER, "march2": m.OC_KERNEL_MARCH2, "resident": m.OC_KERNEL_RESIDENT}[kernel]
 
 
 def nbad(a, b):
@@ -42,7 +42,7 @@ def nbad(a, b):
 # golden vectors of the verbatim reference
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("name", ["grid_21x21.npz", "grid_37x23.npz", "grid_64x64.npz", "grid_256x256.npz"])
-@pytest.mark.parametrize("kernel,k", [("march", 1), ("march", 4), ("gather", 1), ("march2", 1)])
+@pytest.mark.parametrize("kernel,k", [("march", 1), ("march", 4), ("gather", 1), ("march2", 1), ("resident", 1)])
 def test_cuda_matches_reference_golden(name, kernel, k):
     g, meta = golden(name)
     nx, ny = meta["nx"], meta["ny"]
@@ -78,7 +78,7 @@ def test_energy_trajectory_matches_reference():
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("nx,ny,pre,steps", [(3, 3, 0, 300), (4, 7, 0, 300), (21, 21, 1650, 400), (37, 23, 1800, 300),
                                              (100, 61, 1500, 200), (129, 40, 800, 100), (300, 200, 600, 100), (1000, 37, 300, 50)])
-@pytest.mark.parametrize("kernel,k", [("march", 1), ("march", 2), ("march", 8), ("gather", 1), ("march2", 1)])
+@pytest.mark.parametrize("kernel,k", [("march", 1), ("march", 2), ("march", 8), ("gather", 1), ("march2", 1), ("resident", 1)])
 def test_cuda_matches_oracle_bitwise(nx, ny, pre, steps, kernel, k):
     m = oc()
     x0, xl0 = helpers.developed_state(nx, ny, pre)
@@ -91,6 +91,48 @@ def test_cuda_matches_oracle_bitwise(nx, ny, pre, steps, kernel, k):
     assert bitwise_equal(x, ox), f"{nbad(x, ox)} particles differ"
     assert bitwise_equal(xl, oxl)
     c.close()
+
+
+def test_resident_kernel_small_cloths():
+    """Kernel 4 (state resident in shared memory, all substeps of a call in one launch): what AUTO picks for the
+    reference's own 21 x 21 cloth.  One launch per oc_step call whatever n; odd call patterns (n = 1 writes one
+    buffer, n > 1 two), a particle edit in between, a batch of cloths, the largest size (39 x 39) and the
+    fall-back for cloths that do not fit."""
+    m = oc()
+    c = m.Cloth(21, 21)                                      # AUTO
+    l0 = c.launch_count
+    c.step(1000)
+    assert c.launch_count - l0 == 1
+    g, meta = golden("grid_21x21.npz")
+    x, xl = c.download()
+    assert sha(x) == meta["sha_x"]["1000"] and sha(xl) == meta["sha_xl"]["1000"]
+    c.close()
+    for nx, ny, batch in ((21, 21, 7), (39, 39, 2), (33, 40, 1), (5, 4, 3)):
+        x0, xl0 = helpers.developed_state(nx, ny, 900)
+        o = Oracle(nx, ny); o.set_state(x0, xl0)
+        c = m.Cloth(nx, ny, batch=batch, kernel=m.OC_KERNEL_RESIDENT)
+        c.upload(np.tile(x0, (batch, 1)), np.tile(xl0, (batch, 1)))
+        idx = (ny // 2) * nx + nx // 2
+        for n in (1, 1, 2, 7, 1, 300):
+            c.step(n); o.step(n)
+            if n == 7:
+                c.set_particle(idx, (0.1, 2.5, 0.2), cloth=batch - 1)
+                o2 = Oracle(nx, ny); ox, oxl = o.state(); ox = ox.copy(); oxl = oxl.copy()
+                ox[idx] = (0.1, 2.5, 0.2); oxl[idx] = (0.1, 2.5, 0.2)
+                o2.set_state(ox, oxl)
+        o2.step(1 + 300)
+        x, xl = c.download()
+        ox, oxl = o.state(); px, pxl = o2.state()
+        n1 = nx * ny
+        for b in range(batch):
+            ex, exl = (px, pxl) if b == batch - 1 else (ox, oxl)
+            assert bitwise_equal(x[b * n1:(b + 1) * n1], ex) and bitwise_equal(xl[b * n1:(b + 1) * n1], exl), f"{nx}x{ny} cloth {b}"
+        c.close()
+    big = m.Cloth(100, 61, kernel=m.OC_KERNEL_RESIDENT)      # 6100 particles do not fit: served by the gather kernel
+    big.step(3)
+    o = Oracle(100, 61); o.step(3)
+    assert bitwise_equal(big.download()[0], o.state()[0])
+    big.close()
 
 
 def test_temporal_blocking_equals_single_steps():
