@@ -360,6 +360,45 @@ def test_row_bands_single_process_equal_whole_cloth(nbands, halo, k, kern):
     whole.close()
 
 
+@pytest.mark.parametrize("nx,ny,nbands,halo", [(2304, 4096, 2, 16), (4100, 3000, 3, 24)])
+def test_row_bands_chained_full_size(nx, ny, nbands, halo):
+    """Row bands at a size where the launches of a band are chained tile by tile (OcDep2) although the row range,
+    and with it the tiling, shrinks with every substep of a group: bitwise equal to the undivided cloth stepped
+    by the gather kernel, through several exchanges, and no dependency wait times out."""
+    import ctypes
+    m = oc()
+    from opencloth_b200 import _abi
+    whole = m.Cloth(nx, ny, kernel=m.OC_KERNEL_GATHER)
+    whole.step(40)                                   # leave the flat start
+    wx, wxl = whole.download()
+    cuts = [round(ny * b / nbands) for b in range(nbands + 1)]
+    bands = []
+    for b in range(nbands):
+        c = m.Cloth(nx, ny, row_begin=cuts[b], row_end=cuts[b + 1], halo_rows=halo, kernel=m.OC_KERNEL_MARCH2)
+        sl = slice(cuts[b] * nx, cuts[b + 1] * nx)
+        c.upload(wx[sl], wxl[sl])
+        bands.append(c)
+    arr = (ctypes.c_void_p * nbands)(*[c._h for c in bands])
+    total = 0
+    for rnd in range(3):
+        _abi.check(_abi.load().oc_halo_exchange(arr, nbands))
+        n = halo // 2 if rnd != 1 else halo // 2 - 3
+        for c in bands:
+            c.step(n)
+        total += n
+    whole.step(total)
+    wx, wxl = whole.download()
+    out = (ctypes.c_ulonglong * 4)()
+    for b, c in enumerate(bands):
+        x, xl = c.download()
+        sl = slice(cuts[b] * nx, cuts[b + 1] * nx)
+        assert bitwise_equal(x, wx[sl]) and bitwise_equal(xl, wxl[sl]), f"band {b}: {nbad(x, wx[sl])} particles differ"
+        c._lib.oc_debug_counters(c._h, out)
+        assert (out[2] >> 40) == 0, "a tile-dependency wait timed out"
+        c.close()
+    whole.close()
+
+
 def test_branch_free_math_is_ieee():
     """The MUFU+FFMA sequences used instead of sqrt.rn / rcp.rn / div.rn (no slow-path branch) give
     the correctly rounded result on 2^30 random operands in their accepted exponent ranges."""
