@@ -445,7 +445,7 @@ static int launch_rows(oc_cloth* c, int kern, const OcLaunch& L, int ra, int rb)
         chain_break(c);
         const int N = c->p.nx * c->p.ny;
         const size_t smem = OcResidentSmem::bytes(N);
-        int threads = (6 * N + 31) / 32 * 32; if (threads > OC_RESIDENT_THREADS) threads = OC_RESIDENT_THREADS;
+        int threads = (3 * N + 31) / 32 * 32; if (threads > OC_RESIDENT_THREADS) threads = OC_RESIDENT_THREADS;
         static bool configured[2] = { false, false };
         const void* fn = c->p.exact ? (const void*)&oc_k_resident<MathExact> : (const void*)&oc_k_resident<MathFast>;
         if (!configured[c->p.exact ? 1 : 0]) {

@@ -4,9 +4,10 @@
 // launch per substep is pure launch latency, and one thread per particle is a serial chain of 12 springs.  Here one
 // CTA owns one cloth (blockIdx.x = cloth of a batch), loads X(t), X(t-1) once, takes ALL the substeps of the oc_step
 // call without touching HBM, and writes X(t+n), X(t+n-1) back.  A substep is two phases with a barrier each:
-//   S  every FORWARD spring of the cloth, (+1,0) (+2,0) (0,+1) (0,+2) (+1,+1) (-1,+1) of every particle, is one work
-//      item (6 N items over the CTA's threads): f = springForce(p, partner) into F[type][p].  Evaluated once, by its
-//      upper/left end, with the branch-free exact sequences (oc_spring_bf; IEEE intrinsics on the rare bad operand).
+//   S  the FORWARD springs of the cloth, (+1,0) (+2,0) (0,+1) (0,+2) (+1,+1) (-1,+1) of every particle, two per work
+//      item (3 N items over the CTA's threads, packed FP32x2 like oc_k_march): f = springForce(p, partner) into
+//      F[type][p].  Every spring is evaluated once, by its upper/left end, with the branch-free exact sequences
+//      (oc_spring2; IEEE intrinsics on the rare bad operand).
 //   P  every particle is one work item: base force, the <= 14 spring terms in the reference's order (own forces added,
 //      partners' forces subtracted: f(b,a) == -f(a,b) bitwise), IntegrateVerlet, EllipsoidCollision; then the new
 //      velocity and X - X_last once per particle.
@@ -61,31 +62,45 @@ OC_HD void oc_resident_body(Ctx& ctx, const OcConst& c, const float4* __restrict
     ctx.sync();
 
     for (int step = 0; step < n_steps; ++step) {
-        // ---- S: forward springs ------------------------------------------------------------------------
-        for (int w = tid; w < 6 * N; w += T) {
-            const int t = w / N, p = w - t * N;
+        // ---- S: forward springs, two per work item (packed FP32x2): (+1,0)&(+2,0), (0,+1)&(0,+2), (+1,+1)&(-1,+1) ---
+        for (int w = tid; w < 3 * N; w += T) {
+            const int pr = w / N, p = w - pr * N;
             const int j = p / U, i = p - j * U;
-            int qi = i, qj = j; float rest = 0.0f, nks = c.nks_struct, kd = c.kd_struct;
+            int qi0 = i, qj0 = j, qi1 = i, qj1 = j;
+            float2 rest, nks, kd;
             bool badr = false;
-            switch (t) {
-            case 0:  qi = i + 1;             rest = c.rh1[i];                       break;                                        // V:288-291
-            case 1:  qi = i + 2;             rest = c.rh2[i < U - 2 ? i : 0];        nks = c.nks_bend;  kd = c.kd_bend;  break;     // V:309-314
-            case 2:  qj = j + 1;             rest = c.rv1[j];                       break;                                        // V:294-297
-            case 3:  qj = j + 2;             rest = c.rv2[j < V - 2 ? j : 0];        nks = c.nks_bend;  kd = c.kd_bend;  break;     // V:315-320
-            case 4:  qi = i + 1; qj = j + 1; nks = c.nks_shear; kd = c.kd_shear;    break;                                        // V:301-305
-            default: qi = i - 1; qj = j + 1; nks = c.nks_shear; kd = c.kd_shear;    break;
+            if (pr == 0) {                                                       // V:288-291, V:309-314
+                qi0 = i + 1; qi1 = i + 2;
+                rest = make_float2(c.rh1[i], c.rh2[i]);
+                nks = make_float2(c.nks_struct, c.nks_bend); kd = make_float2(c.kd_struct, c.kd_bend);
+            } else if (pr == 1) {                                                // V:294-297, V:315-320
+                qj0 = j + 1; qj1 = j + 2;
+                rest = make_float2(c.rv1[j], c.rv2[j]);
+                nks = make_float2(c.nks_struct, c.nks_bend); kd = make_float2(c.kd_struct, c.kd_bend);
+            } else {                                                             // V:301-305
+                qi0 = i + 1; qj0 = j + 1; qi1 = i - 1; qj1 = j + 1;
+                rest = oc_sqrt2<M>(make_float2(M::add(c.dx2[i], c.dz2[j]), M::add(c.dx2[i > 0 ? i - 1 : 0], c.dz2[j])), badr);
+                nks = p_bc(c.nks_shear); kd = p_bc(c.kd_shear);
             }
-            if (qi < 0 || qi >= U || qj >= V) continue;                  // no such spring: its slot is never read
-            if (t == 4) rest = oc_len_bf<M>(M::add(c.dx2[i], c.dz2[j]), badr);
-            if (t == 5) rest = oc_len_bf<M>(M::add(c.dx2[i - 1], c.dz2[j]), badr);
-            if (M::kExact && badr) rest = M::sqrt(M::add(c.dx2[t == 4 ? i : i - 1], c.dz2[j]));
-            const int q = qj * U + qi;
+            const bool e0 = qi0 < U && qj0 < V, e1 = qi1 >= 0 && qi1 < U && qj1 < V;
+            if (!e0 && !e1) continue;                                            // no such springs: their slots are never read
             const f3 xp = make_f3(s.X(0)[p], s.X(1)[p], s.X(2)[p]), vp = make_f3(s.V(0)[p], s.V(1)[p], s.V(2)[p]);
-            const f3 xq = make_f3(s.X(0)[q], s.X(1)[q], s.X(2)[q]), vq = make_f3(s.V(0)[q], s.V(1)[q], s.V(2)[q]);
+            // a missing partner is replaced by a ghost at unit distance moving with the particle (result not stored)
+            const int q0 = e0 ? qj0 * U + qi0 : p, q1 = e1 ? qj1 * U + qi1 : p;
+            const float g0 = e0 ? 0.0f : 1.0f, g1 = e1 ? 0.0f : 1.0f;
+            OcPair3 qx, qv;
+            qx.x = make_float2(s.X(0)[q0] + g0, s.X(0)[q1] + g1); qx.y = make_float2(s.X(1)[q0], s.X(1)[q1]); qx.z = make_float2(s.X(2)[q0], s.X(2)[q1]);
+            qv.x = make_float2(s.V(0)[q0], s.V(0)[q1]); qv.y = make_float2(s.V(1)[q0], s.V(1)[q1]); qv.z = make_float2(s.V(2)[q0], s.V(2)[q1]);
             bool bad = false;
-            f3 f = oc_spring_bf<M>(xp, vp, xq, vq, rest, nks, kd, bad);
-            if (M::kExact && bad) f = oc_spring<M>(xp, vp, xq, vq, rest, nks, kd);
-            s.F(t, 0)[p] = f.x; s.F(t, 1)[p] = f.y; s.F(t, 2)[p] = f.z;
+            OcPair3 f = oc_spring2<M>(xp, vp, qx, qv, M::kExact ? rest : p_mul(rest, nks), nks, kd, c.one, bad);
+            if (M::kExact && (bad | badr)) {                                     // rare: IEEE intrinsics
+                if (pr == 2) rest = make_float2(M::sqrt(M::add(c.dx2[i], c.dz2[j])), M::sqrt(M::add(c.dx2[i > 0 ? i - 1 : 0], c.dz2[j])));
+                const f3 f0 = oc_spring<M>(xp, vp, make_f3(qx.x.x, qx.y.x, qx.z.x), make_f3(qv.x.x, qv.y.x, qv.z.x), rest.x, nks.x, kd.x);
+                const f3 f1 = oc_spring<M>(xp, vp, make_f3(qx.x.y, qx.y.y, qx.z.y), make_f3(qv.x.y, qv.y.y, qv.z.y), rest.y, nks.y, kd.y);
+                f.x = make_float2(f0.x, f1.x); f.y = make_float2(f0.y, f1.y); f.z = make_float2(f0.z, f1.z);
+            }
+            if (e0) { s.F(2 * pr, 0)[p] = f.x.x; s.F(2 * pr, 1)[p] = f.y.x; s.F(2 * pr, 2)[p] = f.z.x; }
+            if (e1) { s.F(2 * pr + 1, 0)[p] = f.x.y; s.F(2 * pr + 1, 1)[p] = f.y.y; s.F(2 * pr + 1, 2)[p] = f.z.y; }
         }
         ctx.sync();
         // ---- P: accumulate in the reference's order, integrate, collide -------------------------------------

@@ -238,7 +238,7 @@ static int emu_resident(EmuCloth* e, const OcLaunch& L, int threads)
     const OcConst& k = e->k;
     const int N = k.U * k.V;
     if (e->q.band || N > OC_RESIDENT_MAX_PARTICLES) return -2;
-    if (threads <= 0) { threads = (6 * N + 31) / 32 * 32; if (threads > OC_RESIDENT_THREADS) threads = OC_RESIDENT_THREADS; }
+    if (threads <= 0) { threads = (3 * N + 31) / 32 * 32; if (threads > OC_RESIDENT_THREADS) threads = OC_RESIDENT_THREADS; }
     const float4* A = e->buf[L.src_a].data();
     const float4* B = e->buf[L.src_b].data();
     float4* D = e->buf[L.dst].data();
