@@ -15,8 +15,10 @@
 // rounding: exact mode stays bit-identical.
 //
 // Kernel: S = 1 (no temporal blocking; k > 1 is served by oc_k_march).  WC window columns per CTA,
-// WC/2 threads.  "Interior" CTAs (every column of the window has all four horizontal neighbours) run a
-// steady loop without any predicate; edge CTAs and edge rows use a generic, per-half predicated path.
+// WC/2 threads.  The steady loop (interior rows) has no predicates: in CTAs at a cloth edge the springs of
+// columns that do not exist are multiplied by zero instead.  Edge ROWS (and the pipeline fill of a tile) use a
+// generic, per-half predicated path.  A launch is a 1-D grid of tiles (OcSeg2); consecutive launches are
+// chained tile by tile instead of by a grid-wide barrier (OcDep2).
 #pragma once
 #include "oc_core.cuh"
 #include "oc_march.cuh"
