@@ -71,6 +71,39 @@ static inline void oc_host_derive_scalars(const oc_params& p, OcConst& k)
         float d = tx * tx + ty * ty + tz * tz;
         k.tinv[a][0] = tx / d; k.tinv[a][1] = ty / d; k.tinv[a][2] = tz / d;
     }
+    // Bounding sphere of the collider, from the matrix the test really uses (V:511): delta0 = A X + t - c with A, t the
+    // linear part and translation of inverse_ellipsoid.  |delta0| >= sigma_min(A) |X - Xc|, Xc = A^-1 (c - t), and
+    // sigma_min(A) >= 1 / ||A^-1||_F: a particle with |X - Xc| > 1.05 ||A^-1||_F has |delta0| > 1.05 and is outside
+    // whatever the fp32 rounding of V:511-514 (its error is ~1e-6 of the squared magnitudes below, bounded by 1e-2).
+    // Anything unusual (singular A, large offsets, non-finite entries) switches the shortcut off.
+    {
+        double A[3][3], t[3];
+        for (int r = 0; r < 3; ++r) { for (int col = 0; col < 3; ++col) A[r][col] = p.inv_ellipsoid[col * 4 + r]; t[r] = p.inv_ellipsoid[12 + r]; }
+        const double det = A[0][0] * (A[1][1] * A[2][2] - A[1][2] * A[2][1]) - A[0][1] * (A[1][0] * A[2][2] - A[1][2] * A[2][0]) +
+                           A[0][2] * (A[1][0] * A[2][1] - A[1][1] * A[2][0]);
+        k.bs_c[0] = k.bs_c[1] = k.bs_c[2] = 0.0f; k.bs_r2 = INFINITY;
+        double na = 0.0; for (int r = 0; r < 3; ++r) for (int col = 0; col < 3; ++col) na += A[r][col] * A[r][col];
+        na = sqrt(na);
+        if (det == det && fabs(det) > 1e-9 * na * na * na && na > 0.0) {
+            double I[3][3];
+            I[0][0] =  (A[1][1] * A[2][2] - A[1][2] * A[2][1]) / det; I[0][1] = -(A[0][1] * A[2][2] - A[0][2] * A[2][1]) / det; I[0][2] =  (A[0][1] * A[1][2] - A[0][2] * A[1][1]) / det;
+            I[1][0] = -(A[1][0] * A[2][2] - A[1][2] * A[2][0]) / det; I[1][1] =  (A[0][0] * A[2][2] - A[0][2] * A[2][0]) / det; I[1][2] = -(A[0][0] * A[1][2] - A[0][2] * A[1][0]) / det;
+            I[2][0] =  (A[1][0] * A[2][1] - A[1][1] * A[2][0]) / det; I[2][1] = -(A[0][0] * A[2][1] - A[0][1] * A[2][0]) / det; I[2][2] =  (A[0][0] * A[1][1] - A[0][1] * A[1][0]) / det;
+            double ni = 0.0, xc[3], nt = 0.0, nc = 0.0, nx = 0.0;
+            for (int r = 0; r < 3; ++r) for (int col = 0; col < 3; ++col) ni += I[r][col] * I[r][col];
+            ni = sqrt(ni);
+            for (int r = 0; r < 3; ++r) {
+                xc[r] = I[r][0] * (p.center[0] - t[0]) + I[r][1] * (p.center[1] - t[1]) + I[r][2] * (p.center[2] - t[2]);
+                nt += t[r] * t[r]; nc += (double)p.center[r] * p.center[r]; nx += xc[r] * xc[r];
+            }
+            const double rb = 1.05 * ni;
+            const double mag = na * (sqrt(nx) + rb) + sqrt(nt) + sqrt(nc);       // magnitude of the terms of V:511-513 near the sphere
+            if (rb == rb && mag == mag && mag < 100.0 && rb < 1e6) {
+                for (int r = 0; r < 3; ++r) k.bs_c[r] = (float)xc[r];
+                k.bs_r2 = (float)(rb * rb * 1.001 + 1e-6 * (nx + rb * rb));          // rounding of the centre and of the distance test itself
+            }
+        }
+    }
 }
 
 static inline float oc_host_rest(float ax, float az, float bx, float bz)

@@ -415,59 +415,66 @@ struct OcMarch2 {
             n.z = p_sump<M>(p_mul(p_bc(c.dt2m), F.z), p_add(me.x.z, dme.z), c.one);
             if (n.y.x < 0.0f) n.y.x = 0.0f;
             if (n.y.y < 0.0f) n.y.y = 0.0f;
-            OcPair3 p0;         // X_0 = inverse_ellipsoid * vec4(X,1) - center, rows x, y, z for (a, b)
-            p0.x = p_sub(p_add(p_sump<M>(p_mul(p_bc(c.im[0][2]), n.z), p_sump<M>(p_mul(p_bc(c.im[0][1]), n.y), p_mul(p_bc(c.im[0][0]), n.x), c.one), c.one), p_bc(c.im[0][3])), p_bc(c.center[0]));
-            p0.y = p_sub(p_add(p_sump<M>(p_mul(p_bc(c.im[1][2]), n.z), p_sump<M>(p_mul(p_bc(c.im[1][1]), n.y), p_mul(p_bc(c.im[1][0]), n.x), c.one), c.one), p_bc(c.im[1][3])), p_bc(c.center[1]));
-            p0.z = p_sub(p_add(p_sump<M>(p_mul(p_bc(c.im[2][2]), n.z), p_sump<M>(p_mul(p_bc(c.im[2][1]), n.y), p_mul(p_bc(c.im[2][0]), n.x), c.one), c.one), p_bc(c.im[2][3])), p_bc(c.center[2]));
-            const float2 sq = p_sump<M>(p_mul(p0.z, p0.z), p_sump<M>(p_mul(p0.y, p0.y), p_mul(p0.x, p0.x), c.one), c.one);
-            bool hit_a = sq.x < 1.0f, hit_b = sq.y < 1.0f;                                           // V:513-514 (see oc_core.cuh)
+            // A particle outside the collider's bounding sphere (OcConst::bs_*, conservative) cannot be inside the
+            // ellipsoid: the transform of V:511-513 is skipped for it (most of the cloth, most of the time).
+            bool hit_a = false, hit_b = false;
+            const float2 ex = p_sub(n.x, p_bc(c.bs_c[0])), ey = p_sub(n.y, p_bc(c.bs_c[1])), ez = p_sub(n.z, p_bc(c.bs_c[2]));
+            const float2 e2 = p_fma(ez, ez, p_fma(ey, ey, p_mul(ex, ex)));
+            if ((e2.x <= c.bs_r2) | (e2.y <= c.bs_r2)) {
+                OcPair3 p0;         // X_0 = inverse_ellipsoid * vec4(X,1) - center, rows x, y, z for (a, b)
+                p0.x = p_sub(p_add(p_sump<M>(p_mul(p_bc(c.im[0][2]), n.z), p_sump<M>(p_mul(p_bc(c.im[0][1]), n.y), p_mul(p_bc(c.im[0][0]), n.x), c.one), c.one), p_bc(c.im[0][3])), p_bc(c.center[0]));
+                p0.y = p_sub(p_add(p_sump<M>(p_mul(p_bc(c.im[1][2]), n.z), p_sump<M>(p_mul(p_bc(c.im[1][1]), n.y), p_mul(p_bc(c.im[1][0]), n.x), c.one), c.one), p_bc(c.im[1][3])), p_bc(c.center[1]));
+                p0.z = p_sub(p_add(p_sump<M>(p_mul(p_bc(c.im[2][2]), n.z), p_sump<M>(p_mul(p_bc(c.im[2][1]), n.y), p_mul(p_bc(c.im[2][0]), n.x), c.one), c.one), p_bc(c.im[2][3])), p_bc(c.center[2]));
+                const float2 sq = p_sump<M>(p_mul(p0.z, p0.z), p_sump<M>(p_mul(p0.y, p0.y), p_mul(p0.x, p0.x), c.one), c.one);
+                hit_a = sq.x < 1.0f; hit_b = sq.y < 1.0f;                                           // V:513-514 (see oc_core.cuh)
 #ifdef __CUDA_ARCH__
-            if ((c.dbg & 4) && (hit_a | hit_b)) { atomicAdd(c.dbg_cnt + 3, 1ull); if ((threadIdx.x & 31) == __ffs(__activemask()) - 1) atomicAdd(c.dbg_cnt + 3, 1ull << 32); }
+                if ((c.dbg & 4) && (hit_a | hit_b)) { atomicAdd(c.dbg_cnt + 3, 1ull); if ((threadIdx.x & 31) == __ffs(__activemask()) - 1) atomicAdd(c.dbg_cnt + 3, 1ull << 32); }
 #endif
-            if (__builtin_expect(hit_a | hit_b, 0)) {
-                // EllipsoidCollision (V:514-530) of both particles at once, branch-free, with the same exact sqrt and
-                // division sequences as the springs; the result is taken per half where that particle is inside.
-                // (Contact zones are compact: whole CTAs spend every iteration here, so this path must be short.)
-                OcPair3 nn;
-                bool slow = false;
+                if (__builtin_expect(hit_a | hit_b, 0)) {
+                    // EllipsoidCollision (V:514-530) of both particles at once, branch-free, with the same exact sqrt and
+                    // division sequences as the springs; the result is taken per half where that particle is inside.
+                    // (Contact zones are compact: whole CTAs spend every iteration here, so this path must be short.)
+                    OcPair3 nn;
+                    bool slow = false;
 #ifdef __CUDA_ARCH__
-                if (M::kExact) {
-                    OcRange rc; rc.init();
-                    OcRangeStrict rn; rn.init();
-                    const float2 distance = oc_sqrt2<M>(sq, rc);
-                    const float2 sc = p_sub(p_bc(c.radius), distance);                                   // V:515
-                    const float2 y0 = p_rcp(distance);
-                    const float2 inv = p_fma(y0, p_fma(y0, p_neg(distance), p_bc(1.0f)), y0);            // 1/distance, correctly rounded
-                    const float2 ax = p_mul(sc, p0.x), ay = p_mul(sc, p0.y), az = p_mul(sc, p0.z);
-                    rn.add(ax.x); rn.add(ax.y); rn.add(ay.x); rn.add(ay.y); rn.add(az.x); rn.add(az.y);
-                    float2 q0 = p_mul(ax, inv); const float2 dx = p_fma(inv, p_fma(q0, p_neg(distance), ax), q0);   // (sc*x0)/distance
-                    q0 = p_mul(ay, inv);        const float2 dy = p_fma(inv, p_fma(q0, p_neg(distance), ay), q0);
-                    q0 = p_mul(az, inv);        const float2 dz = p_fma(inv, p_fma(q0, p_neg(distance), az), q0);
-                    // dot(d, transformInv row) = (dx*t0 + dy*t1) + dz*t2                                 V:520-528
-                    nn.x = p_add(n.x, p_sump<M>(p_mul(dz, p_bc(c.tinv[0][2])), p_sump<M>(p_mul(dy, p_bc(c.tinv[0][1])), p_mul(dx, p_bc(c.tinv[0][0])), c.one), c.one));
-                    nn.y = p_add(n.y, p_sump<M>(p_mul(dz, p_bc(c.tinv[1][2])), p_sump<M>(p_mul(dy, p_bc(c.tinv[1][1])), p_mul(dx, p_bc(c.tinv[1][0])), c.one), c.one));
-                    nn.z = p_add(n.z, p_sump<M>(p_mul(dz, p_bc(c.tinv[2][2])), p_sump<M>(p_mul(dy, p_bc(c.tinv[2][1])), p_mul(dx, p_bc(c.tinv[2][0])), c.one), c.one));
-                    // (a half that is not inside is tested too: if it trips the test the scalar path below still only
-                    // touches the halves that are inside)
-                    slow = rc.bad() | rn.bad(OC_NUM_LO_BITS, OC_NUM_HI_BITS);
-                } else
+                    if (M::kExact) {
+                        OcRange rc; rc.init();
+                        OcRangeStrict rn; rn.init();
+                        const float2 distance = oc_sqrt2<M>(sq, rc);
+                        const float2 sc = p_sub(p_bc(c.radius), distance);                                   // V:515
+                        const float2 y0 = p_rcp(distance);
+                        const float2 inv = p_fma(y0, p_fma(y0, p_neg(distance), p_bc(1.0f)), y0);            // 1/distance, correctly rounded
+                        const float2 ax = p_mul(sc, p0.x), ay = p_mul(sc, p0.y), az = p_mul(sc, p0.z);
+                        rn.add(ax.x); rn.add(ax.y); rn.add(ay.x); rn.add(ay.y); rn.add(az.x); rn.add(az.y);
+                        float2 q0 = p_mul(ax, inv); const float2 dx = p_fma(inv, p_fma(q0, p_neg(distance), ax), q0);   // (sc*x0)/distance
+                        q0 = p_mul(ay, inv);        const float2 dy = p_fma(inv, p_fma(q0, p_neg(distance), ay), q0);
+                        q0 = p_mul(az, inv);        const float2 dz = p_fma(inv, p_fma(q0, p_neg(distance), az), q0);
+                        // dot(d, transformInv row) = (dx*t0 + dy*t1) + dz*t2                                 V:520-528
+                        nn.x = p_add(n.x, p_sump<M>(p_mul(dz, p_bc(c.tinv[0][2])), p_sump<M>(p_mul(dy, p_bc(c.tinv[0][1])), p_mul(dx, p_bc(c.tinv[0][0])), c.one), c.one));
+                        nn.y = p_add(n.y, p_sump<M>(p_mul(dz, p_bc(c.tinv[1][2])), p_sump<M>(p_mul(dy, p_bc(c.tinv[1][1])), p_mul(dx, p_bc(c.tinv[1][0])), c.one), c.one));
+                        nn.z = p_add(n.z, p_sump<M>(p_mul(dz, p_bc(c.tinv[2][2])), p_sump<M>(p_mul(dy, p_bc(c.tinv[2][1])), p_mul(dx, p_bc(c.tinv[2][0])), c.one), c.one));
+                        // (a half that is not inside is tested too: if it trips the test the scalar path below still only
+                        // touches the halves that are inside)
+                        slow = rc.bad() | rn.bad(OC_NUM_LO_BITS, OC_NUM_HI_BITS);
+                    } else
 #endif
-                if (!M::kExact) {
-                    const float2 rinv = p_rsq(sq);
-                    const float2 q = p_mul(p_sub(p_bc(c.radius), p_mul(sq, rinv)), rinv);                // (radius - distance) / distance
-                    const float2 dx = p_mul(q, p0.x), dy = p_mul(q, p0.y), dz = p_mul(q, p0.z);
-                    nn.x = p_add(n.x, p_fma(dz, p_bc(c.tinv[0][2]), p_fma(dy, p_bc(c.tinv[0][1]), p_mul(dx, p_bc(c.tinv[0][0])))));
-                    nn.y = p_add(n.y, p_fma(dz, p_bc(c.tinv[1][2]), p_fma(dy, p_bc(c.tinv[1][1]), p_mul(dx, p_bc(c.tinv[1][0])))));
-                    nn.z = p_add(n.z, p_fma(dz, p_bc(c.tinv[2][2]), p_fma(dy, p_bc(c.tinv[2][1]), p_mul(dx, p_bc(c.tinv[2][0])))));
-                } else {
-                    slow = true;                                      // host (emulator), exact mode: the scalar reference form
+                    if (!M::kExact) {
+                        const float2 rinv = p_rsq(sq);
+                        const float2 q = p_mul(p_sub(p_bc(c.radius), p_mul(sq, rinv)), rinv);                // (radius - distance) / distance
+                        const float2 dx = p_mul(q, p0.x), dy = p_mul(q, p0.y), dz = p_mul(q, p0.z);
+                        nn.x = p_add(n.x, p_fma(dz, p_bc(c.tinv[0][2]), p_fma(dy, p_bc(c.tinv[0][1]), p_mul(dx, p_bc(c.tinv[0][0])))));
+                        nn.y = p_add(n.y, p_fma(dz, p_bc(c.tinv[1][2]), p_fma(dy, p_bc(c.tinv[1][1]), p_mul(dx, p_bc(c.tinv[1][0])))));
+                        nn.z = p_add(n.z, p_fma(dz, p_bc(c.tinv[2][2]), p_fma(dy, p_bc(c.tinv[2][1]), p_mul(dx, p_bc(c.tinv[2][0])))));
+                    } else {
+                        slow = true;                                      // host (emulator), exact mode: the scalar reference form
+                    }
+                    if (__builtin_expect(slow, 0)) {
+                        if (hit_a) { const f3 r = oc_march2_collide<M>(&c, make_f3(p0.x.x, p0.y.x, p0.z.x), sq.x, make_f3(n.x.x, n.y.x, n.z.x)); nn.x.x = r.x; nn.y.x = r.y; nn.z.x = r.z; }
+                        if (hit_b) { const f3 r = oc_march2_collide<M>(&c, make_f3(p0.x.y, p0.y.y, p0.z.y), sq.y, make_f3(n.x.y, n.y.y, n.z.y)); nn.x.y = r.x; nn.y.y = r.y; nn.z.y = r.z; }
+                    }
+                    if (hit_a) { n.x.x = nn.x.x; n.y.x = nn.y.x; n.z.x = nn.z.x; }
+                    if (hit_b) { n.x.y = nn.x.y; n.y.y = nn.y.y; n.z.y = nn.z.y; }
                 }
-                if (__builtin_expect(slow, 0)) {
-                    if (hit_a) { const f3 r = oc_march2_collide<M>(&c, make_f3(p0.x.x, p0.y.x, p0.z.x), sq.x, make_f3(n.x.x, n.y.x, n.z.x)); nn.x.x = r.x; nn.y.x = r.y; nn.z.x = r.z; }
-                    if (hit_b) { const f3 r = oc_march2_collide<M>(&c, make_f3(p0.x.y, p0.y.y, p0.z.y), sq.y, make_f3(n.x.y, n.y.y, n.z.y)); nn.x.y = r.x; nn.y.y = r.y; nn.z.y = r.z; }
-                }
-                if (hit_a) { n.x.x = nn.x.x; n.y.x = nn.y.x; n.z.x = nn.z.x; }
-                if (hit_b) { n.x.y = nn.x.y; n.y.y = nn.y.y; n.z.y = nn.z.y; }
             }
             const long long o = goff + (long long)row * U;
             if (sta) C[o]     = make_float4(n.x.x, n.y.x, n.z.x, oc_u2f(hit_a ? OC_W_HIT : OC_W_PLAIN));

@@ -396,6 +396,13 @@ int emu_halo_region(void* h, int side, int which, int send, void** ptr, size_t* 
     *count = (size_t)rows * e->k.U;
     return 0;
 }
+// the collider's bounding sphere as the kernels use it (centre xyz, squared radius; +inf = shortcut off)
+int emu_bounding_sphere(void* h, float out[4])
+{
+    const OcConst& k = ((EmuCloth*)h)->k;
+    out[0] = k.bs_c[0]; out[1] = k.bs_c[1]; out[2] = k.bs_c[2]; out[3] = k.bs_r2;
+    return 0;
+}
 int emu_halo_refreshed(void* h) { ((EmuCloth*)h)->q.fresh = 0; return 0; }
 int emu_halo_budget(void* h) { EmuCloth* e = (EmuCloth*)h; return e->q.band ? e->q.kmax - e->q.fresh : 0x7fffffff; }
 

@@ -258,6 +258,7 @@ def emu_lib():
         L.emu_halo_region.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                       ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_size_t)]
         L.emu_set_order.argtypes = [ctypes.c_int]
+        L.emu_bounding_sphere.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         _emu = L
     return _emu
 
@@ -298,6 +299,11 @@ class Emu:
         xl = np.empty((self.n_local, 3), np.float32)
         self.L.emu_download(self.h, vp(x), vp(xl))
         return x, xl
+
+    def bounding_sphere(self):
+        out = np.zeros(4, np.float32)
+        self.L.emu_bounding_sphere(self.h, vp(out))
+        return out
 
     def halo_region(self, side, which, send):
         ptr = ctypes.c_void_p(); cnt = ctypes.c_size_t()

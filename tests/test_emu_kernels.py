@@ -213,3 +213,64 @@ def test_band_refuses_to_step_past_its_halo():
     assert e.halo_budget == 0
     rc = helpers.emu_lib().emu_step(e.h, 1, MARCH, 1, 1, 32, 0)
     assert rc == -3
+
+
+def _mat4(rot_axis_angle, scale, translate):
+    """column-major 4x4 of translate * rotate * scale and its inverse, float32 like the reference's GLM matrices"""
+    ax, ang = rot_axis_angle
+    ax = np.asarray(ax, np.float64); ax /= np.linalg.norm(ax)
+    K = np.array([[0, -ax[2], ax[1]], [ax[2], 0, -ax[0]], [-ax[1], ax[0], 0]])
+    R = np.eye(3) + np.sin(ang) * K + (1 - np.cos(ang)) * K @ K
+    E = np.eye(4); E[:3, :3] = R @ np.diag(scale); E[:3, 3] = translate
+    return E.T.astype(np.float32).ravel(), np.linalg.inv(E).T.astype(np.float32).ravel()
+
+
+@pytest.mark.parametrize("case", range(6))
+def test_collider_bounding_sphere_is_conservative(case):
+    """oc_k_march2 skips the collider transform (V:511-513) for particles outside a bounding sphere derived on the
+    host from inverse_ellipsoid: no point that the reference's own fp32 test puts inside (or within 2 % of the
+    surface) may lie outside that sphere; degenerate colliders switch the shortcut off."""
+    rng = np.random.RandomState(100 + case)
+    if case == 0:
+        kw = {}                                                     # the reference's collider (V:324-327)
+    elif case < 4:
+        e, ie = _mat4((rng.normal(size=3), rng.uniform(0, 3)), rng.uniform(0.3, 2.5, 3), rng.uniform(-3, 3, 3))
+        kw = dict(ellipsoid=e, inv_ellipsoid=ie, center=tuple(rng.uniform(-0.5, 0.5, 3)))
+    elif case == 4:
+        e, ie = _mat4(((1, 0, 0), 0.3), (1, 1, 1), (500.0, 0, 0))   # large offsets: rounding of V:511 is no longer negligible
+        kw = dict(ellipsoid=e, inv_ellipsoid=ie)
+    else:
+        e, ie = _mat4(((0, 1, 0), 0.0), (1, 1, 1), (0, 0, 0))
+        ie = ie.copy(); ie[0:3] = 0.0                               # singular linear part
+        kw = dict(ellipsoid=e, inv_ellipsoid=ie)
+    emu = Emu(5, 5, **kw)
+    bs = emu.bounding_sphere()
+    if case >= 4:
+        assert np.isinf(bs[3])
+        return
+    assert np.isfinite(bs).all()
+    o = Oracle(5, 5, **kw)
+    p = o.params if hasattr(o, "params") else None
+    ie = np.asarray(kw.get("inv_ellipsoid", emu_default_inv()), np.float32).reshape(4, 4).T       # row-major A | t
+    c = np.asarray(kw.get("center", (0, 0, 0)), np.float32)
+    X = (bs[:3] + rng.uniform(-1, 1, (400000, 3)) * np.sqrt(bs[3]) * 1.6).astype(np.float32)
+    f = np.float32
+    rows = []
+    for r in range(3):                                              # products, then left-to-right sums (type_mat4x4.inl:567-571)
+        acc = f(ie[r, 0]) * X[:, 0] + f(ie[r, 1]) * X[:, 1]
+        acc = acc + f(ie[r, 2]) * X[:, 2]
+        acc = acc + f(ie[r, 3])
+        rows.append(acc - c[r])
+    sq = rows[0] * rows[0] + rows[1] * rows[1] + rows[2] * rows[2]
+    d2 = ((X - bs[:3]) ** 2).sum(1)
+    inside = sq < f(1.04)
+    assert inside.sum() > 1000, "the sample does not reach the collider"
+    assert (d2[inside] <= bs[3]).all(), "a point inside the collider lies outside its bounding sphere"
+
+
+def emu_default_inv():
+    from opencloth_b200._abi import OcParams, load
+    import ctypes
+    p = OcParams()
+    load().oc_default_params(ctypes.byref(p), 5, 5)
+    return np.array(list(p.inv_ellipsoid), np.float32)
