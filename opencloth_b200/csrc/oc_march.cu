@@ -249,11 +249,8 @@ cudaError_t oc_march2_launch(const OcConst& c, bool exact, int ra, int rb, int s
     const bool can_flag = chain && chain->flags && (long long)oc_seg2_tiles(seg) * c.batch <= chain->cap;      // one flag per tile and cloth
     if (can_flag) {
         dep.flags = chain->flags; dep.epoch = ++chain->epoch;
-        const int h_max = seg.rs > seg.rs_e ? seg.rs : seg.rs_e;
-        const int p_min = chain->pseg.rs < chain->pseg.rs_e ? chain->pseg.rs : chain->pseg.rs_e;
-        const int h_min = seg.rs < seg.rs_e ? seg.rs : seg.rs_e;
         // <= 4 segments per strip to poll; short tiles gain nothing (measured: 16-row tiles of a 1024^2 cloth lose 15 %)
-        if (chain->valid && pdl && tile_deps && chain->pseg.nstrips == seg.nstrips && h_max + 4 <= 2 * p_min && h_min >= 32) {
+        if (chain->valid && pdl && tile_deps && oc_dep2_chainable(seg, chain->pseg)) {
             dep.mode = 1; dep.pra = chain->pra; dep.prb = chain->prb; dep.pseg = chain->pseg;
         }
     }

@@ -568,6 +568,24 @@ struct OcDep2 {
     OcSeg2    pseg;
 };
 
+// Flag word of the k-th (k = 0..3) segment of strip xs of the PREVIOUS launch that overlaps the rows [r0-2, r1+2) a
+// tile reads; -1 if there is none.  (The host only uses mode 1 when at most four segments can overlap.)
+OC_HD int oc_dep2_index(const OcDep2& d, int xs, int k, int r0, int r1)
+{
+    const int lo = r0 - 2 < d.pra ? d.pra : r0 - 2, hi = r1 + 2 > d.prb ? d.prb : r1 + 2;
+    if (xs < 0 || xs >= d.pseg.nstrips || lo >= hi) return -1;
+    const int h = (xs == 0 || xs == d.pseg.nstrips - 1) ? d.pseg.rs_e : d.pseg.rs;
+    const int y = (lo - d.pra) / h + k, y_hi = (hi - 1 - d.pra) / h;
+    return y <= y_hi ? oc_seg2_index(d.pseg, xs, y) : -1;
+}
+// the host's condition for mode 1: the tallest tile of this launch overlaps at most four segments of the previous one
+OC_HD bool oc_dep2_chainable(const OcSeg2& seg, const OcSeg2& pseg)
+{
+    const int h_max = seg.rs > seg.rs_e ? seg.rs : seg.rs_e, h_min = seg.rs < seg.rs_e ? seg.rs : seg.rs_e;
+    const int p_min = pseg.rs < pseg.rs_e ? pseg.rs : pseg.rs_e;
+    return pseg.nstrips == seg.nstrips && h_max + 4 <= 2 * p_min && h_min >= 32;
+}
+
 template <class M, int WC, class Ctx>
 OC_HD void oc_march2_body(Ctx& ctx, const OcConst& c, const float4* __restrict__ A, const float4* __restrict__ B,
                           float4* __restrict__ C, int ra, int rb, OcSeg2 seg, int x_halo, const OcDep2& dep)
@@ -700,22 +718,17 @@ struct OcDevCtx2 {          // grid = (tiles, 1, batch): the tile -> (strip, seg
         if (d.mode == 0) { asm volatile("griddepcontrol.wait;" ::: "memory"); return; }
         const int t = threadIdx.x;
         if (t < 12) {
-            const int xs = x - 1 + t / 4, k = t % 4;
-            const int lo = r0 - 2 < d.pra ? d.pra : r0 - 2, hi = r1 + 2 > d.prb ? d.prb : r1 + 2;      // rows this tile reads
-            if (xs >= 0 && xs < d.pseg.nstrips && lo < hi) {
-                const int h = (xs == 0 || xs == d.pseg.nstrips - 1) ? d.pseg.rs_e : d.pseg.rs;
-                const int y = (lo - d.pra) / h + k, y_hi = (hi - 1 - d.pra) / h;
-                if (y <= y_hi) {
-                    const unsigned* p = d.flags + (size_t)blockIdx.z * oc_seg2_tiles(d.pseg) + oc_seg2_index(d.pseg, xs, y);   // same cloth
-                    const unsigned want = d.epoch - 1u;
-                    unsigned v, spins = 0, ns = 200;
-                    for (;;) {
-                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-                        if ((int)(v - want) >= 0) break;
-                        __nanosleep(ns);                                   // back off: the polls go to L2
-                        if (ns < 1600) ns += ns;
-                        if (++spins > (1u << 21)) { atomicAdd(c.dbg_cnt + 2, 1ull << 40); break; }      // > 1 s: never in a correct chain
-                    }
+            const int idx = oc_dep2_index(d, x - 1 + t / 4, t % 4, r0, r1);
+            if (idx >= 0) {
+                const unsigned* p = d.flags + (size_t)blockIdx.z * oc_seg2_tiles(d.pseg) + idx;   // same cloth
+                const unsigned want = d.epoch - 1u;
+                unsigned v, spins = 0, ns = 200;
+                for (;;) {
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+                    if ((int)(v - want) >= 0) break;
+                    __nanosleep(ns);                                   // back off: the polls go to L2
+                    if (ns < 1600) ns += ns;
+                    if (++spins > (1u << 21)) { atomicAdd(c.dbg_cnt + 2, 1ull << 40); break; }      // > 1 s: never in a correct chain
                 }
             }
         }

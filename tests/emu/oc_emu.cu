@@ -396,6 +396,51 @@ int emu_halo_region(void* h, int side, int which, int send, void** ptr, size_t* 
     *count = (size_t)rows * e->k.U;
     return 0;
 }
+// Brute-force check of the tile arithmetic of OcSeg2 / OcDep2 (host only).  Previous launch: rows [pra, prb) cut into
+// segments of prs (edge strips prs_e) rows; this launch likewise.  0: every row of every strip is covered exactly once and
+// every previous tile that wrote rows [r0-2, r1+2) of a tile's own or neighbouring strips is among the <= 12 flags that
+// tile waits for; 1: the host would not chain these two launches; negative: a violation.
+int emu_check_tiling(int nstrips, int pra, int prb, int prs, int prs_e, int ra, int rb, int rs, int rs_e, int ignore_height)
+{
+    OcSeg2 pseg, seg;
+    pseg.rs = prs; pseg.rs_e = prs_e; pseg.nstrips = nstrips; oc_seg2_finish(pseg, prb - pra);
+    seg.rs = rs; seg.rs_e = rs_e; seg.nstrips = nstrips; oc_seg2_finish(seg, rb - ra);
+    // coverage of this launch
+    std::vector<int> cover((size_t)nstrips * (rb - ra), 0);
+    for (int t = 0; t < oc_seg2_tiles(seg); ++t) {
+        int bx, by, r0, r1;
+        oc_seg2_tile(seg, t, bx, by);
+        if (bx < 0 || bx >= nstrips || oc_seg2_index(seg, bx, by) != t) return -3;
+        oc_seg2_rows(seg, bx, by, ra, rb, r0, r1);
+        for (int r = r0; r < r1; ++r) cover[(size_t)bx * (rb - ra) + (r - ra)]++;
+    }
+    for (size_t i = 0; i < cover.size(); ++i) if (cover[i] != 1) return -1;
+    // the host's chaining condition; ignore_height drops its "tiles of at least 32 rows" part (a performance rule)
+    const int h_max = seg.rs > seg.rs_e ? seg.rs : seg.rs_e, p_min = pseg.rs < pseg.rs_e ? pseg.rs : pseg.rs_e;
+    if (ignore_height ? !(h_max + 4 <= 2 * p_min) : !oc_dep2_chainable(seg, pseg)) return 1;
+    OcDep2 d = {};
+    d.mode = 1; d.pra = pra; d.prb = prb; d.pseg = pseg;
+    for (int t = 0; t < oc_seg2_tiles(seg); ++t) {
+        int bx, by, r0, r1;
+        oc_seg2_tile(seg, t, bx, by);
+        oc_seg2_rows(seg, bx, by, ra, rb, r0, r1);
+        if (r0 >= r1) continue;
+        int deps[12];
+        for (int k = 0; k < 12; ++k) deps[k] = oc_dep2_index(d, bx - 1 + k / 4, k % 4, r0, r1);
+        for (int u = 0; u < oc_seg2_tiles(pseg); ++u) {
+            int px, py, p0, p1;
+            oc_seg2_tile(pseg, u, px, py);
+            oc_seg2_rows(pseg, px, py, pra, prb, p0, p1);
+            if (p0 >= p1 || px < bx - 1 || px > bx + 1) continue;
+            if (p1 <= r0 - 2 || p0 >= r1 + 2) continue;                 // wrote nothing this tile reads
+            bool found = false;
+            for (int k = 0; k < 12; ++k) found |= deps[k] == u;
+            if (!found) return -2;
+        }
+    }
+    return 0;
+}
+
 // the collider's bounding sphere as the kernels use it (centre xyz, squared radius; +inf = shortcut off)
 int emu_bounding_sphere(void* h, float out[4])
 {

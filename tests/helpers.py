@@ -259,6 +259,7 @@ def emu_lib():
                                       ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_size_t)]
         L.emu_set_order.argtypes = [ctypes.c_int]
         L.emu_bounding_sphere.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        L.emu_check_tiling.argtypes = [ctypes.c_int] * 10
         _emu = L
     return _emu
 

@@ -274,3 +274,29 @@ def emu_default_inv():
     p = OcParams()
     load().oc_default_params(ctypes.byref(p), 5, 5)
     return np.array(list(p.inv_ellipsoid), np.float32)
+
+
+def test_tile_dependencies_cover_every_producer():
+    """OcSeg2 / OcDep2 host arithmetic, brute force over random launch pairs: whole cloths (same rows), row bands whose
+    range shrinks by two rows either side per substep, different segment heights in the two launches, shorter
+    segments in the edge strips, one / two / many strips.  Every row is computed exactly once, and a tile waits for
+    every tile of the previous launch that wrote what it reads."""
+    L = helpers.emu_lib()
+    rng = np.random.RandomState(7)
+    chained = 0
+    for trial in range(3000):
+        nstrips = int(rng.choice([1, 2, 3, 4, 17, 34, 67]))
+        prows = int(rng.randint(40, 1400))
+        pra = int(rng.randint(0, 50))
+        prb = pra + prows
+        shrink = int(rng.choice([0, 2]))
+        ra, rb = pra + shrink, prb - shrink
+        prs = int(rng.randint(8, 300)); prs_e = max(8, int(prs / rng.uniform(1.0, 1.4)))
+        if rng.rand() < 0.5:
+            rs, rs_e = prs, prs_e
+        else:
+            rs = int(rng.randint(8, 300)); rs_e = max(8, int(rs / rng.uniform(1.0, 1.4)))
+        rc = L.emu_check_tiling(nstrips, pra, prb, prs, prs_e, ra, rb, rs, rs_e, 1)
+        assert rc >= 0, f"violation {rc}: strips {nstrips}, prev [{pra},{prb}) {prs}|{prs_e}, now [{ra},{rb}) {rs}|{rs_e}"
+        chained += rc == 0
+    assert chained > 500
