@@ -123,11 +123,28 @@ def run_reference(args):
     n_side = 2048 if args.gpus == 1 else 8192
     steps = max(1, args.steps)
     base, ms = cpu_reference(n_side, steps, max(0, args.warmup), budget_s=90.0)
+    # for context only: the C restatement of the same algorithm (oracle/oc_oracle.c, OpenMP over particles) on every
+    # host thread, same sample size — what a multi-threaded CPU port of the reference would reach on this host
+    port = None
+    try:
+        import re
+        import helpers
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
+        side = int(re.search(r"of a (\d+)x", base["sample"]).group(1))
+        sim = helpers.Oracle(side, side)
+        sim.step(1)
+        t0 = time.perf_counter()
+        sim.step(steps)
+        dt = time.perf_counter() - t0
+        port = {"value": side * side * steps / dt, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                "sample": f"{steps} steps of a {side}x{side} cloth, OpenMP restatement on all host threads"}
+    except Exception as e:                                   # never let the extra figure break the arm
+        port = {"error": str(e)[:200]}
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic (closed-form flat sheet of InitGL, reference parameters)",
             "config": {"workload": workload_name(args), "note": "bounded sample of the workload on the host CPU, see cpu_baseline.sample"},
-            "cpu_baseline": base,
+            "cpu_baseline": base, "cpu_port_all_threads": port,
             "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
