@@ -23,12 +23,6 @@
 #include "oc_core.cuh"
 #include "oc_march.cuh"
 
-#ifndef OC_M2_UNROLL_EXACT
-#define OC_M2_UNROLL_EXACT 0
-#endif
-#ifndef OC_M2_UNROLL
-#define OC_M2_UNROLL 2      // copies of the fast-mode steady loop body (see oc_march2_body)
-#endif
 
 template <int WC>
 struct OcSmem2 {
@@ -237,7 +231,7 @@ struct OcMarch2 {
         *reinterpret_cast<float2*>(&s.Dd[2][sl][pa]) = d.z;
     }
 
-    template <bool kSteady, bool kInterior, int kSlot>
+    template <bool kSteady, bool kInterior>
     OC_HD void iter(int it)
     {
         Smem& s = *sm;
@@ -263,7 +257,7 @@ struct OcMarch2 {
             if (!kSteady) r = r < 0 ? 0 : (r >= V ? V - 1 : r);
             rv1_n = OC_LDG(c.rv1 + r); rv2_n = OC_LDG(c.rv2 + r); dz2_n = OC_LDG(c.dz2 + r);
         }
-        const int sl = kSlot >= 0 ? kSlot : (row & (OC_RING - 1));
+        const int sl = row & (OC_RING - 1);
         const int s1 = (sl + 1) & (OC_RING - 1), s2 = (sl + 2) & (OC_RING - 1), s3 = (sl + 3) & (OC_RING - 1);
         const int h = sl & 1;
 
@@ -665,7 +659,7 @@ OC_HD void oc_march2_body(Ctx& ctx, const OcConst& c, const float4* __restrict__
     int it = 0;
     for (int phase = 0; phase < 2; ++phase) {
         const int end = phase == 0 ? it_lo : n_it;
-        for (; it < end; ++it) m.template iter<false, false, -1>(it);
+        for (; it < end; ++it) m.template iter<false, false>(it);
 #ifdef __CUDA_ARCH__
         if ((c.dbg & 8) && i == 0) oc_timeline_mark(c, phase == 0 ? 2 : 4);
 #endif
@@ -675,16 +669,11 @@ OC_HD void oc_march2_body(Ctx& ctx, const OcConst& c, const float4* __restrict__
                 // loop-carried rows (measured +2.6 %; three copies are slower again).  Exact mode is not unrolled: its
                 // 2 x 11 KB of hot code, with the cold fallback blocks interleaved, misses in the instruction cache
                 // and loses 10 %.
-                if (!M::kExact || OC_M2_UNROLL_EXACT) {
-#if OC_M2_UNROLL == 3
-                    for (; it + 2 < it_hi; it += 3) { m.template iter<true, true, -1>(it); m.template iter<true, true, -1>(it + 1); m.template iter<true, true, -1>(it + 2); }
-#elif OC_M2_UNROLL == 2
-                    for (; it + 1 < it_hi; it += 2) { m.template iter<true, true, -1>(it); m.template iter<true, true, -1>(it + 1); }
-#endif
-                }
-                for (; it < it_hi; ++it) m.template iter<true, true, -1>(it);
+                if (!M::kExact)
+                    for (; it + 1 < it_hi; it += 2) { m.template iter<true, true>(it); m.template iter<true, true>(it + 1); }
+                for (; it < it_hi; ++it) m.template iter<true, true>(it);
             } else {
-                for (; it < it_hi; ++it) m.template iter<true, false, -1>(it);
+                for (; it < it_hi; ++it) m.template iter<true, false>(it);
             }
 #ifdef __CUDA_ARCH__
             if ((c.dbg & 8) && i == 0) oc_timeline_mark(c, 3);
@@ -694,15 +683,8 @@ OC_HD void oc_march2_body(Ctx& ctx, const OcConst& c, const float4* __restrict__
 }
 
 #ifdef __CUDACC__
-#ifndef OC_CTAS_M2
-#define OC_CTAS_M2 4
-#endif
-
-#ifdef OC_M2_MAXNREG
-#define OC_M2_BOUNDS __maxnreg__(OC_M2_MAXNREG)
-#else
-#define OC_M2_BOUNDS __launch_bounds__(WC / 2, OC_CTAS_M2)
-#endif
+// four CTAs of WC/2 threads per SM: 230-250 registers per thread (every trade of registers for a fifth CTA lost)
+#define OC_M2_BOUNDS __launch_bounds__(WC / 2, 4)
 struct OcDevCtx2 {          // grid = (tiles, 1, batch): the tile -> (strip, segment) map is OcSeg2's
     int x, y;
     __device__ __forceinline__ int tid() const { return threadIdx.x; }

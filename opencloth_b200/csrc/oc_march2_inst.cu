@@ -1,9 +1,4 @@
 // oc_march2_inst.cu — instantiations of the two-columns-per-thread marching kernel, one object per mode.
-#if OC_INST_EXACT
-#define OC_CTAS_M2 4
-#else
-#define OC_CTAS_M2 4
-#endif
 #include "oc_march2.cuh"
 
 #if OC_INST_EXACT
