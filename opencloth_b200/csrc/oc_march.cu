@@ -250,7 +250,7 @@ cudaError_t oc_march2_launch(const OcConst& c, bool exact, int ra, int rb, int s
     if (can_flag) {
         dep.flags = chain->flags; dep.epoch = ++chain->epoch;
         // <= 4 segments per strip to poll; short tiles gain nothing (measured: 16-row tiles of a 1024^2 cloth lose 15 %)
-        if (chain->valid && pdl && tile_deps && oc_dep2_chainable(seg, chain->pseg)) {
+        if (chain->valid && pdl && tile_deps && oc_dep2_chainable(seg, ra, rb, chain->pseg, chain->pra, chain->prb)) {
             dep.mode = 1; dep.pra = chain->pra; dep.prb = chain->prb; dep.pseg = chain->pseg;
         }
     }

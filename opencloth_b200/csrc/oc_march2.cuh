@@ -572,12 +572,31 @@ OC_HD int oc_dep2_index(const OcDep2& d, int xs, int k, int r0, int r1)
     const int y = (lo - d.pra) / h + k, y_hi = (hi - 1 - d.pra) / h;
     return y <= y_hi ? oc_seg2_index(d.pseg, xs, y) : -1;
 }
-// the host's condition for mode 1: the tallest tile of this launch overlaps at most four segments of the previous one
-OC_HD bool oc_dep2_chainable(const OcSeg2& seg, const OcSeg2& pseg)
+// The host's condition for mode 1.
+//  (1) the tallest tile of this launch overlaps at most four segments of the previous one (twelve flags polled);
+//  (2) tiles of at least 32 rows (performance only: short tiles lose more to the polling than they gain);
+//  (3) same tile numbering, and the tile with a given index covers (nearly) the same rows in both launches, so that
+//      it waits for its namesake.  This is what makes one flag word per tile index safe: a word is also written by
+//      the launches after the one a poller waits for, and flags[i] >= e-1 must imply that tile i of launch e-1 is
+//      done.  By (3) tile i of launch e only finishes after tile i of launch e-1 (it read its rows), and so on.
+// Whole cloths have identical tilings; within a group of substeps of a row band the range shrinks by two rows per
+// side and the segment height by at most one row, which (3) admits; anything else falls back to the grid-wide wait.
+OC_HD bool oc_dep2_chainable(const OcSeg2& seg, int ra, int rb, const OcSeg2& pseg, int pra, int prb, bool ignore_height = false)
 {
     const int h_max = seg.rs > seg.rs_e ? seg.rs : seg.rs_e, h_min = seg.rs < seg.rs_e ? seg.rs : seg.rs_e;
     const int p_min = pseg.rs < pseg.rs_e ? pseg.rs : pseg.rs_e;
-    return pseg.nstrips == seg.nstrips && h_max + 4 <= 2 * p_min && h_min >= 32;
+    if (pseg.nstrips != seg.nstrips || h_max + 4 > 2 * p_min) return false;
+    if (!ignore_height && h_min < 32) return false;
+    if (seg.nseg_all != pseg.nseg_all || seg.n_extra != pseg.n_extra) return false;
+    for (int cls = 0; cls < 2; ++cls) {                         // interior strips, edge strips
+        const int h = cls ? seg.rs_e : seg.rs, ph = cls ? pseg.rs_e : pseg.rs;
+        const int ymax = seg.nseg_all + (cls ? seg.n_extra / 2 : 0) - 1;
+        const int lim = h < ph ? h : ph;
+        const int d0 = ra - pra, d1 = (ra + ymax * h) - (pra + ymax * ph);
+        if ((d0 < 0 ? -d0 : d0) + 2 >= lim || (d1 < 0 ? -d1 : d1) + 2 >= lim) return false;
+    }
+    (void)rb; (void)prb;
+    return true;
 }
 
 template <class M, int WC, class Ctx>

@@ -416,17 +416,27 @@ int emu_check_tiling(int nstrips, int pra, int prb, int prs, int prs_e, int ra, 
     }
     for (size_t i = 0; i < cover.size(); ++i) if (cover[i] != 1) return -1;
     // the host's chaining condition; ignore_height drops its "tiles of at least 32 rows" part (a performance rule)
-    const int h_max = seg.rs > seg.rs_e ? seg.rs : seg.rs_e, p_min = pseg.rs < pseg.rs_e ? pseg.rs : pseg.rs_e;
-    if (ignore_height ? !(h_max + 4 <= 2 * p_min) : !oc_dep2_chainable(seg, pseg)) return 1;
+    if (!oc_dep2_chainable(seg, ra, rb, pseg, pra, prb, ignore_height != 0)) return 1;
     OcDep2 d = {};
     d.mode = 1; d.pra = pra; d.prb = prb; d.pseg = pseg;
     for (int t = 0; t < oc_seg2_tiles(seg); ++t) {
         int bx, by, r0, r1;
         oc_seg2_tile(seg, t, bx, by);
         oc_seg2_rows(seg, bx, by, ra, rb, r0, r1);
-        if (r0 >= r1) continue;
+        if (r0 >= r1) r1 = r0;                                          // an empty tile still orders itself (and publishes)
         int deps[12];
         for (int k = 0; k < 12; ++k) deps[k] = oc_dep2_index(d, bx - 1 + k / 4, k % 4, r0, r1);
+        {   // one flag word per tile index: the tile must wait for its namesake of the previous launch (oc_dep2_chainable (3))
+            int px, py, p0, p1;
+            oc_seg2_tile(pseg, t, px, py);
+            oc_seg2_rows(pseg, px, py, pra, prb, p0, p1);
+            if (t < oc_seg2_tiles(pseg) && p0 < p1) {
+                bool found = false;
+                for (int k = 0; k < 12; ++k) found |= deps[k] == t;
+                if (!found) return -4;
+            }
+        }
+        if (r0 >= r1) continue;
         for (int u = 0; u < oc_seg2_tiles(pseg); ++u) {
             int px, py, p0, p1;
             oc_seg2_tile(pseg, u, px, py);
