@@ -6,16 +6,22 @@
   torchrun --nproc-per-node N bench.py --gpus N ...              one rank per GPU (N = 2, 4, 8)
 
 A "step" is one StepPhysics over the whole cloth (one substep).  Workloads (BASELINE.json configs):
-  N = 1 : 2048 x 2048 cloth, reference parameters, flat-sheet start          (config 3)
-  N > 1 : 8192 x 8192 cloth cut into N row bands, halo exchange over NCCL     (config 4, strong scaling)
-  --workload batch : 4096 independent 128 x 128 cloths sharded over the ranks (config 5, no communication)
+  N = 1 : 2048 x 2048 cloth, reference parameters, flat-sheet start                       (config 3)
+  N > 1 : 8192 x 8192 cloth cut into N LINKED row bands (strong scaling): the step kernel itself stores each band's
+          two boundary rows into the neighbour's halo over NVLink peer memory and orders the GPUs with flag words,
+          tile by tile; torch.distributed (NCCL) only carries the endpoints, barriers and the timing reductions (config 4)
+  --workload batch : 4096 independent 128 x 128 cloths sharded over the ranks             (config 5, no communication)
 
-Prints ONE JSON line (rank 0).  Timing: CUDA events on the stream the kernels run on, W warm-up steps,
-then exactly K steps between barrier + synchronize, max over ranks.  The state (>= 200 MB) is larger
-than the 126 MB L2, so consecutive steps cannot be served from cache.
+Prints ONE JSON line (rank 0).  Timing: CUDA events on the stream the kernels run on, W (>= 3) warm-up steps, then
+exactly K steps between barrier + synchronize, max over ranks.  Everything that is set-up (process group, IPC
+mapping of the neighbours' buffers, the first launches) happens before the warm-up ends; the timed region contains
+kernel launches only.  The state (>= 200 MB) is larger than the 126 MB L2, so consecutive steps cannot be served
+from cache.  Every N > 1 line also carries `scaling_base` (the same 8192^2 cloth on rank 0's GPU alone, same run),
+`parallel_efficiency` against it, and `parity`: the bands' state after all the steps compared bit for bit with the
+whole cloth stepped on one GPU by the independent gather kernel.
 """
 import argparse
-import ctypes
+import hashlib
 import json
 import os
 import subprocess
@@ -37,6 +43,17 @@ def measured_peak():
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def cpu_model():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
 
 
 # ---------------------------------------------------------------------------------------------
@@ -72,7 +89,7 @@ class ClockSampler:
         self.proc.terminate()
         sm, smax, reasons = [], None, set()
         for ts, line in self.rows:
-            if ts < t0 or ts > t1 + 0.1:
+            if ts < t0 - 0.12 or ts > t1 + 0.12:
                 continue
             f = [x.strip() for x in line.split(",")]
             if len(f) < 8:
@@ -89,79 +106,106 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------
+# workload description shared by both arms (the driver compares the two `config` objects)
+# ---------------------------------------------------------------------------------------------
+def workload_name(args):
+    if args.workload == "batch":
+        return "4096 independent 128x128 cloths sharded over the ranks (BASELINE config 5)"
+    if args.gpus == 1:
+        return f"{args.n}x{args.n} cloth, single B200 (BASELINE config 3)"
+    return f"{args.n}x{args.n} cloth, {args.gpus} row bands (BASELINE config 4)"
+
+
+def config_of(args):
+    return {"workload": workload_name(args), "cloth": [args.n, args.n] if args.workload == "cloth" else [128, 128],
+            "cloths": 1 if args.workload == "cloth" else 4096, "bands": args.gpus if args.workload == "cloth" else 1,
+            "mode": args.mode, "parameters": "reference defaults (V:59-62, V:97-104, V:123-130), flat-sheet start (V:254-260)"}
+
+
+# ---------------------------------------------------------------------------------------------
 # the reference arm: the reference's own CPU implementation (oracle/_ref, verbatim StepPhysics)
 # ---------------------------------------------------------------------------------------------
-def cpu_reference(n_side, steps, warmup, budget_s=20.0):
-    """Times the verbatim reference StepPhysics (single thread — that is how the reference runs it) on a
-    bounded sample: an n_side x n_side cloth sized so that (steps + warmup) steps fit the budget."""
+def cpu_time(side, steps, warmup, threads=1, verbatim=True):
+    """Times `steps` StepPhysics of a side x side cloth on the host.  verbatim: the reference's own text
+    (oracle/_ref, single thread — that is how the reference runs it); else the C restatement (OpenMP)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import helpers
     helpers.ensure_built()
-    kind = "reference" if helpers.have_ref() else "port"
-    rate_guess = 5.0e6                                   # updates/s at large grids (SURVEY.md section 6)
-    per_step = budget_s / max(1, steps + warmup)
-    side = int(min(n_side, max(21, (per_step * rate_guess) ** 0.5)))
-    if kind == "reference":
+    use_ref = verbatim and helpers.have_ref()
+    if use_ref:
         sim = helpers.Ref(side, side)
     else:
-        os.environ.setdefault("OMP_NUM_THREADS", "1")
+        os.environ["OMP_NUM_THREADS"] = str(threads)
         sim = helpers.Oracle(side, side)
-    sim.step(warmup)
+    if warmup:
+        sim.step(warmup)
     t0 = time.perf_counter()
     sim.step(steps)
     dt = time.perf_counter() - t0
-    val = side * side * steps / dt
-    return {"value": val, "unit": UNIT, "cores": 1, "kind": kind,
-            "sample": f"{steps} steps of a {side}x{side} cloth (reference parameters), single thread as the reference runs it; "
-                      f"host has {os.cpu_count()} logical cores"}, dt / steps * 1e3
+    if hasattr(sim, "close"):
+        sim.close()
+    return side * side * steps / dt, dt, ("reference" if use_ref else "port")
+
+
+def cpu_reference(n_side, steps, warmup, budget_s=20.0):
+    """The verbatim reference StepPhysics on a bounded sample: an n x n cloth sized so that (steps + warmup) steps
+    fit the budget (the full side if it fits)."""
+    rate_guess = 5.0e6                                   # updates/s at large grids (SURVEY.md section 6)
+    per_step = budget_s / max(1, steps + warmup)
+    side = int(min(n_side, max(21, (per_step * rate_guess) ** 0.5)))
+    val, dt, kind = cpu_time(side, steps, warmup)
+    return {"value": val, "unit": UNIT, "cores": 1, "kind": kind, "cpu": cpu_model(), "host_logical_cores": os.cpu_count(),
+            "sample": f"{steps} steps of a {side}x{side} cloth (reference parameters), single thread as the reference runs it: "
+                      f"1 core used of {os.cpu_count()}"}, dt / steps * 1e3
+
+
+def cpu_baseline_configs():
+    """the reference's CPU path at 21^2 x 1000, 256^2 x 1000 and 2048^2 x 10 steps, one core."""
+    out = []
+    for side, steps in ((21, 1000), (256, 1000), (2048, 10)):
+        val, dt, kind = cpu_time(side, steps, 0)
+        out.append({"cloth": f"{side}x{side}", "steps": steps, "value": val, "unit": UNIT, "seconds": dt, "kind": kind, "cores": 1})
+    return out
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_side = 2048 if args.gpus == 1 else 8192
     steps = max(1, args.steps)
-    base, ms = cpu_reference(n_side, steps, max(0, args.warmup), budget_s=90.0)
+    base, ms = cpu_reference(args.n, steps, max(0, args.warmup), budget_s=90.0)
     # for context only: the C restatement of the same algorithm (oracle/oc_oracle.c, OpenMP over particles) on every
     # host thread, same sample size — what a multi-threaded CPU port of the reference would reach on this host
     port = None
     try:
         import re
-        import helpers
-        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
         side = int(re.search(r"of a (\d+)x", base["sample"]).group(1))
-        sim = helpers.Oracle(side, side)
-        sim.step(1)
-        t0 = time.perf_counter()
-        sim.step(steps)
-        dt = time.perf_counter() - t0
-        port = {"value": side * side * steps / dt, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+        val, dt, _ = cpu_time(side, steps, 1, threads=os.cpu_count() or 1, verbatim=False)
+        port = {"value": val, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                 "sample": f"{steps} steps of a {side}x{side} cloth, OpenMP restatement on all host threads"}
     except Exception as e:                                   # never let the extra figure break the arm
         port = {"error": str(e)[:200]}
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
-            "steps": steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak",
+            "steps": steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "strong" if (args.gpus > 1 and args.workload == "cloth") else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic (closed-form flat sheet of InitGL, reference parameters)",
-            "config": {"workload": workload_name(args), "note": "bounded sample of the workload on the host CPU, see cpu_baseline.sample"},
+            "config": config_of(args),
+            "detail": {"note": "bounded sample of the workload on the host CPU, see cpu_baseline.sample"},
             "cpu_baseline": base, "cpu_port_all_threads": port,
             "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
-def workload_name(args):
-    if args.workload == "batch":
-        return "4096 independent 128x128 cloths sharded over the ranks (BASELINE config 5)"
-    if args.gpus == 1:
-        return f"{args.n}x{args.n} cloth, single B200 (BASELINE config 3)"
-    return f"{args.n}x{args.n} cloth, {args.gpus} row bands with halo exchange (BASELINE config 4)"
-
-
 # ---------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------
+def sha_rows(a):
+    return hashlib.sha256(memoryview(a)).hexdigest()
+
+
 def run_ours(args):
+    import numpy as np
     import torch
     import torch.distributed as dist
     import opencloth_b200 as oc
@@ -180,29 +224,38 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
 
     exact = 1 if args.mode == "exact" else 0
-    K, W = args.steps, args.warmup
+    K, W = args.steps, max(args.warmup, 3)
     nx = ny = args.n
     drv = None
+    band = None
+    linked = False
     if args.workload == "batch":
         nx = ny = 128
         total_batch = 4096
         b0, b1 = (total_batch * rank) // world, (total_batch * (rank + 1)) // world
         cloth = oc.Cloth(nx, ny, batch=b1 - b0, device=local, exact=exact, substeps_per_launch=args.k)
         particles_total = total_batch * nx * ny
-        band = None
     elif world == 1:
         cloth = oc.Cloth(nx, ny, device=local, exact=exact, substeps_per_launch=args.k)
         particles_total = nx * ny
-        band = None
     else:
-        band = B.CudaBand(nx, ny, world, rank, args.halo_rows, local, exact=exact, substeps_per_launch=args.k)
+        linked = args.exchange == "linked"
+        band = B.CudaBand(nx, ny, world, rank, 2 if linked else args.halo_rows, local, exact=exact,
+                          substeps_per_launch=1 if linked else args.k)
         cloth = band.cloth
-        drv = B.BandDriver(band, rank, world, overlap=args.overlap and not args.no_overlap)
         particles_total = nx * ny
-    # a non-default torch stream: the library launches on it, torch events time it, NCCL orders against it
+    # a non-default torch stream: the library launches on it and torch events time it
     stream = torch.cuda.Stream(dev)
     torch.cuda.set_stream(stream)
-    cloth.set_stream(stream.cuda_stream)
+    if band is not None and not linked:
+        drv = B.BandDriver(band, rank, world, overlap=args.overlap)     # binds its own stream (NCCL orders against it)
+        stream = drv.stream
+        torch.cuda.set_stream(stream)
+    else:
+        cloth.set_stream(stream.cuda_stream)
+        if band is not None:
+            drv = B.LinkedBandDriver(band, rank, world)
+            drv.link()                                                   # IPC mapping of the neighbours' buffers, halos, barriers
 
     def advance(n, finish=False):
         if drv is not None:
@@ -212,7 +265,11 @@ def run_ours(args):
         else:
             cloth.step(n)
 
-    advance(max(W, 3), finish=True)
+    steps_taken = 0
+    if drv is not None and not linked:
+        W = max(W, args.halo_rows + 1)          # NCCL exchange: two complete exchange periods before the clock starts
+    advance(W, finish=True)
+    steps_taken += W
     torch.cuda.synchronize(dev)
     if world > 1:
         dist.barrier()
@@ -225,52 +282,99 @@ def run_ours(args):
     torch.cuda.synchronize(dev)
     if world > 1:
         dist.barrier()
+        torch.cuda.synchronize(dev)
     t_host0 = time.time()
     ev0.record(stream)
     advance(K, finish=True)
     ev1.record(stream)
     torch.cuda.synchronize(dev)
+    t_host1 = time.time()
     if world > 1:
         dist.barrier()
-    t_host1 = time.time()
+    steps_taken += K
     ms = ev0.elapsed_time(ev1)
     launches = cloth.launch_count - launches0
+    ms_ranks = [ms]
     if world > 1:
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+        g = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(g, t)
+        ms_ranks = [float(x.item()) for x in g]
+        ms = max(ms_ranks)
         lt = torch.tensor([launches], device=dev, dtype=torch.int64)
         dist.all_reduce(lt, op=dist.ReduceOp.SUM)
         launches = int(lt.item())
     clocks = sampler.stop(t_host0, t_host1) if rank == 0 else None
     value = particles_total * K / (ms * 1e-3)
 
-    # ---- e2e: the same metric through the C-ABI with HOST buffers (pinned): upload, step, download ----
-    e2e = None
-    if True:
-        n_local = cloth.n_local
-        hx = torch.empty((n_local, 3), dtype=torch.float32).pin_memory()
-        hl = torch.empty((n_local, 3), dtype=torch.float32).pin_memory()
-        cloth.download_into(hx.data_ptr(), hl.data_ptr(), 3)
-        e_steps = max(3, min(K, args.e2e_steps))
-        for _ in range(2):
-            cloth.upload_from(hx.data_ptr(), hl.data_ptr(), 3); advance(1, True); cloth.download_into(hx.data_ptr(), hl.data_ptr(), 3)
-        torch.cuda.synchronize(dev)
-        if world > 1:
+    # ---- N > 1: bitwise parity of the bands with the whole cloth on one GPU, and the 1-GPU rate of the same cloth ----
+    parity = None
+    scaling_base = None
+    if band is not None:
+        if not args.no_parity:
+            hx = np.empty((cloth.n_local, 3), np.float32)
+            hl = np.empty((cloth.n_local, 3), np.float32)
+            cloth.download(out=(hx, hl))
+            mine = (band.begin, band.end, sha_rows(hx), sha_rows(hl))
+            every = [None] * world
+            dist.all_gather_object(every, mine)
+            if rank == 0:
+                # the independent cross-check kernel (one thread per particle, 12-neighbour gather, scalar exact math)
+                whole = oc.Cloth(nx, ny, device=local, exact=exact, kernel=oc.OC_KERNEL_GATHER if exact else oc.OC_KERNEL_AUTO)
+                whole.step(steps_taken)
+                wx, wl = whole.download()
+                whole.close()
+                bad = []
+                for (b, e, sx, sl_) in every:
+                    if sha_rows(wx[b * nx:e * nx]) != sx or sha_rows(wl[b * nx:e * nx]) != sl_:
+                        bad.append([b, e])
+                parity = {"bitwise": len(bad) == 0, "rows": ny, "bands": [[b, e] for (b, e, _, _) in every], "steps": steps_taken,
+                          "against": ("whole cloth on one GPU, oc_k_gather (independent kernel), SHA-256 of X and X_last per band" if exact
+                                      else "whole cloth on one GPU, same kernel and mode (fast mode is deterministic), SHA-256 of X and X_last per band"),
+                          "mismatching_bands": bad}
+                del wx, wl
             dist.barrier()
-        t0 = time.perf_counter()
-        for _ in range(e_steps):
-            cloth.upload_from(hx.data_ptr(), hl.data_ptr(), 3)      # H2D of X, X_last (pinned, 12 B/particle each)
-            advance(1, True)                                       # one StepPhysics (row bands: halo exchange first)
-            cloth.download_into(hx.data_ptr(), hl.data_ptr(), 3)    # D2H of X, X_last; synchronises
-        dt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        e2e = {"value": particles_total * e_steps / dt, "unit": UNIT,
-               "h2d_bytes_per_step": particles_total * 24, "d2h_bytes_per_step": particles_total * 24,
-               "steps": e_steps, "note": "per step: oc_upload(X, X_last from pinned host) + oc_step(1) + oc_download(X, X_last)"}
+        if rank == 0:
+            big = oc.Cloth(nx, ny, device=local, exact=exact, substeps_per_launch=args.k)
+            big.step(W)
+            n_b = max(3, min(max(K, 20), 200))
+            b_ms = big.step_timed(n_b)
+            big.close()
+            scaling_base = {"workload": f"{nx}x{ny} cloth, single B200 (this workload on rank 0's GPU alone, same run)",
+                            "value": nx * ny * n_b / (b_ms * 1e-3), "unit": UNIT, "steps": n_b, "mode": args.mode}
+        dist.barrier()
+
+    # ---- e2e: the same metric through the C-ABI with HOST buffers (pinned): upload, step, download ----
+    n_local = cloth.n_local
+    hx = torch.empty((n_local, 3), dtype=torch.float32).pin_memory()
+    hl = torch.empty((n_local, 3), dtype=torch.float32).pin_memory()
+    cloth.download_into(hx.data_ptr(), hl.data_ptr(), 3)
+    e_steps = max(3, min(K, args.e2e_steps))
+
+    def e2e_step():
+        cloth.upload_from(hx.data_ptr(), hl.data_ptr(), 3)      # H2D of X, X_last (pinned, 12 B/particle each)
+        if linked:
+            drv.resync()                                       # linked row bands: the halo rows follow the uploaded state
+        advance(1, True)                                       # one StepPhysics
+        cloth.download_into(hx.data_ptr(), hl.data_ptr(), 3)    # D2H of X, X_last; synchronises
+
+    for _ in range(2):
+        e2e_step()
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e_steps):
+        e2e_step()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    e2e = {"value": particles_total * e_steps / dt, "unit": UNIT,
+           "h2d_bytes_per_step": particles_total * 24, "d2h_bytes_per_step": particles_total * 24,
+           "steps": e_steps, "note": "per step: oc_upload(X, X_last from pinned host) + oc_step(1) + oc_download(X, X_last)"
+                                     + (" (+ halo refresh between the bands)" if band is not None else "")}
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -281,27 +385,41 @@ def run_ours(args):
                 traffic = json.load(f).get(f"{args.mode}_k{args.k}_{nx}")
         except Exception:
             pass
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(W, 3),
+        if band is None:
+            exch = "none"
+        elif linked:
+            exch = ("in-kernel: every step the band-edge tiles store 2 rows per side into the neighbour's halo over NVLink peer memory "
+                    "(CUDA IPC) and release per-strip flag words the neighbour's edge tiles wait for; no host exchange")
+        else:
+            exch = "NCCL send/recv, " + ("overlapped" if args.overlap else "blocking") + f", one per {args.halo_rows // 2} steps"
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms / K, "higher_is_better": True,
                 "scaling": "weak" if (world == 1 or args.workload == "batch") else "strong",
                 "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic (closed-form flat sheet of InitGL V:254-260, reference parameters; state larger than L2)",
-                "config": {"workload": workload_name(args), "mode": args.mode + (" (bit-identical to the reference CPU path)" if exact else " (FMA/rsqrt, within 1e-5 / 1e-3 of extent)"),
-                           "substeps_per_launch": args.k, "kernel": "oc_k_march2 (fused marching stencil, 2 columns/thread, packed FP32x2)" if args.k <= 1 else "oc_k_march (staged, k substeps per launch)",
-                           "l2": "state 48 B x particles per step > 126 MB L2 (no flush needed)" if particles_total * 48 > 126e6 else "state fits L2",
-                           "halo_rows": args.halo_rows if band is not None else 0,
-                           "exchange": ("overlapped with the interior of the last substep of each group" if (band is not None and args.overlap and not args.no_overlap) else ("blocking, one per halo_rows/2 steps" if band is not None else "none"))},
+                "config": config_of(args),
+                "detail": {"mode": args.mode + (" (bit-identical to the reference CPU path)" if exact else " (FMA/rsqrt, within 1e-5 / 1e-3 of extent)"),
+                           "substeps_per_launch": args.k,
+                           "kernel": "oc_k_march2 (fused marching stencil, 2 columns/thread, packed FP32x2)" if args.k <= 1 else "oc_k_march (staged, k substeps per launch)",
+                           "l2": "state 48 B x particles per step > 126 MB L2 (no flush needed)" if particles_total * 48 / max(1, world) > 126e6 else "state fits L2",
+                           "halo_rows": (2 if linked else args.halo_rows) if band is not None else 0, "exchange": exch,
+                           "halo_bytes_per_step_per_gpu": (2 * 2 * nx * 16 if (band is not None and linked) else None),
+                           "ms_per_rank": [m_ / K for m_ in ms_ranks]},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_update": ALG_BYTES_PER_UPDATE,
-                             "note": "per GPU; achieved = updates/s/GPU x 48 B; the kernel is FP32-issue/LSU bound, not DRAM bound (DESIGN.md)"},
-                "clocks": clocks, "gpu_launches": launches}
-        if e2e is not None:
-            line["e2e"] = e2e
+                             "note": "per GPU; achieved = updates/s/GPU x 48 B; the kernel is FP32-issue bound, not DRAM bound (DESIGN.md)"},
+                "clocks": clocks, "gpu_launches": launches, "e2e": e2e}
+        if band is not None:
+            line["exchanges"] = drv.exchanges if not linked else 0
+            line["exchange_ms_per_step"] = 0.0 if linked else None
+            line["scaling_base"] = scaling_base
+            line["parallel_efficiency"] = value / (world * scaling_base["value"]) if scaling_base else None
+            line["parity"] = parity
         if world == 1 and args.workload == "cloth":
             # the library's other arithmetic mode on the same workload (not the headline; CUDA events in oc_step_timed)
             other = oc.Cloth(nx, ny, device=local, exact=0 if exact else 1, substeps_per_launch=args.k)
-            other.step(max(W, 3))
-            n_o = max(3, min(K, 500))
+            other.step(W)
+            n_o = max(3, min(max(K, 20), 500))
             o_ms = other.step_timed(n_o)
             o_val = nx * ny * n_o / (o_ms * 1e-3)
             other.close()
@@ -311,15 +429,28 @@ def run_ours(args):
             # N > 1 runs split the 8192^2 cloth of BASELINE config 4 (strong scaling): its 1-GPU rate, measured here, is
             # the base a parallel efficiency has to be computed against (not this line's 2048^2 value)
             big = oc.Cloth(8192, 8192, device=local, exact=exact, substeps_per_launch=args.k)
-            big.step(max(W, 3))
-            n_b = max(3, min(K, 300))
+            big.step(W)
+            n_b = max(3, min(max(K, 20), 200))
             b_ms = big.step_timed(n_b)
             big.close()
             line["scaling_base"] = {"workload": "8192x8192 cloth, single B200 (the N>1 workload on one GPU)", "value": 8192 * 8192 * n_b / (b_ms * 1e-3),
                                     "unit": UNIT, "steps": n_b, "mode": args.mode}
+        if world == 1 and args.workload == "cloth" and not args.no_batch:
+            # BASELINE config 5 on this GPU (its share of the 8-GPU job: 512 of the 4096 cloths), same mode
+            bc = oc.Cloth(128, 128, batch=512, device=local, exact=exact)
+            bc.step(W)
+            n_c = max(3, min(max(K, 20), 200))
+            c_ms = bc.step_timed(n_c)
+            bc.close()
+            line["batch_config5"] = {"workload": "512 independent 128x128 cloths (one GPU's share of BASELINE config 5; no communication)",
+                                     "value": 512 * 128 * 128 * n_c / (c_ms * 1e-3), "unit": UNIT, "steps": n_c, "mode": args.mode}
         if world == 1 and not args.no_cpu_baseline:
             base, _ = cpu_reference(nx, 3, 1, budget_s=15.0)
             line["cpu_baseline"] = base
+            try:
+                line["cpu_baseline_configs"] = cpu_baseline_configs()
+            except Exception as e:
+                line["cpu_baseline_configs"] = {"error": str(e)[:200]}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -336,17 +467,19 @@ def main():
     ap.add_argument("--n", type=int, default=0, help="cloth side; default 2048 at N=1, 8192 at N>1")
     ap.add_argument("--mode", default="exact", choices=["exact", "fast"])
     ap.add_argument("--k", type=int, default=1, help="substeps per launch (temporal blocking)")
-    ap.add_argument("--halo-rows", type=int, default=24, help="row bands: halo rows either side (one exchange per halo_rows/2 steps)")
+    ap.add_argument("--exchange", default="linked", choices=["linked", "nccl"],
+                    help="row bands: linked = in-kernel peer stores + flag words (default); nccl = host-driven send/recv every halo_rows/2 steps")
+    ap.add_argument("--halo-rows", type=int, default=24, help="--exchange nccl: halo rows either side (one exchange per halo_rows/2 steps)")
     ap.add_argument("--e2e-steps", type=int, default=20)
-    ap.add_argument("--overlap", action="store_true", help="row bands: start the halo exchange on a side stream while the interior of the last "
-                    "substep of a group is still computed (measured slower than the blocking exchange at N = 8: the split launches "
-                    "interrupt the chained steps)")
-    ap.add_argument("--no-overlap", action="store_true", help="(default) blocking halo exchange")
+    ap.add_argument("--overlap", action="store_true", help="--exchange nccl: start the exchange on a side stream during the last substep of a group")
+    ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the bitwise comparison with the whole cloth on one GPU")
+    ap.add_argument("--no-batch", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    args.gpus = max(args.gpus, world) if world > 1 else args.gpus
     if args.n == 0:
-        args.n = 2048 if max(args.gpus, world) == 1 else 8192
+        args.n = 2048 if args.gpus == 1 else 8192
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define OC_ABI_VERSION 1
+#define OC_ABI_VERSION 2
 
 typedef enum oc_status {
     OC_OK = 0,
@@ -48,7 +48,8 @@ typedef enum oc_kernel {
     OC_KERNEL_MARCH = 2,     /* fused shared-memory marching stencil, one column per thread, k substeps per launch */
     OC_KERNEL_MARCH2 = 3,    /* the same with two columns per thread (one substep per launch) */
     OC_KERNEL_RESIDENT = 4   /* small whole cloths (<= 1536 particles): one CTA per cloth keeps the state in shared memory
-                                and takes all the substeps of an oc_step call in one launch */
+                                and takes all the substeps of an oc_step call in one launch; larger cloths and row
+                                bands are served by OC_KERNEL_MARCH2 */
 } oc_kernel;
 
 typedef struct oc_cloth oc_cloth;      /* opaque; owns all device memory of one simulation */
@@ -124,7 +125,11 @@ const char* oc_last_error(void);
 int oc_set_particle(oc_cloth* c, int cloth, int idx, const float xyz[3]);
 
 /* ---- stream / timing plumbing (the host side owns streams; torch passes its current stream) --- */
-int oc_set_stream(oc_cloth* c, void* cuda_stream);          /* cudaStream_t; NULL = handle's own stream */
+/* Launch on the caller's stream (cudaStream_t).  NULL is CUDA's legacy default stream, as everywhere in the runtime
+ * API (so torch's default stream, whose handle is 0, binds correctly).  oc_reset_stream returns to the handle's own
+ * non-blocking stream, which is what a new handle uses.  Both wait for the work queued so far. */
+int oc_set_stream(oc_cloth* c, void* cuda_stream);
+int oc_reset_stream(oc_cloth* c);
 /* kernels launched by this handle since create (bench.py's gpu_launches) */
 long long oc_launch_count(const oc_cloth* c);
 /* time n substeps on the device with CUDA events on the handle's stream; returns milliseconds */
@@ -158,6 +163,31 @@ int oc_step_split(oc_cloth* c, int n, void* exchange_stream, int* did_split);
  * across devices, i.e. NVLink on an HGX box), ordered after each band's queued work and before its
  * next step, without blocking the host, then marks all bands refreshed. */
 int oc_halo_exchange(oc_cloth* const* bands, int n);
+
+/* ---- linked row bands: halo rows pushed by the kernel over peer memory (NVLink), no exchange step ----------------
+ * Multi-GPU path of choice.  One band handle per GPU (oc_params.row_begin/row_end,
+ * halo_rows >= 2), in one process or one process per GPU.  Linking maps each neighbour's position buffers and a small
+ * array of flag words into this handle (CUDA IPC across processes, peer access inside one).  From then on oc_step on
+ * a linked band computes exactly its owned rows every substep; the tiles at the band edge store the two rows the
+ * neighbour's bend springs reach (V:311, V:317) straight into the neighbour's halo and release one flag word per
+ * column strip in the neighbour's memory, and the neighbour's edge tiles of the next substep wait for those words.
+ * No host round trip, no exchange period, no recomputed rows, and the chained launches of a band never break.
+ * Every band must take the same steps (same n, same order) — the flag words count linked substeps.
+ *
+ * Protocol (the caller provides the barriers when the bands live in different processes):
+ *   1. every band: oc_sync, oc_band_endpoint(c, blob)              -> exchange the blobs (any transport)
+ *   2. [barrier]   every band: oc_band_link(c, upper blob or NULL, lower blob or NULL), oc_band_pull_halo, oc_sync
+ *   3. [barrier]   oc_step(c, n) on every band, freely; oc_sync / oc_download as usual
+ * After oc_upload / oc_set_particle on any band (call oc_set_particle on EVERY band: each updates the copies it
+ * stores): every band oc_sync, [barrier], oc_band_pull_halo, oc_sync, [barrier].
+ * oc_band_link_local does steps 1-3 for bands living in one process (the C++ harness; tests).
+ * A band that waits more than 30 s for a neighbour makes oc_sync / oc_step / oc_download fail with OC_ERR_CUDA. */
+#define OC_BAND_ENDPOINT_BYTES 512
+int oc_band_endpoint(oc_cloth* c, void* blob, size_t bytes);
+int oc_band_link(oc_cloth* c, const void* upper_blob, const void* lower_blob);
+int oc_band_pull_halo(oc_cloth* c);
+int oc_band_unlink(oc_cloth* c);
+int oc_band_link_local(oc_cloth* const* bands, int n);
 
 /* ---- environment switches (development / measurement; read by the library, defaults in brackets) -------------
  *   OC_PDL=0          launch oc_k_march2 without programmatic stream serialization              [on]

@@ -6,7 +6,7 @@ include/opencloth.h.  Importing the package does not need a GPU; creating a ``Cl
 fails loudly without one (there is no CPU fallback).
 """
 from ._abi import (LIB_PATH, OcParams, OpenClothError, OC_KERNEL_AUTO, OC_KERNEL_GATHER, OC_KERNEL_MARCH, OC_KERNEL_MARCH2, OC_KERNEL_RESIDENT)
-from .cloth import Cloth, default_params, version
+from .cloth import Cloth, default_params, version, link_bands_local
 
-__all__ = ["Cloth", "default_params", "version", "OcParams", "OpenClothError", "LIB_PATH",
+__all__ = ["Cloth", "default_params", "version", "link_bands_local", "OcParams", "OpenClothError", "LIB_PATH",
            "OC_KERNEL_AUTO", "OC_KERNEL_GATHER", "OC_KERNEL_MARCH", "OC_KERNEL_MARCH2", "OC_KERNEL_RESIDENT"]

@@ -23,6 +23,8 @@ OC_KERNEL_MARCH = 2
 OC_KERNEL_MARCH2 = 3
 OC_KERNEL_RESIDENT = 4
 
+OC_BAND_ENDPOINT_BYTES = 512
+
 
 class OcParams(ctypes.Structure):
     """Mirror of ``oc_params`` (include/opencloth.h). Field order and types must match exactly."""
@@ -65,6 +67,12 @@ SYMBOLS = {
     "oc_last_error": (ctypes.c_char_p, []),
     "oc_set_particle": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, _P(ctypes.c_float)]),
     "oc_set_stream": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "oc_reset_stream": (ctypes.c_int, [ctypes.c_void_p]),
+    "oc_band_endpoint": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]),
+    "oc_band_link": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "oc_band_pull_halo": (ctypes.c_int, [ctypes.c_void_p]),
+    "oc_band_unlink": (ctypes.c_int, [ctypes.c_void_p]),
+    "oc_band_link_local": (ctypes.c_int, [_P(ctypes.c_void_p), ctypes.c_int]),
     "oc_launch_count": (ctypes.c_longlong, [ctypes.c_void_p]),
     "oc_step_timed": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _P(ctypes.c_float)]),
     "oc_halo_send_region": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, _P(ctypes.c_void_p), _P(ctypes.c_size_t)]),

@@ -13,6 +13,8 @@ gloo (tests/test_bands_gloo.py drives it with the kernel emulator as the band ob
 the band object is an ``opencloth_b200.Cloth`` created with a row range and the tensors alias the
 library's device buffers (NCCL send/recv over NVLink).
 """
+import contextlib
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -72,8 +74,53 @@ class CudaBand:
         return self.cloth.halo_budget
 
     def use_current_stream(self):
-        """Run the band's kernels on torch's current stream so that torch.distributed orders against them."""
+        """Run the band's kernels on torch's current stream so that torch.distributed orders against them
+        (torch's default stream has handle 0 = CUDA's legacy default stream, which oc_set_stream(NULL) now means)."""
         self.cloth.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+
+
+class LinkedBandDriver:
+    """One row band per process / GPU, linked to its neighbours through peer memory (include/opencloth.h, "linked
+    row bands").  The process group is used ONCE, to hand the neighbours' endpoints round and for the barriers of the
+    link protocol; after that ``step(n)`` is just ``oc_step(n)`` on every rank — the kernel itself stores the two
+    boundary rows into the neighbour's halo over NVLink and orders the steps of different GPUs with flag words, tile by
+    tile.  No exchange step, no recomputed halo rows, no host synchronisation while stepping.
+
+    Every rank must call step() with the same n in the same order.
+    """
+
+    def __init__(self, band, rank, world, group=None):
+        self.band, self.rank, self.world, self.group = band, rank, world, group
+        self.cloth = band.cloth
+        self.exchanges = 0                  # host-side exchanges on the step path: none
+
+    def link(self):
+        c = self.cloth
+        c.sync()
+        blobs = [None] * self.world
+        dist.all_gather_object(blobs, c.band_endpoint(), group=self.group)      # doubles as the barrier after sync
+        c.band_link(blobs[self.rank - 1] if self.rank > 0 else None,
+                    blobs[self.rank + 1] if self.rank + 1 < self.world else None)
+        self.resync(barrier_before=False)
+
+    def resync(self, barrier_before=True):
+        """After oc_upload / oc_set_particle on the bands: refresh the halo rows from the neighbours' owned rows."""
+        c = self.cloth
+        if barrier_before:
+            c.sync()
+            dist.barrier(group=self.group)
+        c.band_pull_halo()
+        c.sync()
+        dist.barrier(group=self.group)
+
+    def exchange(self):
+        self.resync()
+
+    def step(self, n):
+        self.cloth.step(n)
+
+    def finish(self):
+        pass
 
 
 class BandDriver:
@@ -90,6 +137,13 @@ class BandDriver:
     def __init__(self, band, rank, world, group=None, overlap=False):
         self.band, self.rank, self.world, self.group = band, rank, world, group
         self.exchanges = 0
+        # torch.distributed orders its send/recv against torch's CURRENT stream: the band's kernels must run on that
+        # very stream, or the exchange could read boundary rows before the step has written them.  CUDA bands are
+        # bound to a dedicated torch stream here; step() and exchange() run inside it.
+        self.stream = None
+        if hasattr(band, "cloth") and torch.cuda.is_available():
+            self.stream = torch.cuda.Stream(band.device)
+            band.cloth.set_stream(self.stream.cuda_stream)
         # overlap: start the exchange as soon as the boundary rows of the last substep of a group exist, on a
         # side stream, while the interior of that substep is still being computed (CUDA bands only)
         self.overlap = overlap and hasattr(band, "step_split") and torch.cuda.is_available()
@@ -122,7 +176,23 @@ class BandDriver:
             self.band.refreshed()
             self.exchanges += 1
 
+    def _in_stream(self):
+        return torch.cuda.stream(self.stream) if self.stream is not None else contextlib.nullcontext()
+
     def exchange(self):
+        with self._in_stream():
+            self._exchange()
+
+    def step(self, n):
+        with self._in_stream():
+            self._step(n)
+
+    def finish(self):
+        """Complete an exchange that is still in flight (call before reading the state)."""
+        with self._in_stream():
+            self._finish_pending()
+
+    def _exchange(self):
         if self.pending is not None:
             return self._finish_pending()
         ops = self._ops()
@@ -132,10 +202,10 @@ class BandDriver:
         self.band.refreshed()
         self.exchanges += 1
 
-    def step(self, n):
+    def _step(self, n):
         while n > 0:
             if self.band.budget == 0:
-                self.exchange()
+                self._exchange()
             m = min(n, self.band.budget)
             if self.overlap and m == self.band.budget:
                 # this group ends at an exchange point: boundary rows first, exchange on the side stream
@@ -149,11 +219,6 @@ class BandDriver:
             else:
                 self.band.step(m)
             n -= m
-
-    def finish(self):
-        """Complete an exchange that is still in flight (call before reading the state)."""
-        self._finish_pending()
-
 
 def gather_rows(local_x, ny, nx, world, rank, group=None):
     """All ranks' owned rows concatenated on every rank (diagnostics / tests only; not on the step path)."""

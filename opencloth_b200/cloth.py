@@ -124,7 +124,27 @@ class Cloth:
 
     # ---- plumbing ----------------------------------------------------------------------------
     def set_stream(self, cuda_stream_ptr):
+        """Launch on this cudaStream_t (0 / None = CUDA's legacy default stream, e.g. torch's default stream)."""
         check(self._lib.oc_set_stream(self._h, ctypes.c_void_p(cuda_stream_ptr) if cuda_stream_ptr else None))
+
+    def reset_stream(self):
+        """Back to the handle's own non-blocking stream."""
+        check(self._lib.oc_reset_stream(self._h))
+
+    # ---- linked row bands (include/opencloth.h, "linked row bands") -----------------------------
+    def band_endpoint(self):
+        blob = ctypes.create_string_buffer(_abi.OC_BAND_ENDPOINT_BYTES)
+        check(self._lib.oc_band_endpoint(self._h, blob, len(blob)))
+        return blob.raw
+
+    def band_link(self, upper, lower):
+        check(self._lib.oc_band_link(self._h, upper, lower))      # bytes or None
+
+    def band_pull_halo(self):
+        check(self._lib.oc_band_pull_halo(self._h))
+
+    def band_unlink(self):
+        check(self._lib.oc_band_unlink(self._h))
 
     @property
     def launch_count(self):
@@ -164,3 +184,9 @@ class Cloth:
 
 def version():
     return _abi.load().oc_version().decode()
+
+
+def link_bands_local(cloths):
+    """Link band handles that live in this process (rows in order): oc_band_link_local."""
+    arr = (ctypes.c_void_p * len(cloths))(*[c._h for c in cloths])
+    check(_abi.load().oc_band_link_local(arr, len(cloths)))

@@ -68,7 +68,21 @@ struct oc_cloth {
     double*   d_energy;
     unsigned long long* d_dbg;   // development counters (OC_DEBUG & 4)
     OcChain2  chain;             // tile-level dependencies between consecutive oc_k_march2 launches (oc_march2.cuh)
+    unsigned* h_err;             // sticky error word written by the kernels (pinned, mapped): see OcConst::err
+    // linked row bands (OcPeer2): the neighbours' buffers and flag words, mapped into this process / device
+    struct {
+        bool      on;
+        bool      has[2];               // [0] upper, [1] lower neighbour
+        float4*   buf[2][4];            // the neighbour's four position buffers
+        unsigned* flags_out[2];         // the neighbour's incoming-flag array for my side
+        int       row_lo[2];            // global row held in the neighbour's storage row 0
+        int       row_begin[2], row_end[2];
+        void*     opened[2][5];         // cudaIpcOpenMemHandle mappings to close (nullptr: same process)
+        unsigned  epoch;                // linked steps taken
+    } link;
+    unsigned* in_flags;          // device: 2 x OC_LINK_STRIPS words released by the neighbours' boundary tiles
 };
+#define OC_LINK_STRIPS 4096
 #define OC_CHAIN_CAP (1 << 16)
 // anything that writes the state other than the chained kernel itself, or reorders the stream, breaks the chain
 static inline void chain_break(oc_cloth* c) { c->chain.valid = false; }
@@ -83,6 +97,9 @@ static int free_handle(oc_cloth* c)
     if (c->d_energy) cudaFree(c->d_energy);
     if (c->d_dbg) cudaFree(c->d_dbg);
     if (c->chain.flags) cudaFree(c->chain.flags);
+    if (c->in_flags) cudaFree(c->in_flags);
+    if (c->h_err) cudaFreeHost(c->h_err);
+    for (int sd = 0; sd < 2; ++sd) for (int b = 0; b < 5; ++b) if (c->link.opened[sd][b]) cudaIpcCloseMemHandle(c->link.opened[sd][b]);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->ev_ready) cudaEventDestroy(c->ev_ready);
@@ -241,10 +258,10 @@ extern "C" int oc_create(oc_cloth** out, const oc_params* p)
     if (!c) return oc_fail(OC_ERR_NOMEM, "host allocation failed");
     memset(c, 0, sizeof(*c));
     c->p = *p;
-    if (p->device >= 0) c->dev = p->device; else { OC_CUDA(cudaGetDevice(&c->dev)); }
-    if (c->dev >= ndev) { delete c; return oc_fail(OC_ERR_INVALID, "device %d of %d", p->device, ndev); }
 #define OC_CREATE_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { free_handle(c); \
         return oc_fail(e_ == cudaErrorMemoryAllocation ? OC_ERR_NOMEM : OC_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); } } while (0)
+    if (p->device >= 0) c->dev = p->device; else { OC_CREATE_CUDA(cudaGetDevice(&c->dev)); }
+    if (c->dev >= ndev) { free_handle(c); return oc_fail(OC_ERR_INVALID, "device %d of %d", p->device, ndev); }
     OC_CREATE_CUDA(cudaSetDevice(c->dev));
     OC_CREATE_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->dev));
 
@@ -271,6 +288,11 @@ extern "C" int oc_create(oc_cloth** out, const oc_params* p)
     OC_CREATE_CUDA(cudaMalloc(&c->chain.flags, OC_CHAIN_CAP * sizeof(unsigned)));
     OC_CREATE_CUDA(cudaMemset(c->chain.flags, 0, OC_CHAIN_CAP * sizeof(unsigned)));
     c->chain.cap = OC_CHAIN_CAP; c->chain.epoch = 0; c->chain.valid = false;
+    OC_CREATE_CUDA(cudaMalloc(&c->in_flags, 2 * OC_LINK_STRIPS * sizeof(unsigned)));
+    OC_CREATE_CUDA(cudaMemset(c->in_flags, 0, 2 * OC_LINK_STRIPS * sizeof(unsigned)));
+    OC_CREATE_CUDA(cudaHostAlloc(&c->h_err, sizeof(unsigned), cudaHostAllocMapped));
+    *c->h_err = 0u;
+    OC_CREATE_CUDA(cudaHostGetDevicePointer(&k.err, c->h_err, 0));
     OC_CREATE_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
     OC_CREATE_CUDA(cudaEventCreate(&c->ev0));
@@ -288,6 +310,9 @@ extern "C" int oc_create(oc_cloth** out, const oc_params* p)
     }
     rc = oc_march_configure(c->dev);
     if (rc == 0) rc = oc_march2_configure(c->dev);
+    // function attributes are per device: set them at every create, for the device of this handle
+    if (rc == 0) rc = (int)cudaFuncSetAttribute((const void*)&oc_k_resident<MathExact>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OcResidentSmem::bytes(OC_RESIDENT_MAX_PARTICLES));
+    if (rc == 0) rc = (int)cudaFuncSetAttribute((const void*)&oc_k_resident<MathFast>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OcResidentSmem::bytes(OC_RESIDENT_MAX_PARTICLES));
     if (rc != 0) { free_handle(c); return oc_fail(OC_ERR_CUDA, "oc_march_configure failed: %s", cudaGetErrorString((cudaError_t)rc)); }
 #undef OC_CREATE_CUDA
     *out = c;
@@ -325,14 +350,32 @@ extern "C" int oc_get_params(const oc_cloth* c, oc_params* p)
     return OC_OK;
 }
 
+static int bind_stream(oc_cloth* c, cudaStream_t s)
+{
+    OC_CUDA(cudaSetDevice(c->dev));
+    OC_CUDA(cudaStreamSynchronize(c->stream));
+    c->stream = s;
+    chain_break(c);
+    return OC_OK;
+}
 extern "C" int oc_set_stream(oc_cloth* c, void* s)
 {
     if (!c) return oc_fail(OC_ERR_INVALID, "oc_set_stream: null");
-    OC_CUDA(cudaSetDevice(c->dev));
-    OC_CUDA(cudaStreamSynchronize(c->stream));
-    c->stream = s ? (cudaStream_t)s : c->own_stream;
-    chain_break(c);
-    return OC_OK;
+    return bind_stream(c, (cudaStream_t)s);          // NULL is the legacy default stream, like everywhere in CUDA
+}
+extern "C" int oc_reset_stream(oc_cloth* c)
+{
+    if (!c) return oc_fail(OC_ERR_INVALID, "oc_reset_stream: null");
+    return bind_stream(c, c->own_stream);
+}
+
+// a kernel that gave up on a tile dependency has written why into the handle's error word and trapped
+static int check_err_word(const oc_cloth* c)
+{
+    const unsigned e = c->h_err ? *(volatile unsigned*)c->h_err : 0u;
+    if (e == 0u) return OC_OK;
+    return oc_fail(OC_ERR_CUDA, e == 2u ? "a tile waited more than 30 s for a boundary tile of a neighbour GPU (linked row bands): a band fell behind, failed, or took a different number of steps"
+                                        : "a tile dependency between consecutive launches timed out; the state is invalid");
 }
 
 extern "C" long long oc_launch_count(const oc_cloth* c) { return c ? c->launches : 0; }
@@ -341,7 +384,10 @@ extern "C" int oc_sync(oc_cloth* c)
 {
     if (!c) return oc_fail(OC_ERR_INVALID, "oc_sync: null");
     OC_CUDA(cudaSetDevice(c->dev));
-    OC_CUDA(cudaStreamSynchronize(c->stream));
+    const cudaError_t e = cudaStreamSynchronize(c->stream);
+    const int rc = check_err_word(c);
+    if (rc) return rc;
+    OC_CUDA(e);
     return OC_OK;
 }
 
@@ -396,8 +442,7 @@ extern "C" int oc_download(oc_cloth* c, float* X, float* X_last, int stride)
     OC_CUDA(cudaGetLastError());
     if (X) OC_CUDA(cudaMemcpyAsync(X, c->stage[0], bytes, cudaMemcpyDeviceToHost, c->stream));
     if (X_last) OC_CUDA(cudaMemcpyAsync(X_last, c->stage[1], bytes, cudaMemcpyDeviceToHost, c->stream));
-    OC_CUDA(cudaStreamSynchronize(c->stream));
-    return OC_OK;
+    return oc_sync(c);
 }
 
 extern "C" int oc_set_particle(oc_cloth* c, int cloth, int idx, const float xyz[3])
@@ -421,7 +466,8 @@ extern "C" int oc_set_particle(oc_cloth* c, int cloth, int idx, const float xyz[
 static int pick_kernel(const oc_cloth* c)
 {
     const bool can_reside = !c->q.band && (long long)c->p.nx * c->p.ny <= OC_RESIDENT_MAX_PARTICLES;
-    if (c->p.kernel == OC_KERNEL_RESIDENT) return can_reside ? OC_KERNEL_RESIDENT : OC_KERNEL_GATHER;
+    if (c->link.on) return OC_KERNEL_MARCH2;             // linked row bands: the kernel that pushes its boundary rows
+    if (c->p.kernel == OC_KERNEL_RESIDENT) return can_reside ? OC_KERNEL_RESIDENT : OC_KERNEL_MARCH2;   // a cloth that does not fit one CTA's shared memory: the fastest general kernel
     if (c->p.kernel != OC_KERNEL_AUTO) return c->p.kernel;
     // small whole cloths (the reference's own 21 x 21): state resident in shared memory, all substeps in one launch.
     // One CTA per cloth: worth it while the CTA's 1024 threads cover the cloth's springs in a few passes (beyond that
@@ -437,8 +483,20 @@ static int launch_rows(oc_cloth* c, int kern, const OcLaunch& L, int ra, int rb)
     if (rb <= ra) return OC_OK;
     if (kern == OC_KERNEL_MARCH2) {
         int nl = 0;
+        OcPeer2 peer = {};
+        if (c->link.on) {
+            const long long U = c->p.nx;
+            for (int sd = 0; sd < 2; ++sd) {
+                if (!c->link.has[sd]) continue;
+                peer.c[sd] = c->link.buf[sd][L.dst] - (long long)c->link.row_lo[sd] * U;
+                peer.flags_out[sd] = c->link.flags_out[sd];
+                peer.flags_in[sd] = c->in_flags + sd * OC_LINK_STRIPS;
+            }
+            peer.epoch = ++c->link.epoch;
+        }
         cudaError_t e = oc_march2_launch(c->k, c->p.exact != 0, ra, rb, c->sm_count,
-                                         c->buf[L.src_a], c->buf[L.src_b], c->buf[L.dst], c->stream, &nl, &c->chain);
+                                         c->buf[L.src_a], c->buf[L.src_b], c->buf[L.dst], c->stream, &nl, &c->chain,
+                                         c->link.on ? &peer : nullptr);
         c->launches += nl;
         if (e != cudaSuccess) return oc_fail(OC_ERR_CUDA, "march2 kernel launch failed: %s", cudaGetErrorString(e));
     } else if (kern == OC_KERNEL_RESIDENT) {
@@ -446,12 +504,6 @@ static int launch_rows(oc_cloth* c, int kern, const OcLaunch& L, int ra, int rb)
         const int N = c->p.nx * c->p.ny;
         const size_t smem = OcResidentSmem::bytes(N);
         int threads = (3 * N + 31) / 32 * 32; if (threads > OC_RESIDENT_THREADS) threads = OC_RESIDENT_THREADS;
-        static bool configured[2] = { false, false };
-        const void* fn = c->p.exact ? (const void*)&oc_k_resident<MathExact> : (const void*)&oc_k_resident<MathFast>;
-        if (!configured[c->p.exact ? 1 : 0]) {
-            OC_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OcResidentSmem::bytes(OC_RESIDENT_MAX_PARTICLES)));
-            configured[c->p.exact ? 1 : 0] = true;
-        }
         if (c->p.exact) oc_k_resident<MathExact><<<c->p.batch, threads, smem, c->stream>>>(c->k, c->buf[L.src_a], c->buf[L.src_b], c->buf[L.dst], c->buf[L.dst_prev], L.S);
         else            oc_k_resident<MathFast><<<c->p.batch, threads, smem, c->stream>>>(c->k, c->buf[L.src_a], c->buf[L.src_b], c->buf[L.dst], c->buf[L.dst_prev], L.S);
         c->launches++;
@@ -482,7 +534,8 @@ static int step_impl(oc_cloth* c, int n, cudaStream_t split_stream, bool want_sp
     if (did_split) *did_split = 0;
     if (!c) return oc_fail(OC_ERR_INVALID, "oc_step: null");
     if (n < 0) return oc_fail(OC_ERR_INVALID, "oc_step: n < 0");
-    if (c->q.band && c->q.fresh + n > c->q.kmax)
+    { const int rc = check_err_word(c); if (rc) return rc; }
+    if (c->q.band && !c->q.linked && c->q.fresh + n > c->q.kmax)
         return oc_fail(OC_ERR_INVALID, "oc_step: %d substeps requested but only %d remain before the halo rows must be exchanged "
                                        "(halo_rows=%d)", n, c->q.kmax - c->q.fresh, c->p.halo_rows);
     OC_CUDA(cudaSetDevice(c->dev));
@@ -493,7 +546,7 @@ static int step_impl(oc_cloth* c, int n, cudaStream_t split_stream, bool want_sp
         OcLaunch L;
         oc_host_next_launch(c->q, n, kmaxS, L);
         const int H = c->p.halo_rows;
-        const bool split = want_split && n == 0 && c->q.band && L.S == 1 && L.ra == c->p.row_begin && L.rb == c->p.row_end &&
+        const bool split = want_split && n == 0 && c->q.band && !c->q.linked && L.S == 1 && L.ra == c->p.row_begin && L.rb == c->p.row_end &&
                            (L.rb - L.ra) > 2 * H + 8;
         int rc;
         if (!split) {
@@ -565,7 +618,7 @@ extern "C" int oc_halo_refreshed(oc_cloth* c)
 extern "C" int oc_halo_budget(const oc_cloth* c)
 {
     if (!c) return 0;
-    return c->q.band ? c->q.kmax - c->q.fresh : 0x7fffffff;
+    return (c->q.band && !c->q.linked) ? c->q.kmax - c->q.fresh : 0x7fffffff;
 }
 
 extern "C" int oc_halo_exchange(oc_cloth* const* bands, int n)
@@ -623,6 +676,169 @@ extern "C" int oc_halo_exchange(oc_cloth* const* bands, int n)
         if (b + 1 < n) OC_CUDA(cudaStreamWaitEvent(me->stream, bands[b + 1]->ev_filled, 0));
         me->q.fresh = 0;
     }
+    return OC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// linked row bands: peer-memory halos and cross-GPU tile flags (OcPeer2 in oc_march2.cuh)
+// ------------------------------------------------------------------------------------------------
+#include <unistd.h>
+struct OcEndpoint {
+    unsigned magic, abi;
+    long long pid;
+    int dev;
+    int nx, ny, row_begin, row_end, row_lo, srows, halo_rows, ia, ib;
+    int ipc_ok;
+    unsigned long long buf_ptr[4], flags_ptr;        // addresses in the exporting process
+    cudaIpcMemHandle_t buf_h[4], flags_h;
+};
+static_assert(sizeof(OcEndpoint) <= OC_BAND_ENDPOINT_BYTES, "OC_BAND_ENDPOINT_BYTES too small");
+#define OC_ENDPOINT_MAGIC 0x4f43424eu
+
+extern "C" int oc_band_endpoint(oc_cloth* c, void* blob, size_t bytes)
+{
+    if (!c || !blob) return oc_fail(OC_ERR_INVALID, "oc_band_endpoint: null");
+    if (bytes < OC_BAND_ENDPOINT_BYTES) return oc_fail(OC_ERR_INVALID, "oc_band_endpoint: buffer of %zu bytes, need OC_BAND_ENDPOINT_BYTES = %d", bytes, OC_BAND_ENDPOINT_BYTES);
+    if (!c->q.band) return oc_fail(OC_ERR_INVALID, "oc_band_endpoint: the handle owns the whole cloth");
+    OC_CUDA(cudaSetDevice(c->dev));
+    memset(blob, 0, OC_BAND_ENDPOINT_BYTES);
+    OcEndpoint e;
+    memset(&e, 0, sizeof(e));
+    e.magic = OC_ENDPOINT_MAGIC; e.abi = OC_ABI_VERSION; e.pid = (long long)getpid(); e.dev = c->dev;
+    e.nx = c->p.nx; e.ny = c->p.ny; e.row_begin = c->p.row_begin; e.row_end = c->p.row_end;
+    e.row_lo = c->k.row_lo; e.srows = c->k.srows; e.halo_rows = c->p.halo_rows; e.ia = c->q.ia; e.ib = c->q.ib;
+    e.ipc_ok = 1;
+    for (int b = 0; b < 4; ++b) {
+        e.buf_ptr[b] = (unsigned long long)(uintptr_t)c->buf[b];
+        if (cudaIpcGetMemHandle(&e.buf_h[b], c->buf[b]) != cudaSuccess) e.ipc_ok = 0;
+    }
+    e.flags_ptr = (unsigned long long)(uintptr_t)c->in_flags;
+    if (cudaIpcGetMemHandle(&e.flags_h, c->in_flags) != cudaSuccess) e.ipc_ok = 0;
+    cudaGetLastError();                    // without IPC support the endpoint still serves bands of the same process
+    memcpy(blob, &e, sizeof(e));
+    return OC_OK;
+}
+
+static void unlink_band(oc_cloth* c)
+{
+    for (int sd = 0; sd < 2; ++sd)
+        for (int b = 0; b < 5; ++b)
+            if (c->link.opened[sd][b]) { cudaIpcCloseMemHandle(c->link.opened[sd][b]); c->link.opened[sd][b] = nullptr; }
+    memset(&c->link, 0, sizeof(c->link));
+    c->q.linked = false;
+    chain_break(c);
+}
+
+extern "C" int oc_band_unlink(oc_cloth* c)
+{
+    if (!c) return oc_fail(OC_ERR_INVALID, "oc_band_unlink: null");
+    OC_CUDA(cudaSetDevice(c->dev));
+    OC_CUDA(cudaStreamSynchronize(c->stream));
+    unlink_band(c);
+    if (c->q.band) c->q.fresh = c->q.kmax;          // halo rows are stale until an exchange
+    return OC_OK;
+}
+
+extern "C" int oc_band_link(oc_cloth* c, const void* up_blob, const void* down_blob)
+{
+    if (!c) return oc_fail(OC_ERR_INVALID, "oc_band_link: null");
+    if (!c->q.band) return oc_fail(OC_ERR_INVALID, "oc_band_link: the handle owns the whole cloth");
+    if (c->p.halo_rows < 2 || c->rows_own < 4) return oc_fail(OC_ERR_UNSUPPORTED, "oc_band_link: needs halo_rows >= 2 and at least 4 owned rows");
+    if (oc_march2_nstrips(c->p.nx) > OC_LINK_STRIPS) return oc_fail(OC_ERR_UNSUPPORTED, "oc_band_link: cloth too wide (%d strips)", oc_march2_nstrips(c->p.nx));
+    const bool need[2] = { c->p.row_begin > 0, c->p.row_end < c->p.ny };
+    const void* blobs[2] = { up_blob, down_blob };
+    OC_CUDA(cudaSetDevice(c->dev));
+    OC_CUDA(cudaStreamSynchronize(c->stream));
+    unlink_band(c);
+    for (int sd = 0; sd < 2; ++sd) {
+        if (!need[sd]) continue;
+        if (!blobs[sd]) return oc_fail(OC_ERR_INVALID, "oc_band_link: rows [%d,%d) of %d have a neighbour %s but no endpoint was given",
+                                       c->p.row_begin, c->p.row_end, c->p.ny, sd ? "below" : "above");
+        OcEndpoint e;
+        memcpy(&e, blobs[sd], sizeof(e));
+        if (e.magic != OC_ENDPOINT_MAGIC || e.abi != OC_ABI_VERSION) { unlink_band(c); return oc_fail(OC_ERR_INVALID, "oc_band_link: not an endpoint of this library version"); }
+        const bool adjacent = sd == 0 ? e.row_end == c->p.row_begin : e.row_begin == c->p.row_end;
+        if (e.nx != c->p.nx || e.ny != c->p.ny || !adjacent || e.halo_rows < 2 || e.row_end - e.row_begin < 4) {
+            unlink_band(c);
+            return oc_fail(OC_ERR_INVALID, "oc_band_link: endpoint rows [%d,%d) of a %d x %d cloth are not the %s neighbour of rows [%d,%d) of a %d x %d cloth",
+                           e.row_begin, e.row_end, e.nx, e.ny, sd ? "lower" : "upper", c->p.row_begin, c->p.row_end, c->p.nx, c->p.ny);
+        }
+        if (e.ia != c->q.ia || e.ib != c->q.ib) {
+            unlink_band(c);
+            return oc_fail(OC_ERR_INVALID, "oc_band_link: the bands have taken different numbers of steps (buffer rotation %d/%d vs %d/%d)", e.ia, e.ib, c->q.ia, c->q.ib);
+        }
+        void* ptr[5];
+        if (e.pid == (long long)getpid()) {
+            for (int b = 0; b < 4; ++b) ptr[b] = (void*)(uintptr_t)e.buf_ptr[b];
+            ptr[4] = (void*)(uintptr_t)e.flags_ptr;
+            if (e.dev != c->dev) {
+                int can = 0;
+                if (cudaDeviceCanAccessPeer(&can, c->dev, e.dev) != cudaSuccess || !can) {
+                    unlink_band(c);
+                    return oc_fail(OC_ERR_UNSUPPORTED, "oc_band_link: device %d cannot access device %d's memory", c->dev, e.dev);
+                }
+                const cudaError_t pe = cudaDeviceEnablePeerAccess(e.dev, 0);
+                if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) { unlink_band(c); OC_CUDA(pe); }
+                cudaGetLastError();
+            }
+        } else {
+            if (!e.ipc_ok) { unlink_band(c); return oc_fail(OC_ERR_UNSUPPORTED, "oc_band_link: the neighbour could not export CUDA IPC handles"); }
+            for (int b = 0; b < 5; ++b) {
+                const cudaError_t oe = cudaIpcOpenMemHandle(&ptr[b], b < 4 ? e.buf_h[b] : e.flags_h, cudaIpcMemLazyEnablePeerAccess);
+                if (oe != cudaSuccess) { unlink_band(c); OC_CUDA(oe); }
+                c->link.opened[sd][b] = ptr[b];
+            }
+        }
+        for (int b = 0; b < 4; ++b) c->link.buf[sd][b] = (float4*)ptr[b];
+        // the neighbour's words for ITS side that faces me: I am the lower neighbour (side 1) of my upper neighbour
+        c->link.flags_out[sd] = (unsigned*)ptr[4] + (1 - sd) * OC_LINK_STRIPS;
+        c->link.row_lo[sd] = e.row_lo; c->link.row_begin[sd] = e.row_begin; c->link.row_end[sd] = e.row_end;
+        c->link.has[sd] = true;
+    }
+    OC_CUDA(cudaMemsetAsync(c->in_flags, 0, 2 * OC_LINK_STRIPS * sizeof(unsigned), c->stream));
+    OC_CUDA(cudaStreamSynchronize(c->stream));
+    c->link.epoch = 0;
+    c->link.on = true;
+    c->q.linked = true;
+    return OC_OK;
+}
+
+extern "C" int oc_band_pull_halo(oc_cloth* c)
+{
+    if (!c) return oc_fail(OC_ERR_INVALID, "oc_band_pull_halo: null");
+    if (!c->link.on) return oc_fail(OC_ERR_INVALID, "oc_band_pull_halo: the band is not linked");
+    OC_CUDA(cudaSetDevice(c->dev));
+    chain_break(c);
+    const long long U = c->p.nx;
+    for (int sd = 0; sd < 2; ++sd) {
+        if (!c->link.has[sd]) continue;
+        const int r0 = sd == 0 ? c->p.row_begin - 2 : c->p.row_end;         // the two rows next to my band, owned by the neighbour
+        for (int which = 0; which < 2; ++which) {
+            const int b = which == 0 ? c->q.ia : c->q.ib;
+            const float4* src = c->link.buf[sd][b] + (long long)(r0 - c->link.row_lo[sd]) * U;
+            float4* dst = c->buf[b] + (long long)(r0 - c->k.row_lo) * U;
+            OC_CUDA(cudaMemcpyAsync(dst, src, (size_t)2 * U * sizeof(float4), cudaMemcpyDefault, c->stream));
+        }
+    }
+    return OC_OK;
+}
+
+extern "C" int oc_band_link_local(oc_cloth* const* bands, int n)
+{
+    if (!bands || n < 1) return oc_fail(OC_ERR_INVALID, "oc_band_link_local: no bands");
+    std::vector<std::vector<unsigned char>> ep((size_t)n, std::vector<unsigned char>(OC_BAND_ENDPOINT_BYTES));
+    for (int b = 0; b < n; ++b) {
+        if (!bands[b]) return oc_fail(OC_ERR_INVALID, "oc_band_link_local: null band");
+        int rc = oc_sync(bands[b]);                                         // every band's state is final ...
+        if (rc == 0) rc = oc_band_endpoint(bands[b], ep[b].data(), ep[b].size());
+        if (rc) return rc;
+    }
+    for (int b = 0; b < n; ++b) {
+        const int rc = oc_band_link(bands[b], b > 0 ? ep[b - 1].data() : nullptr, b + 1 < n ? ep[b + 1].data() : nullptr);
+        if (rc) return rc;
+    }
+    for (int b = 0; b < n; ++b) { const int rc = oc_band_pull_halo(bands[b]); if (rc) return rc; }
+    for (int b = 0; b < n; ++b) { const int rc = oc_sync(bands[b]); if (rc) return rc; }      // ... and every halo current before anyone steps
     return OC_OK;
 }
 

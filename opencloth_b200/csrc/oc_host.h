@@ -154,6 +154,7 @@ struct OcSeq {
     int row_begin, row_end;   // rows owned
     int V;
     bool band;                // owns a strict sub-range of the rows
+    bool linked;              // band whose halo rows are kept current by its neighbours (peer stores every substep): no shrink
     int kmax;                 // band: substeps between halo exchanges (halo_rows / 2)
     // running
     int fresh;                // band: substeps taken since the halo rows were last current
@@ -175,7 +176,7 @@ static inline void oc_host_geometry(oc_params& p, OcConst& k, OcSeq& q)
     k.U = U; k.V = V; k.row_lo = lo; k.srows = hi - lo; k.batch = p.batch;
     k.cloth_stride = (long long)k.srows * U;
     q.row_begin = rb; q.row_end = re; q.V = V;
-    q.kmax = halo / 2; q.fresh = 0; q.ia = 0; q.ib = 1;
+    q.kmax = halo / 2; q.fresh = 0; q.ia = 0; q.ib = 1; q.linked = false;
 }
 
 // Stage counts (substeps per launch) the marching kernel is compiled for: 1, 2, 4, 8.
@@ -204,7 +205,7 @@ static inline void oc_host_next_launch(OcSeq& q, int& n, int k, OcLaunch& L)
     int S = n < k ? n : k;
     L.S = S;
     L.ra = q.row_begin; L.rb = q.row_end;
-    if (q.band) {
+    if (q.band && !q.linked) {
         int grow = 2 * (q.kmax - q.fresh - S);
         L.ra -= grow; L.rb += grow;
         if (L.ra < 0) L.ra = 0;
@@ -215,7 +216,7 @@ static inline void oc_host_next_launch(OcSeq& q, int& n, int k, OcLaunch& L)
     L.src_a = q.ia; L.src_b = q.ib; L.dst = f[0]; L.dst_prev = f[1];
     if (S == 1) { q.ib = q.ia; q.ia = L.dst; }
     else        { q.ia = L.dst; q.ib = L.dst_prev; }
-    if (q.band) q.fresh += S;
+    if (q.band && !q.linked) q.fresh += S;
     n -= S;
 }
 

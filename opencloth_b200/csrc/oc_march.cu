@@ -165,7 +165,23 @@ int oc_march2_configure(int device)
     return 0;
 }
 
-int oc_march2_plan(const OcConst& c, bool exact, bool chained, int ra, int rb, int sm_count, int occ_hint, OcMarchPlan* pl, OcSeg2* seg)
+int oc_march2_nstrips(int nx)
+{
+    const int WC = pick_wc(nx);
+    const int W_out = WC - 2 * ((nx <= WC) ? 0 : 2);
+    return (nx + W_out - 1) / W_out;
+}
+
+// Linked row bands: the first and the last segment of a strip hold (at least) the two rows pushed to the neighbour,
+// so that exactly one tile per strip produces, and reads, each halo (OcPeer2).  Segments are uniform with the
+// remainder in the last one: grow rs until that remainder is at least 2 rows.
+static int fix_last_segment(int rows, int rs)
+{
+    while (rs < rows && (rows - 1) % rs + 1 < 2) ++rs;
+    return rs;
+}
+
+int oc_march2_plan(const OcConst& c, bool exact, bool chained, bool linked, int ra, int rb, int sm_count, int occ_hint, OcMarchPlan* pl, OcSeg2* seg)
 {
     const int U = c.U;
     const int WC = pick_wc(U);
@@ -198,6 +214,7 @@ int oc_march2_plan(const OcConst& c, bool exact, bool chained, int ra, int rb, i
         const int rs = (rows + nseg - 1) / nseg;
         if (nseg >= 1 && rs >= 32) { best_rs = rs; oversub = true; }
     }
+    if (linked) best_rs = fix_last_segment(rows, best_rs);
     pl->TW = WC; pl->S = 1; pl->x_halo = x_halo; pl->W_out = W_out; pl->nstrips = nstrips;
     pl->RS = best_rs; pl->nseg = (rows + best_rs - 1) / best_rs; pl->threads = WC / 2; pl->smem = smem2(WC);
     seg->rs = seg->rs_e = best_rs; seg->nstrips = nstrips; seg->nseg_all = pl->nseg; seg->n_extra = 0;
@@ -206,7 +223,7 @@ int oc_march2_plan(const OcConst& c, bool exact, bool chained, int ra, int rb, i
     const char* ee = getenv("OC_MARCH2_EDGE");
     const int edge = ee ? atoi(ee) : (exact ? OC_MARCH2_EDGE_EXACT : OC_MARCH2_EDGE_FAST);
     const long long tiles = (long long)nstrips * pl->nseg;
-    if (!oversub && !(env && atoi(env) > 0) && edge > 0 && c.batch == 1 && nstrips >= 3 && tiles <= slots) {
+    if (!linked && !oversub && !(env && atoi(env) > 0) && edge > 0 && c.batch == 1 && nstrips >= 3 && tiles <= slots) {
         for (int e = edge; e >= 4; e -= 2) {                          // the largest ratio whose extra edge tiles fit the same wave
             OcSeg2 g = *seg;
             g.rs_e = (int)((100.0 * g.rs) / (100.0 + e) + 0.5);
@@ -220,7 +237,8 @@ int oc_march2_plan(const OcConst& c, bool exact, bool chained, int ra, int rb, i
 }
 
 cudaError_t oc_march2_launch(const OcConst& c, bool exact, int ra, int rb, int sm_count,
-                             const float4* A, const float4* B, float4* C, cudaStream_t stream, int* n_launches, OcChain2* chain)
+                             const float4* A, const float4* B, float4* C, cudaStream_t stream, int* n_launches, OcChain2* chain,
+                             const OcPeer2* peer)
 {
     *n_launches = 0;
     OcMarchPlan pl;
@@ -229,7 +247,7 @@ cudaError_t oc_march2_launch(const OcConst& c, bool exact, int ra, int rb, int s
     static const bool pdl = !(getenv("OC_PDL") && atoi(getenv("OC_PDL")) == 0);
     static const bool tile_deps = !(getenv("OC_TILE_DEPS") && atoi(getenv("OC_TILE_DEPS")) == 0);
     const bool chained = pdl && tile_deps && chain && chain->flags;
-    if (oc_march2_plan(c, exact, chained, ra, rb, sm_count, g_occ2[exact ? 1 : 0][WC == 128], &pl, &seg) != 0) return cudaErrorInvalidValue;
+    if (oc_march2_plan(c, exact, chained, peer != nullptr, ra, rb, sm_count, g_occ2[exact ? 1 : 0][WC == 128], &pl, &seg) != 0) return cudaErrorInvalidValue;
     const void* fn = exact ? oc_march2_fn_exact(WC) : oc_march2_fn_fast(WC);
     if (!fn) return cudaErrorInvalidDeviceFunction;
     if (c.batch > 65535) return cudaErrorInvalidConfiguration;
@@ -254,6 +272,7 @@ cudaError_t oc_march2_launch(const OcConst& c, bool exact, int ra, int rb, int s
             dep.mode = 1; dep.pra = chain->pra; dep.prb = chain->prb; dep.pseg = chain->pseg;
         }
     }
+    if (peer) { dep.peer = *peer; dep.peer.ra = ra; dep.peer.rb = rb; dep.peer.nstrips = seg.nstrips; }
     void* args[] = { &cc, (void*)&A, (void*)&B, (void*)&C, &ra, &rb, &seg, &xh, &dep };
     // Programmatic dependent launch: consecutive steps are kernel -> kernel edges on one stream; the next launch's CTAs
     // are placed while this one drains and wait (griddepcontrol.wait) before they touch the state.  OC_PDL=0 turns it off.

@@ -35,6 +35,23 @@ struct OcSmem2 {
     float4 stage[4][WC / 2];            // landing zone of the asynchronous row loads: A[a], B[a], A[b], B[b] per thread
 };
 
+// Linked row bands (multi-GPU): the cloth is cut into row bands, one handle per GPU, and the bands are
+// LINKED through peer memory (CUDA IPC across processes, plain peer access inside one).  There is no halo exchange
+// step: the tiles at a band boundary store the two rows the neighbour's stencil reaches (bend springs, reach 2:
+// V:311, V:317) straight into the neighbour's halo rows as they produce them (NVLink stores), and the per-tile
+// dependency flags span the GPUs: after its last store a boundary tile releases one word per strip in the NEIGHBOUR's
+// memory (system scope); the neighbour's boundary tiles of the next step poll their local copy.  Steps on different
+// GPUs are thereby ordered tile by tile, without the host and without a grid-wide or machine-wide barrier.
+struct OcPeer2 {
+    float4*         c[2];          // [0] upper, [1] lower neighbour: its destination buffer of this step, biased so that
+                                   // element row * U + column is that particle's slot; nullptr = cloth edge / not linked
+    unsigned*       flags_out[2];  // words [strip] in the neighbour's memory that this band's boundary tiles release
+    const unsigned* flags_in[2];   // local words [strip] released by the neighbour's boundary tiles
+    unsigned        epoch;         // linked steps taken, this one included (the same number on every band)
+    int             ra, rb;        // rows of this launch (= the band's owned rows)
+    int             nstrips;
+};
+
 // ---- spring pair with a pair-valued first end (particles a and b of the thread) ----------------------
 template <class M>
 OC_HD OcPair3 oc_spring2v(const OcPair3& px, const OcPair3& pv, const OcPair3& qx, const OcPair3& qv,
@@ -175,6 +192,7 @@ struct OcMarch2 {
     OcPair3q me_x, me_v, w1_x, w1_v;         // own columns, rows row and row+1
     OcPair3q k1_q, k2a_q, k2b_q;             // carried (0,+1) of row-1, (0,+2) of row-1 and row-2
     f3 kDa, kAb;                             // carried internal shear forces of row-1: f(a->b'), f(b->a')
+    const OcPeer2* peer;                     // linked row bands (kernel-parameter space; read on the generic path only)
 
     OC_HD OcMarch2(Ctx& ctx_, const OcConst& c_) : ctx(ctx_), c(c_) {}
 
@@ -471,8 +489,22 @@ struct OcMarch2 {
                 }
             }
             const long long o = goff + (long long)row * U;
-            if (sta) C[o]     = make_float4(n.x.x, n.y.x, n.z.x, oc_u2f(hit_a ? OC_W_HIT : OC_W_PLAIN));
-            if (stb) C[o + 1] = make_float4(n.x.y, n.y.y, n.z.y, oc_u2f(hit_b ? OC_W_HIT : OC_W_PLAIN));
+            const float4 out_a = make_float4(n.x.x, n.y.x, n.z.x, oc_u2f(hit_a ? OC_W_HIT : OC_W_PLAIN));
+            const float4 out_b = make_float4(n.x.y, n.y.y, n.z.y, oc_u2f(hit_b ? OC_W_HIT : OC_W_PLAIN));
+            if (sta) C[o]     = out_a;
+            if (stb) C[o + 1] = out_b;
+            if (!kSteady) {
+                // linked row bands: the first / last two rows of the band also go into the neighbour's halo (OcPeer2);
+                // the steady range of a boundary tile excludes them, so the steady loop knows nothing of this
+                float4* pc = nullptr;
+                if (peer->c[0] && row < peer->ra + 2) pc = peer->c[0];
+                if (peer->c[1] && row >= peer->rb - 2) pc = peer->c[1];
+                if (pc) {
+                    const long long po = (long long)row * U + ga;
+                    if (sta) pc[po]     = out_a;
+                    if (stb) pc[po + 1] = out_b;
+                }
+            }
         }
         if (doP) {
             k2b_q = k2a_q; k2a_q = p_pack3(gV2); k1_q = p_pack3(gV1);
@@ -560,6 +592,7 @@ struct OcDep2 {
     int       mode;
     int       pra, prb;       // previous launch: row range and segmentation
     OcSeg2    pseg;
+    OcPeer2   peer;           // linked row bands: the neighbours' halos and flag words (all null otherwise)
 };
 
 // Flag word of the k-th (k = 0..3) segment of strip xs of the PREVIOUS launch that overlaps the rows [r0-2, r1+2) a
@@ -622,6 +655,7 @@ OC_HD void oc_march2_body(Ctx& ctx, const OcConst& c, const float4* __restrict__
     const int n_it = r1 - first + OC_MARCH_LAG;
     const int row0 = first - OC_MARCH_LAG;
     m.lo = lo; m.hi = hi; m.plo = plo; m.in_lo = in_lo; m.in_hi = in_hi; m.first = first; m.row0 = row0;
+    m.peer = &dep.peer;
     m.oka = ga >= 0 && ga < U; m.okb = gb >= 0 && gb < U;
     m.sta = m.oka && 2 * i >= x_halo && 2 * i < WC - x_halo;
     m.stb = m.okb && 2 * i + 1 >= x_halo && 2 * i + 1 < WC - x_halo;
@@ -665,6 +699,9 @@ OC_HD void oc_march2_body(Ctx& ctx, const OcConst& c, const float4* __restrict__
     int st_lo = lo > plo + 1 ? lo : plo + 1; if (st_lo < 2) st_lo = 2;
     int st_hi = hi < V - 3 ? hi : V - 3;
     if (st_hi > in_hi - OC_MARCH_LAG) st_hi = in_hi - OC_MARCH_LAG;
+    // linked row bands: the two rows pushed into a neighbour's halo are taken on the generic path
+    if (dep.peer.c[0] && st_lo < dep.peer.ra + 2) st_lo = dep.peer.ra + 2;
+    if (dep.peer.c[1] && st_hi > dep.peer.rb - 2) st_hi = dep.peer.rb - 2;
     int it_lo = st_lo - row0, it_hi = st_hi - row0;
     if (it_lo < 0) it_lo = 0;
     if (it_hi > n_it) it_hi = n_it;
@@ -704,6 +741,32 @@ OC_HD void oc_march2_body(Ctx& ctx, const OcConst& c, const float4* __restrict__
 #ifdef __CUDACC__
 // four CTAs of WC/2 threads per SM: 230-250 registers per thread (every trade of registers for a fifth CTA lost)
 #define OC_M2_BOUNDS __launch_bounds__(WC / 2, 4)
+// Poll a dependency flag until it reaches `want` (acquire; kSys: the word is written by another GPU).  The polls go to
+// L2, with exponential back-off.  A wait that does not end (2 s for a flag of this GPU, 30 s for a neighbour GPU's:
+// its process may lag) cannot happen in a correct chain of launches: the kernel records why in the handle's error word
+// (host-mapped, read by oc_sync / oc_download / oc_step) and traps instead of computing from stale rows.
+template <bool kSys>
+__device__ __forceinline__ void oc_flag_wait(const OcConst& c, const unsigned* p, unsigned want)
+{
+    unsigned v, ns = 100;
+    unsigned long long t0 = 0;
+    for (;;) {
+        if (kSys) asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+        else      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+        if ((int)(v - want) >= 0) return;
+        __nanosleep(ns);
+        if (ns < 1600) ns += ns;
+        else {
+            unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            if (t0 == 0) t0 = t;
+            const unsigned long long limit = (c.dbg & 32) ? 50000000ull : (kSys ? 30000000000ull : 2000000000ull);
+            if (t - t0 > limit) {
+                if (c.err) { *c.err = kSys ? 2u : 1u; __threadfence_system(); }
+                __trap();
+            }
+        }
+    }
+}
 struct OcDevCtx2 {          // grid = (tiles, 1, batch): the tile -> (strip, segment) map is OcSeg2's
     int x, y;
     __device__ __forceinline__ int tid() const { return threadIdx.x; }
@@ -716,33 +779,40 @@ struct OcDevCtx2 {          // grid = (tiles, 1, batch): the tile -> (strip, seg
     // overlap the previous launch; the state buffers are only touched after it.  See OcDep2.
     __device__ __forceinline__ void wait_deps(const OcDep2& d, const OcConst& c, int r0, int r1) const
     {
-        if (d.mode == 0) { asm volatile("griddepcontrol.wait;" ::: "memory"); return; }
         const int t = threadIdx.x;
-        if (t < 12) {
+        if (d.mode == 0) asm volatile("griddepcontrol.wait;" ::: "memory");
+        else if (t < 12) {
             const int idx = oc_dep2_index(d, x - 1 + t / 4, t % 4, r0, r1);
-            if (idx >= 0) {
-                const unsigned* p = d.flags + (size_t)blockIdx.z * oc_seg2_tiles(d.pseg) + idx;   // same cloth
-                const unsigned want = d.epoch - 1u;
-                unsigned v, spins = 0, ns = 200;
-                for (;;) {
-                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-                    if ((int)(v - want) >= 0) break;
-                    __nanosleep(ns);                                   // back off: the polls go to L2
-                    if (ns < 1600) ns += ns;
-                    if (++spins > (1u << 21)) { atomicAdd(c.dbg_cnt + 2, 1ull << 40); break; }      // > 1 s: never in a correct chain
-                }
-            }
+            if (idx >= 0)
+                oc_flag_wait<false>(c, d.flags + (size_t)blockIdx.z * oc_seg2_tiles(d.pseg) + idx, d.epoch - 1u + ((c.dbg & 32) ? 1000u : 0u));   // same cloth
+        }
+        // linked row bands: a tile that reads halo rows waits for the neighbour's boundary tiles of the previous step in
+        // its own and the two adjacent strips (they wrote those rows, and they were the last readers of the neighbour's
+        // halo rows this tile is about to overwrite)
+        if (t >= 16 && t < 22) {
+            const int side = (t - 16) / 3, xs = x - 1 + (t - 16) % 3;
+            const bool reads_halo = side == 0 ? r0 < d.peer.ra + 2 : r1 > d.peer.rb - 2;
+            if (d.peer.flags_in[side] && reads_halo && xs >= 0 && xs < d.peer.nstrips)
+                oc_flag_wait<true>(c, d.peer.flags_in[side] + xs, d.peer.epoch - 1u);
         }
         __syncthreads();
     }
     // after the tile's last store
-    __device__ __forceinline__ void publish(const OcDep2& d) const
+    __device__ __forceinline__ void publish(const OcDep2& d, int r0, int r1) const
     {
-        if (!d.flags) return;
+        if (!d.flags && !d.peer.flags_out[0] && !d.peer.flags_out[1]) return;
         __syncthreads();
         if (threadIdx.x == 0) {
-            __threadfence();
-            asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(d.flags + (size_t)blockIdx.z * gridDim.x + blockIdx.x), "r"(d.epoch) : "memory");
+            if (d.flags) {
+                __threadfence();
+                asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(d.flags + (size_t)blockIdx.z * gridDim.x + blockIdx.x), "r"(d.epoch) : "memory");
+            }
+            const bool up = d.peer.flags_out[0] && r0 < d.peer.ra + 2 && r1 > r0, dn = d.peer.flags_out[1] && r1 > d.peer.rb - 2 && r1 > r0;
+            if (up | dn) {
+                __threadfence_system();
+                if (up) asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(d.peer.flags_out[0] + x), "r"(d.peer.epoch) : "memory");
+                if (dn) asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(d.peer.flags_out[1] + x), "r"(d.peer.epoch) : "memory");
+            }
         }
     }
 };
@@ -756,13 +826,16 @@ oc_k_march2(const __grid_constant__ OcConst c, const float4* __restrict__ A, con
     OcDevCtx2 ctx;
     oc_seg2_tile(seg, blockIdx.x, ctx.x, ctx.y);
     oc_march2_body<M, WC, OcDevCtx2>(ctx, c, A, B, C, ra, rb, seg, x_halo, dep);
-    ctx.publish(dep);
+    int r0, r1;
+    oc_seg2_rows(seg, ctx.x, ctx.y, ra, rb, r0, r1);
+    ctx.publish(dep, r0, r1);
 }
 #endif
 
 // ---- host side (oc_march.cu) -------------------------------------------------------------------
 int  oc_march2_configure(int device);
-int  oc_march2_plan(const OcConst& c, bool exact, bool chained, int ra, int rb, int sm_count, int occ_hint, OcMarchPlan* plan, OcSeg2* seg);
+int  oc_march2_plan(const OcConst& c, bool exact, bool chained, bool linked, int ra, int rb, int sm_count, int occ_hint, OcMarchPlan* plan, OcSeg2* seg);
+int  oc_march2_nstrips(int nx);
 // host side of OcDep2: the chain of launches of one handle
 struct OcChain2 {
     unsigned* flags; int cap;      // device flag words
@@ -773,5 +846,6 @@ struct OcChain2 {
 };
 #ifdef __CUDACC__
 cudaError_t oc_march2_launch(const OcConst& c, bool exact, int ra, int rb, int sm_count,
-                             const float4* A, const float4* B, float4* C, cudaStream_t stream, int* n_launches, OcChain2* chain);
+                             const float4* A, const float4* B, float4* C, cudaStream_t stream, int* n_launches, OcChain2* chain,
+                             const OcPeer2* peer = nullptr);
 #endif

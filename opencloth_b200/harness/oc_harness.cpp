@@ -11,8 +11,10 @@
 //     glutMainLoop / OnShutdown     ->  --frames iterations, oc_destroy
 //     mouse drag (V:184-210)        ->  --poke idx,x,y,z  (oc_set_particle before the first frame)
 //
-// It can also cut the cloth into row bands over several GPUs of ONE process (--gpus g): every band
-// is a handle on its own device, halos move with oc_halo_exchange (cudaMemcpyPeerAsync).
+// It can also cut the cloth into row bands over several GPUs of ONE process (--gpus g [--devices d]): every band
+// is a handle on device (band % d).  By default the bands are LINKED (oc_band_link_local): the step kernel stores
+// the boundary rows into the neighbour's halo itself (peer memory) and no exchange step exists; --link 0 keeps the
+// older host-driven exchange (oc_halo_exchange, cudaMemcpyPeerAsync every halo_rows/2 substeps).
 // No oracle, no CPU path: without a CUDA device it prints the library's error and exits 2.
 #include "../../include/opencloth.h"
 
@@ -32,7 +34,7 @@ static void die(const char* what)
 
 int main(int argc, char** argv)
 {
-    int nx = 21, ny = 21, frames = 10, substeps = 100, k = 1, exact = 1, gpus = 1, batch = 1, halo = 16, energy = 1;
+    int nx = 21, ny = 21, frames = 10, substeps = 100, k = 1, exact = 1, gpus = 1, batch = 1, halo = 16, energy = 1, link = 1, devices = 0;
     int poke_idx = -1; float poke[3] = { 0, 0, 0 };
     std::string dump;
     for (int a = 1; a < argc; ++a) {
@@ -46,12 +48,14 @@ int main(int argc, char** argv)
         else if (is("--gpus")) gpus = atoi(argv[++a]);
         else if (is("--batch")) batch = atoi(argv[++a]);
         else if (is("--halo")) halo = atoi(argv[++a]);
+        else if (is("--link")) link = atoi(argv[++a]);
+        else if (is("--devices")) devices = atoi(argv[++a]);
         else if (is("--energy")) energy = atoi(argv[++a]);
         else if (is("--dump")) dump = argv[++a];
         else if (is("--poke")) { if (sscanf(argv[++a], "%d,%f,%f,%f", &poke_idx, &poke[0], &poke[1], &poke[2]) != 4) { fprintf(stderr, "--poke idx,x,y,z\n"); return 1; } }
         else {
-            fprintf(stderr, "usage: oc_harness [--nx N --ny N] [--frames F] [--substeps S] [--k K] [--exact 0|1] [--gpus G] [--batch B]\n"
-                            "                  [--halo ROWS] [--energy 0|1] [--poke idx,x,y,z] [--dump file.f32]\n");
+            fprintf(stderr, "usage: oc_harness [--nx N --ny N] [--frames F] [--substeps S] [--k K] [--exact 0|1] [--gpus G [--devices D] [--link 0|1]]\n"
+                            "                  [--batch B] [--halo ROWS] [--energy 0|1] [--poke idx,x,y,z] [--dump file.f32]\n");
             return 1;
         }
     }
@@ -62,10 +66,16 @@ int main(int argc, char** argv)
         oc_params p;
         CK(oc_default_params(&p, nx, ny));
         p.batch = batch; p.substeps_per_launch = k; p.exact = exact;
-        if (gpus > 1) { p.row_begin = (int)((long long)ny * g / gpus); p.row_end = (int)((long long)ny * (g + 1) / gpus); p.halo_rows = halo; p.device = g; }
+        if (gpus > 1) {
+            p.row_begin = (int)((long long)ny * g / gpus); p.row_end = (int)((long long)ny * (g + 1) / gpus);
+            p.halo_rows = link ? 2 : halo; p.device = g % (devices > 0 ? devices : gpus);
+            if (link) { p.substeps_per_launch = 1; p.kernel = OC_KERNEL_AUTO; }
+        }
         CK(oc_create(&bands[g], &p));
     }
     if (poke_idx >= 0) for (auto* b : bands) CK(oc_set_particle(b, 0, poke_idx, poke));      // V:203-208
+    const bool linked = gpus > 1 && link;
+    if (linked) CK(oc_band_link_local(bands.data(), gpus));
 
     const double particles = (double)nx * ny * batch;
     int step = 0;
@@ -74,7 +84,8 @@ int main(int argc, char** argv)
         int left = substeps;
         while (left > 0) {
             int n = left;
-            if (gpus > 1) {
+            if (linked) n = 1;          // interleave the bands' launches: each band's edge tiles wait for the neighbours' previous step
+            else if (gpus > 1) {
                 if (oc_halo_budget(bands[0]) == 0) CK(oc_halo_exchange(bands.data(), gpus));
                 n = oc_halo_budget(bands[0]) < left ? oc_halo_budget(bands[0]) : left;
             }

@@ -151,6 +151,8 @@ struct EmuCloth {
     long long stored;
     int rows_own;
     long long barrier_errors;
+    EmuCloth* nb[2];            // linked row bands: upper / lower neighbour (same process, host memory)
+    unsigned link_epoch;
 };
 
 template <class M, int S, int TW>
@@ -209,6 +211,15 @@ static int emu_march2(EmuCloth* e, const OcLaunch& L, int RS)
     const float4* A = e->buf[L.src_a].data();
     const float4* B = e->buf[L.src_b].data();
     float4* C = e->buf[L.dst].data();
+    // linked row bands: the same OcPeer2 the library passes (peer stores into the neighbours' halo rows); the flag
+    // words stay null, the emulator runs bands and tiles one after the other
+    OcDep2 dep = OcDep2();
+    if (e->q.linked) {
+        for (int sd = 0; sd < 2; ++sd)
+            if (e->nb[sd]) dep.peer.c[sd] = e->nb[sd]->buf[L.dst].data() - (long long)e->nb[sd]->k.row_lo * k.U;
+        dep.peer.epoch = ++e->link_epoch; dep.peer.ra = L.ra; dep.peer.rb = L.rb; dep.peer.nstrips = nstrips;
+        if ((rows - 1) % seg.rs + 1 < 2) return -4;          // the library's planner never produces this (fix_last_segment)
+    }
     int rc = 0;
     for (int bz = 0; bz < k.batch; ++bz)
         for (int t = 0; t < oc_seg2_tiles(seg); ++t) {
@@ -216,7 +227,7 @@ static int emu_march2(EmuCloth* e, const OcLaunch& L, int RS)
             oc_seg2_tile(seg, t, bx, by);
             int ra = L.ra, rb = L.rb;
             rc |= run_cta(WC / 2, bx, by, bz, sizeof(OcSmem2<WC>), [&](EmuCtx& ctx) {
-                oc_march2_body<M, WC, EmuCtx>(ctx, k, A, B, C, ra, rb, seg, x_halo, OcDep2());
+                oc_march2_body<M, WC, EmuCtx>(ctx, k, A, B, C, ra, rb, seg, x_halo, dep);
             });
         }
     return rc;
@@ -287,6 +298,7 @@ void* emu_create(const oc_params* p)
         e->buf[0][t] = e->buf[1][t] = e->buf[2][t] = e->buf[3][t] = v;
     }
     e->barrier_errors = 0;
+    e->nb[0] = e->nb[1] = nullptr; e->link_epoch = 0;
     return e;
 }
 void emu_destroy(void* h) { delete (EmuCloth*)h; }
@@ -340,7 +352,8 @@ int emu_download(void* h, float* X, float* XL)
 int emu_step(void* h, int n, int kernel, int exact, int k, int TW, int RS)
 {
     EmuCloth* e = (EmuCloth*)h;
-    if (e->q.band && e->q.fresh + n > e->q.kmax) return -3;
+    if (e->q.band && !e->q.linked && e->q.fresh + n > e->q.kmax) return -3;
+    if (e->q.linked && kernel != 3) return -2;
     int rc = 0;
     while (n > 0) {
         OcLaunch L;
@@ -381,6 +394,35 @@ int emu_halo_copy(void* hsrc, int side, void* hdst)
         const float4* src = s->buf[which == 0 ? s->q.ia : s->q.ib].data() + (long long)(r0s - s->k.row_lo) * U;
         float4* dst = d->buf[which == 0 ? d->q.ia : d->q.ib].data() + (long long)(r0d - d->k.row_lo) * U;
         memcpy(dst, src, (size_t)ns * U * sizeof(float4));
+    }
+    return 0;
+}
+// Linked row bands (oc_band_link_local): h[0..n) are the bands of one cloth in row order.  Pulls the halos once; from
+// then on every emu_step(band, 1, kernel 3, ...) pushes its boundary rows into the neighbours (step all bands in turn).
+int emu_band_link(void** h, int n)
+{
+    for (int b = 0; b < n; ++b) {
+        EmuCloth* e = (EmuCloth*)h[b];
+        if (!e->q.band || e->p.halo_rows < 2 || e->rows_own < 4) return -1;
+        e->nb[0] = b > 0 ? (EmuCloth*)h[b - 1] : nullptr;
+        e->nb[1] = b + 1 < n ? (EmuCloth*)h[b + 1] : nullptr;
+        if ((e->p.row_begin > 0) != (e->nb[0] != nullptr) || (e->p.row_end < e->p.ny) != (e->nb[1] != nullptr)) return -1;
+        if (e->nb[0] && e->nb[0]->p.row_end != e->p.row_begin) return -1;
+        e->q.linked = true; e->link_epoch = 0;
+    }
+    for (int b = 0; b < n; ++b) {
+        EmuCloth* e = (EmuCloth*)h[b];
+        const long long U = e->k.U;
+        for (int sd = 0; sd < 2; ++sd) {
+            EmuCloth* o = e->nb[sd];
+            if (!o) continue;
+            const int r0 = sd == 0 ? e->p.row_begin - 2 : e->p.row_end;
+            for (int which = 0; which < 2; ++which) {
+                const int bi = which == 0 ? e->q.ia : e->q.ib;
+                if (o->q.ia != e->q.ia || o->q.ib != e->q.ib) return -2;
+                memcpy(e->buf[bi].data() + (long long)(r0 - e->k.row_lo) * U, o->buf[bi].data() + (long long)(r0 - o->k.row_lo) * U, (size_t)2 * U * sizeof(float4));
+            }
+        }
     }
     return 0;
 }

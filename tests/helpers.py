@@ -258,6 +258,7 @@ def emu_lib():
         L.emu_halo_region.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                       ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_size_t)]
         L.emu_set_order.argtypes = [ctypes.c_int]
+        L.emu_band_link.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int]
         L.emu_bounding_sphere.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         L.emu_check_tiling.argtypes = [ctypes.c_int] * 10
         _emu = L
@@ -290,7 +291,7 @@ class Emu:
 
     def step(self, n, kernel=2, exact=1, k=1, TW=32, RS=0):
         rc = self.L.emu_step(self.h, n, kernel, exact, k, TW, RS)
-        assert rc == 0, f"emu_step rc={rc} (-1 barrier mismatch, -2 unsupported variant, -3 halo exhausted)"
+        assert rc == 0, f"emu_step rc={rc} (-1 barrier mismatch, -2 unsupported variant, -3 halo exhausted, -4 last segment under 2 rows)"
 
     def upload(self, x, xl):
         self.L.emu_upload(self.h, vp(np.ascontiguousarray(x, np.float32)), vp(np.ascontiguousarray(xl, np.float32)))
@@ -328,6 +329,13 @@ class Emu:
             self.close()
         except Exception:
             pass
+
+
+def emu_link_bands(bands):
+    """oc_band_link_local for emulated bands (rows in order)."""
+    arr = (ctypes.c_void_p * len(bands))(*[b.h for b in bands])
+    rc = emu_lib().emu_band_link(arr, len(bands))
+    assert rc == 0, f"emu_band_link rc={rc}"
 
 
 def developed_state(nx, ny, steps):

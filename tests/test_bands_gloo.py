@@ -7,6 +7,7 @@ import ctypes
 import os
 import socket
 import sys
+import time
 
 import numpy as np
 import pytest
@@ -98,6 +99,80 @@ def test_multiprocess_row_bands_equal_whole_cloth(world, halo, k, steps):
     assert helpers.bitwise_equal(ret["xl"], oxl)
     per = halo // 2
     assert ret["exchanges"] >= -(-sum(steps) // per)      # at least one exchange per halo_rows/2 substeps
+
+
+class _FakeLinkedCloth:
+    """Records the calls LinkedBandDriver makes (the link protocol of include/opencloth.h) into a shared log."""
+
+    def __init__(self, rank, log):
+        self.rank, self.log = rank, log
+
+    def _rec(self, what):
+        self.log.append((time.monotonic(), self.rank, what))
+
+    def sync(self):
+        self._rec("sync")
+
+    def band_endpoint(self):
+        self._rec("endpoint")
+        return b"endpoint-of-%d" % self.rank
+
+    def band_link(self, upper, lower):
+        self._rec("link")
+        self.linked = (upper, lower)
+
+    def band_pull_halo(self):
+        self._rec("pull")
+
+    def step(self, n):
+        self._rec("step%d" % n)
+
+
+class _FakeBand:
+    def __init__(self, cloth):
+        self.cloth = cloth
+
+
+def _linked_worker(rank, world, port, log, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from opencloth_b200.bands import LinkedBandDriver
+        c = _FakeLinkedCloth(rank, log)
+        time.sleep(0.05 * rank)                   # skew the ranks: the barriers must still separate the phases
+        drv = LinkedBandDriver(_FakeBand(c), rank, world)
+        drv.link()
+        drv.step(5)
+        drv.resync()
+        drv.step(2)
+        ret[rank] = c.linked
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_linked_band_driver_protocol_over_gloo(world):
+    """Host side of the linked-band path (the one bench.py runs under torchrun): every rank receives exactly its
+    neighbours' endpoints; nobody links before every band has synchronised, nobody steps before every band has pulled
+    its halos, and a resync pulls only after every band has stopped stepping."""
+    mgr = mp.Manager()
+    log, ret = mgr.list(), mgr.dict()
+    mp.spawn(_linked_worker, args=(world, _free_port(), log, ret), nprocs=world, join=True)
+    for r in range(world):
+        up, lo = ret[r]
+        assert up == (b"endpoint-of-%d" % (r - 1) if r > 0 else None)
+        assert lo == (b"endpoint-of-%d" % (r + 1) if r + 1 < world else None)
+    ev = sorted(log)
+    def times(what):
+        return [t for t, _, w in ev if w == what]
+    assert len(times("link")) == world and len(times("pull")) == 2 * world
+    assert max(times("endpoint")) <= min(times("link"))                  # all_gather of the endpoints is the barrier
+    first_pulls = sorted(times("pull"))[:world]
+    assert max(first_pulls) <= min(times("step5"))                       # halos current everywhere before the first step
+    second_pulls = sorted(times("pull"))[world:]
+    assert max(times("step5")) <= min(second_pulls)                      # resync: everybody stopped stepping first
+    assert max(second_pulls) <= min(times("step2"))
 
 
 def test_band_rows_partition():

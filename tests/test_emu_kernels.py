@@ -206,6 +206,34 @@ def test_row_bands_with_halo_exchange_equal_single_domain(nbands, halo, k, kerne
         assert bitwise_equal(x, wx[sl]) and bitwise_equal(xl, wxl[sl]), f"band {b}"
 
 
+@pytest.mark.parametrize("nbands,WC,RS,nx", [(2, 16, 7, 23), (3, 16, 6, 37), (4, 32, 12, 23), (3, 16, 0, 30)])
+def test_linked_row_bands_push_their_boundary_rows(nbands, WC, RS, nx):
+    """Linked row bands (OcPeer2): no exchange step — every band computes exactly its owned rows, and the tiles at a
+    band edge store the two rows the neighbour's stencil reaches straight into the neighbour's halo.  Same kernel
+    body as the GPU; must equal the undivided cloth bit for bit, through collider contact."""
+    ny = 48
+    x0, xl0 = helpers.developed_state(nx, ny, 1600)
+    whole = Oracle(nx, ny); whole.set_state(x0, xl0)
+    cuts = [round(ny * b / nbands) for b in range(nbands + 1)]
+    bands = []
+    for b in range(nbands):
+        e = Emu(nx, ny, row_begin=cuts[b], row_end=cuts[b + 1], halo_rows=2)
+        sl = slice(cuts[b] * nx, cuts[b + 1] * nx)
+        e.upload(x0[sl], xl0[sl])
+        bands.append(e)
+    helpers.emu_link_bands(bands)
+    steps = 9
+    for s in range(steps):
+        for e in (bands if s % 2 == 0 else bands[::-1]):       # the order of the bands within a step does not matter
+            e.step(1, kernel=MARCH2, TW=WC, RS=RS)
+    whole.step(steps)
+    wx, wxl = whole.state()
+    for b, e in enumerate(bands):
+        x, xl = e.download()
+        sl = slice(cuts[b] * nx, cuts[b + 1] * nx)
+        assert bitwise_equal(x, wx[sl]) and bitwise_equal(xl, wxl[sl]), f"band {b}"
+
+
 def test_band_refuses_to_step_past_its_halo():
     e = Emu(21, 40, row_begin=10, row_end=30, halo_rows=4)
     assert e.halo_budget == 2

@@ -40,10 +40,12 @@ def test_harness_row_bands_in_one_process(tmp_path):
     g = min(4, max(1, torch.cuda.device_count()))
     d1, d2 = str(tmp_path / "a.f32"), str(tmp_path / "b.f32")
     _run("--nx", "300", "--ny", "256", "--frames", "2", "--substeps", "40", "--energy", "0", "--dump", d1)
-    if g > 1:
-        _run("--nx", "300", "--ny", "256", "--frames", "2", "--substeps", "40", "--gpus", str(g), "--halo", "8", "--energy", "0", "--dump", d2)
+    # four bands spread over the devices that exist (all on one device on a 1-GPU box): linked bands, then the
+    # host-driven exchange
+    for extra in (("--link", "1"), ("--link", "0", "--halo", "8")):
+        _run("--nx", "300", "--ny", "256", "--frames", "2", "--substeps", "40", "--gpus", "4", "--devices", str(g), *extra, "--energy", "0", "--dump", d2)
         a, b = np.fromfile(d1, np.uint32), np.fromfile(d2, np.uint32)
-        assert a.shape == b.shape and (a == b).all()
+        assert a.shape == b.shape and (a == b).all(), extra
     x = np.fromfile(d1, np.float32).reshape(-1, 4)
     o = helpers.Oracle(300, 256); o.step(80)
     assert helpers.bitwise_equal(x[:, :3], o.state()[0]) and (x[:, 3] == 1.0).all()

@@ -128,7 +128,7 @@ def test_resident_kernel_small_cloths():
             ex, exl = (px, pxl) if b == batch - 1 else (ox, oxl)
             assert bitwise_equal(x[b * n1:(b + 1) * n1], ex) and bitwise_equal(xl[b * n1:(b + 1) * n1], exl), f"{nx}x{ny} cloth {b}"
         c.close()
-    big = m.Cloth(100, 61, kernel=m.OC_KERNEL_RESIDENT)      # 6100 particles do not fit: served by the gather kernel
+    big = m.Cloth(100, 61, kernel=m.OC_KERNEL_RESIDENT)      # 6100 particles do not fit one CTA's shared memory: served by oc_k_march2
     big.step(3)
     o = Oracle(100, 61); o.step(3)
     assert bitwise_equal(big.download()[0], o.state()[0])
@@ -397,6 +397,94 @@ def test_row_bands_chained_full_size(nx, ny, nbands, halo):
         assert (out[2] >> 40) == 0, "a tile-dependency wait timed out"
         c.close()
     whole.close()
+
+
+@pytest.mark.parametrize("nx,ny,nbands,steps", [(512, 384, 3, 60), (200, 64, 4, 40), (2304, 2048, 2, 120), (1100, 1536, 4, 90)])
+def test_linked_row_bands_equal_whole_cloth(nx, ny, nbands, steps):
+    """Linked row bands (the multi-GPU path: in-kernel peer stores of the boundary rows + flag words between the
+    bands' tiles, no exchange step), here with all bands on ONE device in one process — the same kernel path and the
+    same protocol as across GPUs, only the peer pointers are local.  Bitwise equal to the undivided cloth stepped by
+    the independent gather kernel, from a developed state through an upload and a resynchronisation."""
+    m = oc()
+    whole = m.Cloth(nx, ny, kernel=m.OC_KERNEL_GATHER)
+    whole.step(40)
+    wx, wxl = whole.download()
+    cuts = [round(ny * b / nbands) for b in range(nbands + 1)]
+    bands = []
+    for b in range(nbands):
+        c = m.Cloth(nx, ny, row_begin=cuts[b], row_end=cuts[b + 1], halo_rows=2)
+        sl = slice(cuts[b] * nx, cuts[b + 1] * nx)
+        c.upload(wx[sl], wxl[sl])
+        bands.append(c)
+    m.link_bands_local(bands)
+    n0 = bands[0].launch_count
+    for s in range(steps):
+        for c in (bands if s % 2 == 0 else bands[::-1]):
+            c.step(1)
+    assert bands[0].launch_count - n0 == steps          # one launch per substep, nothing else on the step path
+    whole.step(steps)
+    wx, wxl = whole.download()
+    for b, c in enumerate(bands):
+        x, xl = c.download()
+        sl = slice(cuts[b] * nx, cuts[b + 1] * nx)
+        assert bitwise_equal(x, wx[sl]) and bitwise_equal(xl, wxl[sl]), f"band {b}: {nbad(x, wx[sl])} particles differ"
+    # interaction on linked bands: oc_set_particle on every band (each updates the copies it stores), then step on
+    idx = cuts[1] * nx + nx // 2                          # first row of band 1: also a halo row of band 0
+    for c in bands:
+        c.set_particle(idx, (0.3, 4.2, 1.1))
+    whole.set_particle(idx, (0.3, 4.2, 1.1))
+    for s in range(7):
+        for c in bands:
+            c.step(1)
+    whole.step(7)
+    wx, wxl = whole.download()
+    for b, c in enumerate(bands):
+        x, xl = c.download()
+        sl = slice(cuts[b] * nx, cuts[b + 1] * nx)
+        assert bitwise_equal(x, wx[sl]) and bitwise_equal(xl, wxl[sl]), f"after set_particle, band {b}: {nbad(x, wx[sl])} particles differ"
+        c.close()
+    whole.close()
+
+
+def test_linked_band_validation():
+    m = oc()
+    a = m.Cloth(64, 64, row_begin=0, row_end=32, halo_rows=2)
+    b = m.Cloth(64, 64, row_begin=32, row_end=64, halo_rows=2)
+    w = m.Cloth(64, 64)
+    with pytest.raises(m.OpenClothError):
+        w.band_endpoint()                                # a whole cloth has no neighbours
+    ea, eb = a.band_endpoint(), b.band_endpoint()
+    with pytest.raises(m.OpenClothError):
+        a.band_link(None, None)                          # rows [0,32) of 64 have a lower neighbour
+    with pytest.raises(m.OpenClothError):
+        a.band_link(None, ea)                            # not adjacent
+    a.step(1)
+    a.sync()
+    with pytest.raises(m.OpenClothError):
+        a.band_link(None, eb)                            # different step counts (buffer rotation)
+    for c in (a, b, w):
+        c.close()
+
+
+def test_tile_dependency_timeout_is_an_error():
+    """A tile dependency that never arrives must fail the step (OC_ERR_CUDA from oc_sync / oc_download), not compute
+    from stale rows.  OC_DEBUG=32 makes the chained tiles wait for a launch that does not exist and give up after
+    50 ms; run in a subprocess because the kernel traps (the CUDA context is lost, as after any device fault)."""
+    import subprocess
+    import sys
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "import opencloth_b200 as m\n"
+        "c = m.Cloth(512, 512, kernel=m.OC_KERNEL_MARCH2)\n"
+        "c.step(3)\n"
+        "try:\n"
+        "    c.sync()\n"
+        "    print('NO ERROR')\n"
+        "except m.OpenClothError as e:\n"
+        "    print('ERR', e.code, e)\n" % helpers.ROOT)
+    import os
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=dict(os.environ, OC_DEBUG="32"))
+    assert "ERR -3" in r.stdout and "timed out" in r.stdout, r.stdout + r.stderr
 
 
 def test_branch_free_math_is_ieee():
