@@ -265,6 +265,7 @@ cudaError_t oc_march2_launch(const OcConst& c, bool exact, int ra, int rb, int s
     // dependencies on the previous launch (OcDep2)
     OcDep2 dep = {};
     const bool can_flag = chain && chain->flags && (long long)oc_seg2_tiles(seg) * c.batch <= chain->cap;      // one flag per tile and cloth
+    if (peer && !can_flag) return cudaErrorInvalidConfiguration;      // linked bands publish through the same epilogue
     if (can_flag) {
         dep.flags = chain->flags; dep.epoch = ++chain->epoch;
         // <= 4 segments per strip to poll; short tiles gain nothing (measured: 16-row tiles of a 1024^2 cloth lose 15 %)

@@ -38,7 +38,7 @@ struct EmuCtx {
     int by() const { return by_; }
     int bz() const { return bz_; }
     unsigned char* smem() const { return smem_; }
-    void wait_deps(const OcDep2&, const OcConst&, int, int) const {}       // the emulator runs the tiles of a launch one after the other
+    bool wait_deps(const OcDep2&, const OcConst&, int, int) const { return true; }       // the emulator runs the tiles of a launch one after the other
     void sync();
 };
 

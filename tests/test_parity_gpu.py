@@ -475,7 +475,7 @@ def test_tile_dependency_timeout_is_an_error():
     code = (
         "import sys; sys.path.insert(0, %r)\n"
         "import opencloth_b200 as m\n"
-        "c = m.Cloth(512, 512, kernel=m.OC_KERNEL_MARCH2)\n"
+        "c = m.Cloth(2048, 2048, kernel=m.OC_KERNEL_MARCH2)\n"
         "c.step(3)\n"
         "try:\n"
         "    c.sync()\n"
