@@ -283,6 +283,12 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         torch.cuda.synchronize(dev)
+        # The ranks leave the host barrier up to a millisecond apart (measured), and a band that starts early only
+        # waits for its neighbours: each rank's own clock would then include the others' lateness.  A device-side
+        # barrier (a one-word all-reduce the timed stream waits for, no host synchronisation after it) starts all
+        # GPUs together, with their launches already queued behind it; ev0 comes after it.
+        gate = torch.zeros(1, device=dev)
+        dist.all_reduce(gate)
     t_host0 = time.time()
     ev0.record(stream)
     advance(K, finish=True)
