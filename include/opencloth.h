@@ -52,6 +52,15 @@ typedef enum oc_kernel {
                                 bands are served by OC_KERNEL_MARCH2 */
 } oc_kernel;
 
+/* The reference's explicit integrators on this spring net.  "E:" =
+ * OpenCloth_ExplicitEuler/OpenCloth_ExplicitEuler/main.cpp, "S:" = OpenCloth_SemiImplicit/OpenCloth_SemiImplicit/main.cpp.
+ * The Euler demos keep X and V instead of X and X_last: for them every "X_last" argument / result of this API is V. */
+typedef enum oc_integrator {
+    OC_INTEGRATOR_VERLET = 0,          /* IntegrateVerlet V:428-444 (the hot path)                                       */
+    OC_INTEGRATOR_EULER = 1,           /* ComputeForces E:434-466, IntegrateEuler E:469-482 (X += dt * old V)             */
+    OC_INTEGRATOR_SEMI_IMPLICIT = 2    /* ComputeForces S:402-436, IntegrateSemiImplicit S:464-477 (X += dt * new V)      */
+} oc_integrator;
+
 typedef struct oc_cloth oc_cloth;      /* opaque; owns all device memory of one simulation */
 
 /* All defaults (oc_default_params) are the reference's values. */
@@ -81,11 +90,19 @@ typedef struct oc_params {
     float inv_ellipsoid[16];   /* glm::inverse(ellipsoid)  V:327 */
     float center[3];           /* 0,0,0  V:129 */
     float radius;              /* 1.0f   V:130 */
+    /* ---- the step's optional parts ---------------------------------------------------------------------------- */
+    int   integrator;          /* oc_integrator; fixed at oc_create.  Euler variants: whole cloths only (no row bands),
+                                  served by the gather kernel                                                       */
+    int   provot;              /* 1: ApplyProvotDynamicInverse after EllipsoidCollision, bit-exact in list order
+                                  (V:486-508, which the Verlet demo leaves disabled at V:561 — default 0; E:554-577 /
+                                  S:437-462, enabled at E:639 / S:531 — default 1 there).  Changeable; whole cloths only */
 } oc_params;
 
 /* Fill *p with the reference's values for an nx x ny cloth (replaces the globals V:59-62, V:97-104,
  * V:123-130 and the ellipsoid set-up V:324-327). */
 int oc_default_params(oc_params* p, int nx, int ny);
+/* The same for one of the sibling demos: its own spring constants, mass 0.5 and Provot pass (E:97-102, S:80-85). */
+int oc_default_params_for(oc_params* p, int nx, int ny, int integrator);
 
 /* Allocate device state and initialise X = X_last = the flat sheet of InitGL (V:249-260); the
  * spring net of V:286-320 is implicit in (i,j), its rest lengths are derived from the same fp32

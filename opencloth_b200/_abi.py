@@ -25,6 +25,10 @@ OC_KERNEL_RESIDENT = 4
 
 OC_BAND_ENDPOINT_BYTES = 512
 
+OC_INTEGRATOR_VERLET = 0
+OC_INTEGRATOR_EULER = 1
+OC_INTEGRATOR_SEMI_IMPLICIT = 2
+
 
 class OcParams(ctypes.Structure):
     """Mirror of ``oc_params`` (include/opencloth.h). Field order and types must match exactly."""
@@ -49,6 +53,8 @@ class OcParams(ctypes.Structure):
         ("inv_ellipsoid", ctypes.c_float * 16),
         ("center", ctypes.c_float * 3),
         ("radius", ctypes.c_float),
+        ("integrator", ctypes.c_int),
+        ("provot", ctypes.c_int),
     ]
 
 
@@ -56,6 +62,7 @@ class OcParams(ctypes.Structure):
 _P = ctypes.POINTER
 SYMBOLS = {
     "oc_default_params": (ctypes.c_int, [_P(OcParams), ctypes.c_int, ctypes.c_int]),
+    "oc_default_params_for": (ctypes.c_int, [_P(OcParams), ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "oc_create": (ctypes.c_int, [_P(ctypes.c_void_p), _P(OcParams)]),
     "oc_set_params": (ctypes.c_int, [ctypes.c_void_p, _P(OcParams)]),
     "oc_get_params": (ctypes.c_int, [ctypes.c_void_p, _P(OcParams)]),

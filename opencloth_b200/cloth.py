@@ -20,10 +20,11 @@ from . import _abi
 from ._abi import OcParams, check
 
 
-def default_params(nx=21, ny=21, **overrides):
-    """``oc_params`` filled with the reference's values (V:59-62, V:97-104, V:123-130, V:324-327)."""
+def default_params(nx=21, ny=21, integrator=0, **overrides):
+    """``oc_params`` filled with the reference's values (V:59-62, V:97-104, V:123-130, V:324-327); with
+    ``integrator`` = OC_INTEGRATOR_EULER / OC_INTEGRATOR_SEMI_IMPLICIT the values of that sibling demo."""
     p = OcParams()
-    check(_abi.load().oc_default_params(ctypes.byref(p), nx, ny))
+    check(_abi.load().oc_default_params_for(ctypes.byref(p), nx, ny, integrator))
     for k, v in overrides.items():
         if not hasattr(p, k):
             raise AttributeError(f"oc_params has no field {k!r}")

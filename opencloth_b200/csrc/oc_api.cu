@@ -9,6 +9,7 @@
 #include "oc_core.cuh"
 #include "oc_host.h"
 #include "oc_gather.cuh"
+#include "oc_provot.cuh"
 #include "oc_resident.cuh"
 #include "oc_march.cuh"
 #include "oc_march2.cuh"
@@ -119,6 +120,14 @@ extern "C" int oc_default_params(oc_params* p, int nx, int ny)
     return OC_OK;
 }
 
+extern "C" int oc_default_params_for(oc_params* p, int nx, int ny, int integrator)
+{
+    if (!p) return oc_fail(OC_ERR_INVALID, "oc_default_params_for: null");
+    if (integrator < OC_INTEGRATOR_VERLET || integrator > OC_INTEGRATOR_SEMI_IMPLICIT) return oc_fail(OC_ERR_INVALID, "bad integrator id %d", integrator);
+    oc_host_default_params_for(p, nx, ny, integrator);
+    return OC_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // small kernels: initial sheet, pack / unpack, particle write-back, energy
 // ------------------------------------------------------------------------------------------------
@@ -131,7 +140,8 @@ __global__ void oc_k_init(OcConst c, const float* __restrict__ xs, const float* 
     long long r = t % per;
     int j = (int)(r / c.U) + c.row_lo, i = (int)(r % c.U);
     float4 v = make_float4(xs[i], y, zs[j], oc_u2f(OC_W_PLAIN));       // V:256-257
-    A[t] = v; B[t] = v;
+    A[t] = v;
+    B[t] = c.integ == 0 ? v : make_float4(0.0f, 0.0f, 0.0f, oc_u2f(OC_W_PLAIN));      // X_last = X (V:259), or V = 0 (E:270)
 }
 
 // host layout (stride 3 or 4, owned rows only) -> float4 storage (owned rows inside the halo'd store)
@@ -172,10 +182,10 @@ __global__ void oc_k_pack(OcConst c, int row_begin, int rows, int stride,
     }
 }
 
-__global__ void oc_k_set_particle(float4* A, float4* B, long long o, float x, float y, float z)
+__global__ void oc_k_set_particle(float4* A, float4* B, long long o, float x, float y, float z, int xv)
 {
-    float4 v = make_float4(x, y, z, oc_u2f(OC_W_PLAIN));                // V:203-208
-    A[o] = v; B[o] = v;
+    float4 v = make_float4(x, y, z, oc_u2f(OC_W_PLAIN));                // V:203-208: X_last = X; Euler demos E:201-210: V = 0
+    A[o] = v; B[o] = xv ? make_float4(0.0f, 0.0f, 0.0f, oc_u2f(OC_W_PLAIN)) : v;
 }
 
 // sum over springs of 1/2 Ks (|p1-p2| - rest)^2 in double; every particle owns its forward springs
@@ -240,6 +250,10 @@ static int validate(const oc_params* p)
     if (p->substeps_per_launch < 0 || p->substeps_per_launch > OC_MARCH_MAX_STAGES)
         return oc_fail(OC_ERR_INVALID, "substeps_per_launch must be 0..%d", OC_MARCH_MAX_STAGES);
     if (p->kernel < OC_KERNEL_AUTO || p->kernel > OC_KERNEL_RESIDENT) return oc_fail(OC_ERR_INVALID, "bad kernel id");
+    if (p->integrator < OC_INTEGRATOR_VERLET || p->integrator > OC_INTEGRATOR_SEMI_IMPLICIT) return oc_fail(OC_ERR_INVALID, "bad integrator id %d", p->integrator);
+    if (p->provot != 0 && p->provot != 1) return oc_fail(OC_ERR_INVALID, "provot must be 0 or 1");
+    if ((p->integrator != OC_INTEGRATOR_VERLET || p->provot) && (p->row_begin != 0 || p->row_end != 0) && (p->row_begin > 0 || p->row_end < p->ny))
+        return oc_fail(OC_ERR_UNSUPPORTED, "the Euler integrators and the Provot pass need a whole-cloth handle (no row bands)");
     return OC_OK;
 }
 
@@ -332,6 +346,7 @@ extern "C" int oc_set_params(oc_cloth* c, const oc_params* p)
     if (!c || !p) return oc_fail(OC_ERR_INVALID, "oc_set_params: null");
     oc_params q = *p;
     if (q.row_begin == 0 && q.row_end == 0) q.row_end = q.ny;
+    if (q.integrator != c->p.integrator) return oc_fail(OC_ERR_INVALID, "oc_set_params: the integrator is fixed at oc_create (it decides what the second state buffer holds)");
     if (q.nx != c->p.nx || q.ny != c->p.ny || q.batch != c->p.batch || q.fullsize != c->p.fullsize ||
         q.row_begin != c->p.row_begin || q.row_end != c->p.row_end || (c->q.band && q.halo_rows != c->p.halo_rows))
         return oc_fail(OC_ERR_INVALID, "oc_set_params: nx, ny, batch, row band, halo_rows and fullsize are fixed at oc_create");
@@ -454,7 +469,7 @@ extern "C" int oc_set_particle(oc_cloth* c, int cloth, int idx, const float xyz[
     int j = idx / c->p.nx, i = idx % c->p.nx;
     if (j < c->k.row_lo || j >= c->k.row_lo + c->k.srows) return OC_OK;      // not stored by this band
     OC_CUDA(cudaSetDevice(c->dev));
-    oc_k_set_particle<<<1, 1, 0, c->stream>>>(c->buf[c->q.ia], c->buf[c->q.ib], oc_index(c->k, cloth, i, j), xyz[0], xyz[1], xyz[2]);
+    oc_k_set_particle<<<1, 1, 0, c->stream>>>(c->buf[c->q.ia], c->buf[c->q.ib], oc_index(c->k, cloth, i, j), xyz[0], xyz[1], xyz[2], c->q.xv ? 1 : 0);
     c->launches++;
     OC_CUDA(cudaGetLastError());
     return OC_OK;
@@ -467,6 +482,8 @@ static int pick_kernel(const oc_cloth* c)
 {
     const bool can_reside = !c->q.band && (long long)c->p.nx * c->p.ny <= OC_RESIDENT_MAX_PARTICLES;
     if (c->link.on) return OC_KERNEL_MARCH2;             // linked row bands: the kernel that pushes its boundary rows
+    if (c->p.integrator != OC_INTEGRATOR_VERLET) return OC_KERNEL_GATHER;      // state (X, V): oc_k_gather_xv
+    if (c->p.provot && (c->p.kernel == OC_KERNEL_RESIDENT || c->p.kernel == OC_KERNEL_AUTO)) return OC_KERNEL_MARCH2;   // a pass after EVERY substep
     if (c->p.kernel == OC_KERNEL_RESIDENT) return can_reside ? OC_KERNEL_RESIDENT : OC_KERNEL_MARCH2;   // a cloth that does not fit one CTA's shared memory: the fastest general kernel
     if (c->p.kernel != OC_KERNEL_AUTO) return c->p.kernel;
     // small whole cloths (the reference's own 21 x 21): state resident in shared memory, all substeps in one launch.
@@ -518,13 +535,45 @@ static int launch_rows(oc_cloth* c, int kern, const OcLaunch& L, int ra, int rb)
     } else {
         chain_break(c);
         dim3 blk(128, 1, 1), grd((c->p.nx + 127) / 128, rb - ra, c->p.batch);
-        if (c->p.exact) oc_k_gather<MathExact><<<grd, blk, 0, c->stream>>>(c->k, c->buf[L.src_a], c->buf[L.src_b], c->buf[L.dst], ra);
-        else            oc_k_gather<MathFast><<<grd, blk, 0, c->stream>>>(c->k, c->buf[L.src_a], c->buf[L.src_b], c->buf[L.dst], ra);
+        if (c->q.xv) {
+            if (c->p.exact) oc_k_gather_xv<MathExact><<<grd, blk, 0, c->stream>>>(c->k, c->buf[L.src_a], c->buf[L.src_b], c->buf[L.dst], c->buf[L.dst_prev], ra);
+            else            oc_k_gather_xv<MathFast><<<grd, blk, 0, c->stream>>>(c->k, c->buf[L.src_a], c->buf[L.src_b], c->buf[L.dst], c->buf[L.dst_prev], ra);
+        }
+        else if (c->p.exact) oc_k_gather<MathExact><<<grd, blk, 0, c->stream>>>(c->k, c->buf[L.src_a], c->buf[L.src_b], c->buf[L.dst], ra);
+        else                 oc_k_gather<MathFast><<<grd, blk, 0, c->stream>>>(c->k, c->buf[L.src_a], c->buf[L.src_b], c->buf[L.dst], ra);
         c->launches++;
         OC_CUDA(cudaGetLastError());
     }
     return OC_OK;
 }
+
+// ApplyProvotDynamicInverse on the state the last substep produced (oc_provot.cuh), bit-exact in list order.
+template <class M>
+static int provot_pass_t(oc_cloth* c)
+{
+    const int U = c->p.nx, V = c->p.ny, B = c->p.batch;
+    float4* X = c->buf[c->q.ia];
+    float4* S = c->buf[c->q.ib];          // X_last (Verlet) or V (Euler)
+    chain_break(c);
+    if (c->q.xv) {
+        dim3 blk(128, 1, 1), grd((U + 127) / 128, V, B);
+        oc_k_provot_v<M><<<grd, blk, 0, c->stream>>>(c->k, X, S, S);
+        c->launches++;
+    } else {
+        const long long n = c->stored;
+        oc_k_provot_materialize<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->k, X, S);
+        oc_k_provot_rows<M, 1><<<dim3((V + 127) / 128, B), 128, 0, c->stream>>>(c->k, X);          // V:288-291
+        oc_k_provot_cols<M, 1><<<dim3((U + 127) / 128, B), 128, 0, c->stream>>>(c->k, X);          // V:294-297
+        int t = V - 1 < 1024 ? (V - 1 + 31) / 32 * 32 : 1024;
+        oc_k_provot_shear<M><<<B, t, 0, c->stream>>>(c->k, X);                                     // V:301-305
+        oc_k_provot_rows<M, 2><<<dim3((V + 127) / 128, B), 128, 0, c->stream>>>(c->k, X);          // V:309-314
+        oc_k_provot_cols<M, 2><<<dim3((U + 127) / 128, B), 128, 0, c->stream>>>(c->k, X);          // V:315-320
+        c->launches += 6;
+    }
+    OC_CUDA(cudaGetLastError());
+    return OC_OK;
+}
+static int provot_pass(oc_cloth* c) { return c->p.exact ? provot_pass_t<MathExact>(c) : provot_pass_t<MathFast>(c); }
 
 // n substeps; if split_stream != nullptr and the last substep is a single-substep launch over exactly the
 // owned rows of a band, that launch is issued as boundary rows first (the rows the neighbours need), an
@@ -542,7 +591,8 @@ static int step_impl(oc_cloth* c, int n, cudaStream_t split_stream, bool want_sp
     const int kern = pick_kernel(c);
     const int kdef = c->p.substeps_per_launch > 0 ? c->p.substeps_per_launch : 1;
     while (n > 0) {
-        const int kmaxS = (kern == OC_KERNEL_MARCH) ? oc_host_pick_stages(n < kdef ? n : kdef) : (kern == OC_KERNEL_RESIDENT ? OC_RESIDENT_MAX_STEPS : 1);
+        int kmaxS = (kern == OC_KERNEL_MARCH) ? oc_host_pick_stages(n < kdef ? n : kdef) : (kern == OC_KERNEL_RESIDENT ? OC_RESIDENT_MAX_STEPS : 1);
+        if (c->p.provot || c->q.xv) kmaxS = 1;                    // the Provot pass follows every substep; (X, V) steps are single
         OcLaunch L;
         oc_host_next_launch(c->q, n, kmaxS, L);
         const int H = c->p.halo_rows;
@@ -552,6 +602,7 @@ static int step_impl(oc_cloth* c, int n, cudaStream_t split_stream, bool want_sp
         if (!split) {
             rc = launch_rows(c, kern, L, L.ra, L.rb);
             if (rc) return rc;
+            if (c->p.provot) { rc = provot_pass(c); if (rc) return rc; }
         } else {
             // three launches of ONE step over parts of the rows: each waits for the whole grid before it (no chaining)
             chain_break(c);

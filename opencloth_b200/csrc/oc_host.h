@@ -45,6 +45,15 @@ static inline void oc_host_default_params(oc_params* p, int nx, int ny)
     memcpy(p->inv_ellipsoid, oc_k_inv_ellipsoid, sizeof(oc_k_inv_ellipsoid));
     p->center[0] = p->center[1] = p->center[2] = 0.0f;    // V:129
     p->radius = 1.0f;                                     // V:130
+    p->integrator = OC_INTEGRATOR_VERLET; p->provot = 0;  // V:561 leaves the Provot pass commented out
+}
+// the globals of the sibling demos (E: OpenCloth_ExplicitEuler main.cpp:97-102, S: OpenCloth_SemiImplicit main.cpp:80-85)
+static inline void oc_host_default_params_for(oc_params* p, int nx, int ny, int integrator)
+{
+    oc_host_default_params(p, nx, ny);
+    p->integrator = integrator;
+    if (integrator == OC_INTEGRATOR_EULER)         { p->ks_struct = 0.5f;  p->ks_shear = 0.5f;  p->ks_bend = 0.85f; p->mass = 0.5f; p->provot = 1; }
+    if (integrator == OC_INTEGRATOR_SEMI_IMPLICIT) { p->ks_struct = 0.75f; p->ks_shear = 0.75f; p->ks_bend = 0.95f; p->mass = 0.5f; p->provot = 1; }
 }
 
 // Everything derived from the run-time scalars, with the reference's fp32 operations.
@@ -56,8 +65,11 @@ static inline void oc_host_derive_scalars(const oc_params& p, OcConst& k)
     k.dt_bf = (p.dt >= 0x1.0p-20f && p.dt <= 0x1.0p+20f) ? 1 : 0;
     { const char* e = getenv("OC_DEBUG"); k.dbg = e ? atoi(e) : 0; }
     k.dt2m = (p.dt * p.dt) / p.mass;                                  // V:429
+    k.dtm = p.dt / p.mass;                                            // E:470, S:465
+    k.integ = p.integrator;
     k.damping = p.damping;
-    for (int a = 0; a < 3; ++a) k.f0[a] = 0.0f + p.gravity[a] * p.mass;   // V:452, V:456
+    for (int a = 0; a < 3; ++a)                                       // V:452, V:456; the Euler demos add gravity without the mass (E:441)
+        k.f0[a] = p.integrator == OC_INTEGRATOR_VERLET ? 0.0f + p.gravity[a] * p.mass : 0.0f + p.gravity[a];
     k.nks_struct = -p.ks_struct; k.kd_struct = p.kd_struct;
     k.nks_shear  = -p.ks_shear;  k.kd_shear  = p.kd_shear;
     k.nks_bend   = -p.ks_bend;   k.kd_bend   = p.kd_bend;
@@ -155,6 +167,7 @@ struct OcSeq {
     int V;
     bool band;                // owns a strict sub-range of the rows
     bool linked;              // band whose halo rows are kept current by its neighbours (peer stores every substep): no shrink
+    bool xv;                  // the state is (X, V) — Euler integrators: a step writes both free buffers, ia <- X, ib <- V
     int kmax;                 // band: substeps between halo exchanges (halo_rows / 2)
     // running
     int fresh;                // band: substeps taken since the halo rows were last current
@@ -177,6 +190,7 @@ static inline void oc_host_geometry(oc_params& p, OcConst& k, OcSeq& q)
     k.cloth_stride = (long long)k.srows * U;
     q.row_begin = rb; q.row_end = re; q.V = V;
     q.kmax = halo / 2; q.fresh = 0; q.ia = 0; q.ib = 1; q.linked = false;
+    q.xv = p.integrator != OC_INTEGRATOR_VERLET;
 }
 
 // Stage counts (substeps per launch) the marching kernel is compiled for: 1, 2, 4, 8.
@@ -214,8 +228,8 @@ static inline void oc_host_next_launch(OcSeq& q, int& n, int k, OcLaunch& L)
     int f[2], m = 0;
     for (int b = 0; b < 4; ++b) if (b != q.ia && b != q.ib) f[m++] = b;
     L.src_a = q.ia; L.src_b = q.ib; L.dst = f[0]; L.dst_prev = f[1];
-    if (S == 1) { q.ib = q.ia; q.ia = L.dst; }
-    else        { q.ia = L.dst; q.ib = L.dst_prev; }
+    if (S == 1 && !q.xv) { q.ib = q.ia; q.ia = L.dst; }
+    else                 { q.ia = L.dst; q.ib = L.dst_prev; }
     if (q.band && !q.linked) q.fresh += S;
     n -= S;
 }

@@ -41,7 +41,21 @@ typedef struct oco_params {
     float inv_ellipsoid[16];    /* V:327 */
     float center[3];            /* V:129 */
     float radius;               /* V:130 */
+    int   integrator;           /* 0 Verlet (V:), 1 explicit Euler (E:), 2 semi-implicit / symplectic Euler (S:); see below */
+    int   provot;               /* 1: ApplyProvotDynamicInverse after EllipsoidCollision (V:486-508, disabled at V:561;
+                                   E:554-577 / S:437-462, enabled at E:639 / S:531) */
 } oco_params;
+/* The two explicit-integrator siblings of the Verlet demo, restated from
+ *   E: = /root/reference/OpenCloth_ExplicitEuler/OpenCloth_ExplicitEuler/main.cpp   (StepPhysics E:626-641)
+ *   S: = /root/reference/OpenCloth_SemiImplicit/OpenCloth_SemiImplicit/main.cpp     (StepPhysics S:527-532)
+ * They keep X and V (here: the `xl` array holds V), use the same spring net and the same spring force on the stored
+ * velocities (E:434-466 / S:402-436; gravity is added WITHOUT the mass factor, E:441), integrate with
+ * IntegrateEuler (E:469-482: V += F*(dt/mass); X += dt*oldV) or IntegrateSemiImplicit (S:464-477: X += dt*newV),
+ * zero V on collider contact (E:599 / S:499), and apply the Provot pass to V.  Pinned against the verbatim builds
+ * oracle/_ref/libocref_euler.so / libocref_semi.so by tests/test_oracle.py. */
+#define OCO_VERLET 0
+#define OCO_EULER  1
+#define OCO_SEMI   2
 
 typedef struct oco_cloth {
     oco_params p;
@@ -84,6 +98,15 @@ void oco_default_params(oco_params* p, int nx, int ny)
     memcpy(p->inv_ellipsoid, k_inv_ellipsoid, sizeof(k_inv_ellipsoid));
     p->center[0] = p->center[1] = p->center[2] = 0.0f;
     p->radius = 1.0f;
+    p->integrator = OCO_VERLET; p->provot = 0;
+}
+/* the globals of the sibling demos: E:97-102 / S:80-85 */
+void oco_default_params_for(oco_params* p, int nx, int ny, int integrator)
+{
+    oco_default_params(p, nx, ny);
+    p->integrator = integrator;
+    if (integrator == OCO_EULER) { p->ks_struct = 0.5f;  p->ks_shear = 0.5f;  p->ks_bend = 0.85f; p->mass = 0.5f; p->provot = 1; }
+    if (integrator == OCO_SEMI)  { p->ks_struct = 0.75f; p->ks_shear = 0.75f; p->ks_bend = 0.95f; p->mass = 0.5f; p->provot = 1; }
 }
 
 static float rest_from(float ax, float az, float bx, float bz)
@@ -143,6 +166,7 @@ oco_cloth* oco_create(const oco_params* p)
             count++;
         }
     memcpy(c->xl, c->x, b);
+    if (p->integrator != OCO_VERLET) memset(c->xl, 0, b);      /* V = 0, E:270 / S:237 */
     return c;
 }
 
@@ -157,7 +181,7 @@ void oco_destroy(oco_cloth* c)
 /* run-time changeable scalars (everything except nx, ny, fullsize which fix the spring net) */
 int oco_set_params(oco_cloth* c, const oco_params* p)
 {
-    if (p->nx != c->p.nx || p->ny != c->p.ny || p->fullsize != c->p.fullsize) return -1;
+    if (p->nx != c->p.nx || p->ny != c->p.ny || p->fullsize != c->p.fullsize || p->integrator != c->p.integrator) return -1;
     c->p = *p;
     derive(c);
     return 0;
@@ -216,7 +240,8 @@ static inline void spring(const float* pa, const float* va, const float* pb, con
 #define ADD_SPRING(ni, nj, rest, ks, kd)                                   \
     do {                                                                   \
         float vb_[3], f_[3];                                               \
-        velocity(PX(ni, nj), PL(ni, nj), dt, vb_);                         \
+        if (verlet) velocity(PX(ni, nj), PL(ni, nj), dt, vb_);             \
+        else { const float* q_ = PL(ni, nj); vb_[0] = q_[0]; vb_[1] = q_[1]; vb_[2] = q_[2]; }   /* stored V */ \
         spring(xm, vm, PX(ni, nj), vb_, (rest), (ks), (kd), f_);           \
         F[0] += f_[0]; F[1] += f_[1]; F[2] += f_[2];                       \
     } while (0)
@@ -231,11 +256,17 @@ static void particle_step(const oco_cloth* c, int i, int j, float* xo, float* xl
     const size_t idx = (size_t)j * u + i;
     const int pinned = (idx == 0 || idx == (size_t)(u - 1));      /* V:455, V:479-482: i!=0 && i!=numX */
 
-    /* ---- ComputeForces, first loop (V:451-459) ---- */
+    const int verlet = (p->integrator == OCO_VERLET);
+
+    /* ---- ComputeForces, first loop (V:451-459; E:436-445 / S:406-415) ---- */
     float F[3] = { 0.0f, 0.0f, 0.0f };
     float vm[3];
-    velocity(xm, xlm, dt, vm);
-    if (!pinned) { F[0] += p->gravity[0] * p->mass; F[1] += p->gravity[1] * p->mass; F[2] += p->gravity[2] * p->mass; }
+    if (verlet) velocity(xm, xlm, dt, vm);
+    else { vm[0] = xlm[0]; vm[1] = xlm[1]; vm[2] = xlm[2]; }
+    if (!pinned) {
+        if (verlet) { F[0] += p->gravity[0] * p->mass; F[1] += p->gravity[1] * p->mass; F[2] += p->gravity[2] * p->mass; }
+        else        { F[0] += p->gravity[0]; F[1] += p->gravity[1]; F[2] += p->gravity[2]; }                  /* E:441 */
+    }
     F[0] += p->damping * vm[0]; F[1] += p->damping * vm[1]; F[2] += p->damping * vm[2];
 
     /* ---- ComputeForces, second loop (V:462-483) re-ordered per particle; the order below is the
@@ -264,12 +295,21 @@ static void particle_step(const oco_cloth* c, int i, int j, float* xo, float* xl
         if (j == v - 1) ADD_SPRING(i, j - 2, c->rv2[j - 2], p->ks_bend, p->kd_bend);
     }
 
-    /* ---- IntegrateVerlet (V:428-444) ---- */
-    float dt2m = (dt * dt) / p->mass;                                                   /* V:429 */
-    float nx_ = xm[0] + (xm[0] - xlm[0]) + dt2m * F[0];                                 /* V:436 */
-    float ny_ = xm[1] + (xm[1] - xlm[1]) + dt2m * F[1];
-    float nz_ = xm[2] + (xm[2] - xlm[2]) + dt2m * F[2];
-    float lx = xm[0], ly = xm[1], lz = xm[2];                                           /* V:438 */
+    float nx_, ny_, nz_, lx, ly, lz;
+    if (verlet) {
+        /* ---- IntegrateVerlet (V:428-444) ---- */
+        float dt2m = (dt * dt) / p->mass;                                                   /* V:429 */
+        nx_ = xm[0] + (xm[0] - xlm[0]) + dt2m * F[0];                                       /* V:436 */
+        ny_ = xm[1] + (xm[1] - xlm[1]) + dt2m * F[1];
+        nz_ = xm[2] + (xm[2] - xlm[2]) + dt2m * F[2];
+        lx = xm[0]; ly = xm[1]; lz = xm[2];                                                 /* V:438 */
+    } else {
+        /* ---- IntegrateEuler (E:469-482) / IntegrateSemiImplicit (S:464-477); l* is the new V ---- */
+        float dtm = dt / p->mass;                                                           /* E:470 */
+        lx = vm[0] + F[0] * dtm; ly = vm[1] + F[1] * dtm; lz = vm[2] + F[2] * dtm;          /* E:475 V += F*deltaTimeMass */
+        if (p->integrator == OCO_EULER) { nx_ = xm[0] + dt * vm[0]; ny_ = xm[1] + dt * vm[1]; nz_ = xm[2] + dt * vm[2]; }   /* E:476 oldV */
+        else                            { nx_ = xm[0] + dt * lx;    ny_ = xm[1] + dt * ly;    nz_ = xm[2] + dt * lz; }      /* S:470 */
+    }
     if (ny_ < 0) ny_ = 0;                                                               /* V:440-442 */
 
     /* ---- EllipsoidCollision (V:509-533) ---- */
@@ -286,7 +326,8 @@ static void particle_step(const oco_cloth* c, int i, int j, float* xo, float* xl
         float dy = d0x * c->tinv[1][0] + d0y * c->tinv[1][1] + d0z * c->tinv[1][2];      /* V:523-525 */
         float dz = d0x * c->tinv[2][0] + d0y * c->tinv[2][1] + d0z * c->tinv[2][2];      /* V:526-528 */
         nx_ += dx; ny_ += dy; nz_ += dz;                                                /* V:529 */
-        lx = nx_; ly = ny_; lz = nz_;                                                   /* V:530 */
+        if (verlet) { lx = nx_; ly = ny_; lz = nz_; }                                   /* V:530 */
+        else        { lx = 0.0f; ly = 0.0f; lz = 0.0f; }                                /* E:599 V[i] = vec3(0) */
     }
     xo[0] = nx_; xo[1] = ny_; xo[2] = nz_;
     xlo[0] = lx; xlo[1] = ly; xlo[2] = lz;
@@ -312,9 +353,57 @@ void oco_step_rows(oco_cloth* c, int j0, int j1)
     t = c->xl; c->xl = c->xl2; c->xl2 = t;
 }
 
+/* ApplyProvotDynamicInverse (V:486-508; E:554-577 / S:437-462) over the implicit spring list in the reference's list
+ * order (V:286-320), sequentially like the reference: in the Verlet demo the corrections move X in place, so every
+ * spring sees the positions its predecessors left (Gauss-Seidel); in the Euler demos they are added to V. */
+static void provot_spring(oco_cloth* c, int i1, int j1, int i2, int j2, float rest)
+{
+    const int u = c->p.nx;
+    float* p1 = PX(i1, j1); float* p2 = PX(i2, j2);
+    float dx = p1[0] - p2[0], dy = p1[1] - p2[1], dz = p1[2] - p2[2];              /* V:491 */
+    float sqr = dx * dx + dy * dy + dz * dz;
+    float dist = sqrtf(sqr);                                                        /* V:492 */
+    if (dist > rest) {                                                              /* V:493 */
+        dist -= rest;                                                               /* V:494 */
+        dist /= 2.0f;                                                               /* V:495 */
+        float inv = 1.0f / sqrtf(sqr);                                              /* V:496 glm::normalize */
+        dx = dx * inv; dy = dy * inv; dz = dz * inv;
+        dx *= dist; dy *= dist; dz *= dist;                                         /* V:497 */
+        const size_t a = (size_t)j1 * u + i1, b = (size_t)j2 * u + i2;
+        const int pin1 = (a == 0 || a == (size_t)(u - 1)), pin2 = (b == 0 || b == (size_t)(u - 1));
+        float* t1 = c->p.integrator == OCO_VERLET ? p1 : PL(i1, j1);                /* X (V:498-505) or V (E:567-574) */
+        float* t2 = c->p.integrator == OCO_VERLET ? p2 : PL(i2, j2);
+        if (pin1)      { t2[0] += dx; t2[1] += dy; t2[2] += dz; }                   /* V:498-499 */
+        else if (pin2) { t1[0] -= dx; t1[1] -= dy; t1[2] -= dz; }                   /* V:500-501 */
+        else           { t1[0] -= dx; t1[1] -= dy; t1[2] -= dz; t2[0] += dx; t2[1] += dy; t2[2] += dz; }   /* V:503-504 */
+    }
+}
+void oco_provot(oco_cloth* c)
+{
+    const int u = c->p.nx, v = c->p.ny;
+    for (int j = 0; j < v; ++j) for (int i = 0; i < u - 1; ++i) provot_spring(c, i, j, i + 1, j, c->rh1[i]);     /* V:288-291 */
+    for (int i = 0; i < u; ++i) for (int j = 0; j < v - 1; ++j) provot_spring(c, i, j, i, j + 1, c->rv1[j]);     /* V:294-297 */
+    for (int j = 0; j < v - 1; ++j) for (int i = 0; i < u - 1; ++i) {                                            /* V:301-305 */
+        float r = sqrtf(c->dx2[i] + c->dz2[j]);
+        provot_spring(c, i, j, i + 1, j + 1, r);
+        provot_spring(c, i, j + 1, i + 1, j, r);
+    }
+    for (int j = 0; j < v; ++j) {                                                                                /* V:309-314 */
+        for (int i = 0; i < u - 2; ++i) provot_spring(c, i, j, i + 2, j, c->rh2[i]);
+        provot_spring(c, u - 3, j, u - 1, j, c->rh2[u - 3]);
+    }
+    for (int i = 0; i < u; ++i) {                                                                                /* V:315-320 */
+        for (int j = 0; j < v - 2; ++j) provot_spring(c, i, j, i, j + 2, c->rv2[j]);
+        provot_spring(c, i, v - 3, i, v - 1, c->rv2[v - 3]);
+    }
+}
+
 void oco_step(oco_cloth* c, int n)
 {
-    for (int s = 0; s < n; ++s) oco_step_rows(c, 0, c->p.ny);
+    for (int s = 0; s < n; ++s) {
+        oco_step_rows(c, 0, c->p.ny);
+        if (c->p.provot) oco_provot(c);
+    }
 }
 
 /* Spring energy diagnostic over the reference spring list, duplicates included (ours; the

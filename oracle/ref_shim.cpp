@@ -43,6 +43,7 @@ vector<glm::vec3> F;                       // V:80
 
 #include "_ref/slices/add_spring.inc"      // V:134-144 AddSpring
 #include "_ref/slices/physics.inc"         // V:428-484 IntegrateVerlet, GetVerletVelocity, ComputeForces
+#include "_ref/slices/provot.inc"          // V:486-508 ApplyProvotDynamicInverse
 #include "_ref/slices/collision.inc"       // V:509-533 EllipsoidCollision
 #include "_ref/slices/step.inc"            // V:557-562 StepPhysics
 
@@ -75,6 +76,12 @@ size_t ref_num_particles(void) { return total_points; }
 size_t ref_num_springs(void)   { return springs.size(); }
 void   ref_step(int n)         { for (int s = 0; s < n; ++s) StepPhysics(timeStep); }
 void   ref_step_dt(int n, float dt) { for (int s = 0; s < n; ++s) StepPhysics(dt); }
+// StepPhysics with the call the reference leaves commented out (V:561) enabled: the body of V:558-561, in its order
+void   ref_step_provot(int n)
+{
+    for (int s = 0; s < n; ++s) { ComputeForces(timeStep); IntegrateVerlet(timeStep); EllipsoidCollision(); ApplyProvotDynamicInverse(); }
+}
+void   ref_provot_only(void) { ApplyProvotDynamicInverse(); }
 void   ref_get_state(float* x, float* xl)
 {
     if (x)  memcpy(x,  &X[0],      total_points * sizeof(glm::vec3));

@@ -13,6 +13,7 @@
 #include "../../opencloth_b200/csrc/oc_core.cuh"
 #include "../../opencloth_b200/csrc/oc_host.h"
 #include "../../opencloth_b200/csrc/oc_gather.cuh"
+#include "../../opencloth_b200/csrc/oc_provot.cuh"
 #include "../../opencloth_b200/csrc/oc_march.cuh"
 #include "../../opencloth_b200/csrc/oc_march2.cuh"
 #include "../../opencloth_b200/csrc/oc_resident.cuh"
@@ -269,9 +270,42 @@ static void emu_gather(EmuCloth* e, const OcLaunch& L)
     const float4* A = e->buf[L.src_a].data();
     const float4* B = e->buf[L.src_b].data();
     float4* C = e->buf[L.dst].data();
+    float4* D = e->buf[L.dst_prev].data();
     for (int b = 0; b < k.batch; ++b)
         for (int j = L.ra; j < L.rb; ++j)
-            for (int i = 0; i < k.U; ++i) C[oc_index(k, b, i, j)] = oc_gather_particle<M>(k, A, B, b, i, j);
+            for (int i = 0; i < k.U; ++i) {
+                const long long o = oc_index(k, b, i, j);
+                if (e->q.xv) { float4 v; C[o] = oc_gather_particle<M, true>(k, A, B, b, i, j, &v); D[o] = v; }
+                else C[o] = oc_gather_particle<M>(k, A, B, b, i, j);
+            }
+}
+
+// ApplyProvotDynamicInverse with the library's kernel bodies: per-particle gather into V (Euler forms), or the in-place
+// sweep of X by rows, columns and the skewed shear wavefront (Verlet form; `threads` = CTA size of the wavefront)
+template <class M>
+static int emu_provot(EmuCloth* e, int threads)
+{
+    const OcConst& k = e->k;
+    float4* X = e->buf[e->q.ia].data();
+    float4* S = e->buf[e->q.ib].data();
+    int rc = 0;
+    if (e->q.xv) {
+        std::vector<float4> out((size_t)e->stored);
+        for (int b = 0; b < k.batch; ++b)
+            for (int j = 0; j < k.V; ++j)
+                for (int i = 0; i < k.U; ++i) out[oc_index(k, b, i, j)] = oc_provot_v_particle<M>(k, X, S, b, i, j);
+        memcpy(S, out.data(), out.size() * sizeof(float4));
+        return 0;
+    }
+    for (long long t = 0; t < e->stored; ++t) oc_provot_materialize(X, S, t);
+    for (int b = 0; b < k.batch; ++b) {
+        for (int j = 0; j < k.V; ++j) oc_provot_row<M, 1>(k, X, b, j);
+        for (int i = 0; i < k.U; ++i) oc_provot_col<M, 1>(k, X, b, i);
+        rc |= run_cta(threads, b, 0, 0, 16, [&](EmuCtx& ctx) { oc_provot_shear_body<M, EmuCtx>(ctx, k, X); });
+        for (int j = 0; j < k.V; ++j) oc_provot_row<M, 2>(k, X, b, j);
+        for (int i = 0; i < k.U; ++i) oc_provot_col<M, 2>(k, X, b, i);
+    }
+    return rc;
 }
 
 extern "C" {
@@ -296,6 +330,7 @@ void* emu_create(const oc_params* p)
         int j = (int)(r / e->k.U) + e->k.row_lo, i = (int)(r % e->k.U);
         float4 v = make_float4(xs[i], p->fullsize + 1, zs[j], oc_u2f(OC_W_PLAIN));
         e->buf[0][t] = e->buf[1][t] = e->buf[2][t] = e->buf[3][t] = v;
+        if (e->q.xv) e->buf[1][t] = make_float4(0.0f, 0.0f, 0.0f, oc_u2f(OC_W_PLAIN));
     }
     e->barrier_errors = 0;
     e->nb[0] = e->nb[1] = nullptr; e->link_epoch = 0;
@@ -349,9 +384,13 @@ int emu_download(void* h, float* X, float* XL)
 
 // kernel: 1 = gather, 2 = march, 3 = march2 (TW = window columns).  k = substeps per launch, TW = column window, RS = rows per segment
 // (0 = one segment).  Returns 0, -1 on a barrier-count mismatch, -2 unsupported variant, -3 halo exhausted.
+static int g_provot_threads = 32;
+void emu_set_provot_threads(int t) { g_provot_threads = t > 0 ? t : 32; }
 int emu_step(void* h, int n, int kernel, int exact, int k, int TW, int RS)
 {
     EmuCloth* e = (EmuCloth*)h;
+    if (e->q.xv) kernel = 1;
+    if (e->p.provot || e->q.xv) k = 1;
     if (e->q.band && !e->q.linked && e->q.fresh + n > e->q.kmax) return -3;
     if (e->q.linked && kernel != 3) return -2;
     int rc = 0;
@@ -361,6 +400,7 @@ int emu_step(void* h, int n, int kernel, int exact, int k, int TW, int RS)
         int kk = 1;
         if (kernel == 2) { int w = n < k ? n : k; kk = (TW == 16 && w <= 3) ? w : oc_host_pick_stages(w); }
         if (kernel == 4) kk = OC_RESIDENT_MAX_STEPS;
+        if (e->p.provot || e->q.xv) kk = 1;
         oc_host_next_launch(e->q, n, kk, L);
         if (kernel == 4) {
             int r = exact ? emu_resident<MathExact>(e, L, TW) : emu_resident<MathFast>(e, L, TW);
@@ -377,6 +417,7 @@ int emu_step(void* h, int n, int kernel, int exact, int k, int TW, int RS)
         } else {
             if (exact) emu_gather<MathExact>(e, L); else emu_gather<MathFast>(e, L);
         }
+        if (e->p.provot) rc |= exact ? emu_provot<MathExact>(e, g_provot_threads) : emu_provot<MathFast>(e, g_provot_threads);
     }
     return rc;
 }

@@ -63,8 +63,51 @@ def run(nx, ny, checkpoints, full, row_stride=16, energy_every=10):
     print(path, os.path.getsize(path), "bytes")
 
 
+def run_variant(name, nx, ny, checkpoints, full, row_stride=16):
+    """The sibling integrators and the Provot pass, same fixture format.
+    name: euler | semi (verbatim builds of OpenCloth_ExplicitEuler / OpenCloth_SemiImplicit, Provot on as they ship;
+    the second array is V), euler_noprovot | semi_noprovot (ApplyProvotDynamicInverse switched off: reaches the
+    collider), verlet_provot (the Verlet demo with the call of V:561 enabled; second array is X_last)."""
+    if name == "verlet_provot":
+        r = helpers.Ref(nx, ny)
+        step_fn = r.step_provot
+    else:
+        integ = helpers.EULER if name.startswith("euler") else helpers.SEMI
+        r = helpers.RefVariant(integ, nx, ny, provot=0 if name.endswith("noprovot") else 1)
+        step_fn = r.step
+    out = {}
+    meta = {"variant": name, "nx": nx, "ny": ny, "checkpoints": list(checkpoints), "full": full, "row_stride": row_stride,
+            "sha_x": {}, "sha_xl": {}, "hits": {}}
+    step = 0
+    for cp in checkpoints:
+        step_fn(cp - step)
+        step = cp
+        x, xl = r.state()
+        meta["sha_x"][str(cp)] = sha(x)
+        meta["sha_xl"][str(cp)] = sha(xl)
+        meta["hits"][str(cp)] = int((x == xl).all(1).sum()) if name == "verlet_provot" else int((xl == 0).all(1).sum())
+        if full:
+            out[f"x_{cp}"] = x
+            out[f"xl_{cp}"] = xl
+        else:
+            rows = np.arange(0, ny, row_stride)
+            out[f"x_{cp}"] = x.reshape(ny, nx, 3)[rows].copy()
+            out[f"xl_{cp}"] = xl.reshape(ny, nx, 3)[rows].copy()
+    out["meta"] = np.frombuffer(json.dumps(meta).encode(), np.uint8)
+    path = os.path.join(HERE, f"{name}_{nx}x{ny}.npz")
+    np.savez_compressed(path, **out)
+    print(path, os.path.getsize(path), "bytes", meta["hits"])
+
+
 def main():
     assert helpers.have_ref(), "build oracle/_ref/libocref.so first (./oracle/build_ref.sh)"
+    if len(sys.argv) > 1 and sys.argv[1] == "variants":
+        for name in ("euler", "semi", "euler_noprovot", "semi_noprovot", "verlet_provot"):
+            run_variant(name, 21, 21, [1, 100, 1000, 2000], full=True)
+            run_variant(name, 64, 64, [100, 1000] + ([2000] if "noprovot" in name else []), full=False, row_stride=16)
+        for name in ("euler", "verlet_provot"):
+            run_variant(name, 256, 256, [100, 400], full=False, row_stride=64)
+        return
     # 1. the reference's default configuration; 1672 is the first step at which the collider acts
     run(21, 21, [1, 10, 100, 1000, 1671, 1672, 2000, 3000], full=True)
     run(37, 23, [100, 1000, 2500], full=True)

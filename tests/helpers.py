@@ -24,7 +24,7 @@ def _newer(target, *sources):
 def build_emulator():
     src = os.path.join(ROOT, "tests", "emu", "oc_emu.cu")
     csrc = os.path.join(ROOT, "opencloth_b200", "csrc")
-    deps = [src] + [os.path.join(csrc, f) for f in ("oc_core.cuh", "oc_host.h", "oc_gather.cuh", "oc_march.cuh", "oc_march2.cuh")]
+    deps = [src] + [os.path.join(csrc, f) for f in ("oc_core.cuh", "oc_host.h", "oc_gather.cuh", "oc_provot.cuh", "oc_march.cuh", "oc_march2.cuh", "oc_resident.cuh")]
     if _newer(EMU_SO, *deps):
         return
     subprocess.check_call([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-std=c++17",
@@ -67,9 +67,11 @@ class OcoParams(ctypes.Structure):
                 ("damping", ctypes.c_float), ("gravity", ctypes.c_float * 3),
                 ("mass", ctypes.c_float), ("dt", ctypes.c_float),
                 ("ellipsoid", ctypes.c_float * 16), ("inv_ellipsoid", ctypes.c_float * 16),
-                ("center", ctypes.c_float * 3), ("radius", ctypes.c_float)]
+                ("center", ctypes.c_float * 3), ("radius", ctypes.c_float),
+                ("integrator", ctypes.c_int), ("provot", ctypes.c_int)]
 
 
+VERLET, EULER, SEMI = 0, 1, 2
 _oracle = None
 
 
@@ -80,6 +82,8 @@ def oracle_lib():
         L.oco_create.restype = ctypes.c_void_p
         L.oco_create.argtypes = [ctypes.POINTER(OcoParams)]
         L.oco_default_params.argtypes = [ctypes.POINTER(OcoParams), ctypes.c_int, ctypes.c_int]
+        L.oco_default_params_for.argtypes = [ctypes.POINTER(OcoParams), ctypes.c_int, ctypes.c_int, ctypes.c_int]
+        L.oco_provot.argtypes = [ctypes.c_void_p]
         L.oco_destroy.argtypes = [ctypes.c_void_p]
         L.oco_set_params.argtypes = [ctypes.c_void_p, ctypes.POINTER(OcoParams)]
         L.oco_step.argtypes = [ctypes.c_void_p, ctypes.c_int]
@@ -98,11 +102,13 @@ def oracle_lib():
 class Oracle:
     """CPU restatement of StepPhysics (gather order). The checker."""
 
-    def __init__(self, nx, ny, **overrides):
+    def __init__(self, nx, ny, integrator=VERLET, **overrides):
+        """integrator: VERLET (the reference's Verlet demo defaults), EULER / SEMI (its sibling demos' own defaults:
+        spring constants, mass 0.5, Provot pass on).  For the Euler variants `state()[1]` is V, not X_last."""
         L = oracle_lib()
         self.L = L
         self.p = OcoParams()
-        L.oco_default_params(ctypes.byref(self.p), nx, ny)
+        L.oco_default_params_for(ctypes.byref(self.p), nx, ny, integrator)
         self._apply(overrides)
         self.h = ctypes.c_void_p(L.oco_create(ctypes.byref(self.p)))
         assert self.h, "oco_create failed"
@@ -150,6 +156,9 @@ class Oracle:
     def energy(self):
         return self.L.oco_spring_energy(self.h)
 
+    def provot(self):
+        self.L.oco_provot(self.h)
+
     def tables(self):
         t = [np.empty(self.nx, np.float32) for _ in range(2)] + [np.empty(self.ny, np.float32) for _ in range(2)] + \
             [np.empty(self.nx, np.float32), np.empty(self.ny, np.float32)]
@@ -176,6 +185,46 @@ def have_ref():
 
 
 _ref = None
+_ref_variants = {}
+REF_VARIANT_SO = {EULER: os.path.join(ROOT, "oracle", "_ref", "libocref_euler.so"), SEMI: os.path.join(ROOT, "oracle", "_ref", "libocref_semi.so")}
+
+
+def have_ref_variant(integrator):
+    return os.path.exists(REF_VARIANT_SO[integrator])
+
+
+class RefVariant:
+    """Verbatim build of a sibling demo (explicit Euler / semi-implicit Euler): one global simulation; state = (X, V)."""
+
+    def __init__(self, integrator, nx, ny, provot=1):
+        if integrator not in _ref_variants:
+            L = ctypes.CDLL(REF_VARIANT_SO[integrator])
+            L.ref_num_particles.restype = ctypes.c_size_t
+            L.ref_get_state.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+            L.ref_set_state.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+            L.ref_get_params.argtypes = [ctypes.c_void_p]
+            _ref_variants[integrator] = L
+        self.L = _ref_variants[integrator]
+        assert self.L.ref_init(nx, ny) == 0
+        self.L.ref_set_provot(provot)
+        self.n = self.L.ref_num_particles()
+
+    def step(self, n=1):
+        self.L.ref_step(n)
+
+    def state(self):
+        x = np.empty((self.n, 3), np.float32)
+        v = np.empty((self.n, 3), np.float32)
+        self.L.ref_get_state(vp(x), vp(v))
+        return x, v
+
+    def set_state(self, x, v):
+        self.L.ref_set_state(vp(np.ascontiguousarray(x, np.float32)), vp(np.ascontiguousarray(v, np.float32)))
+
+    def params(self):
+        p = np.empty(16, np.float32)
+        self.L.ref_get_params(vp(p))
+        return p
 
 
 def ref_lib():
@@ -203,6 +252,10 @@ class Ref:
 
     def step(self, n=1):
         self.L.ref_step(n)
+
+    def step_provot(self, n=1):
+        """StepPhysics with the ApplyProvotDynamicInverse call of V:561 enabled."""
+        self.L.ref_step_provot(n)
 
     def state(self):
         x = np.empty((self.n, 3), np.float32)
@@ -258,6 +311,7 @@ def emu_lib():
         L.emu_halo_region.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                       ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_size_t)]
         L.emu_set_order.argtypes = [ctypes.c_int]
+        L.emu_set_provot_threads.argtypes = [ctypes.c_int]
         L.emu_band_link.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int]
         L.emu_bounding_sphere.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         L.emu_check_tiling.argtypes = [ctypes.c_int] * 10
