@@ -120,6 +120,9 @@ int oc_get_params(const oc_cloth* c, oc_params* p);
  * handle's band, cloth-major then row-major.  Replaces UploadCUDA(positions, positions_old, size)
  * (H:53) / UploadOpenCL (LH:155). */
 int oc_upload(oc_cloth* c, const float* X, const float* X_last, int stride_floats);
+/* (Pinned host arrays make the copies asynchronous.  For a whole single cloth the sequence oc_upload, oc_step(c, 1),
+ * oc_download is pipelined in row chunks inside the library — H2D of later rows, the step of the middle ones and D2H
+ * of the early ones overlap — so a host-resident simulation pays PCIe once, not twice, per step.) */
 
 /* n x StepPhysics(dt) (V:557-562; the body of the OnIdle step V:548-552 and of VerletCUDA H:81-100).
  * Asynchronous on the handle's stream. */
@@ -132,6 +135,14 @@ int oc_sync(oc_cloth* c);
  * VBO read (C:603-605) / ReadBuffer (LH:219). */
 int oc_download(oc_cloth* c, float* X, float* X_last, int stride_floats);
 
+/* Render hand-off.  oc_download(..., stride 4) is the float4 (x,y,z,1) vertex buffer of the
+ * reference's GPU back ends (pos_vbo, verlet_kernel.cu:193).  oc_download_normals adds the per-vertex normals the
+ * reference's lit demo computes (UpdateNormals, OpenCloth_ExplicitEuler_TextureMapped_Lit/.../main.cpp:684-707,
+ * over its triangle list :313-327): cross(p2-p1, p3-p1)/3 of every triangle summed into its vertices in list order,
+ * then normalised — history-free (the reference keeps adding onto the previous frame's normals; this is its first
+ * call).  stride 3 or 4 floats per vertex (w = 0); whole-cloth handles. */
+int oc_download_normals(oc_cloth* c, float* N, int stride_floats);
+
 /* ShutdownCUDA (H:27) / OnShutdown (V:418-424). */
 void oc_destroy(oc_cloth* c);
 
@@ -140,6 +151,21 @@ const char* oc_last_error(void);
 
 /* ---- interaction write-back (mouse drag, V:203-208): X[idx] = X_last[idx] = xyz ---------------- */
 int oc_set_particle(oc_cloth* c, int cloth, int idx, const float xyz[3]);
+/* n write-backs in one launch — the per-environment actions of a batch: particle idx[k] of cloth cloth[k] <- xyz[3k..3k+2] */
+int oc_set_particles(oc_cloth* c, int n, const int* cloth, const int* idx, const float* xyz);
+/* oc_upload / oc_download for ONE cloth of a batch (reset / observe one environment); arrays of rows*nx particles */
+int oc_upload_cloth(oc_cloth* c, int cloth, const float* X, const float* X_last, int stride_floats);
+int oc_download_cloth(oc_cloth* c, int cloth, float* X, float* X_last, int stride_floats);
+
+/* ---- run-time pin set ----------------------------------------------------------------------
+ * The reference pins particles 0 and numX by literal index tests (V:455 no gravity term, V:479-482 no spring force
+ * applied; the Provot pass leaves them where they are, V:498-501).  oc_set_pins replaces that set for one cloth of
+ * the batch (cloth = -1: every cloth) with the n linear indices idx[] (n = 0: nothing pinned); "pinned" keeps the
+ * reference's meaning.  A dragged particle (oc_set_particle) that should stay where it is put is pinned the same way.
+ * Rows holding a custom pin are stepped on the kernels' general (edge-row) path.  oc_reset_pins returns to the
+ * reference's two corners.  Row bands: the indices are those of the whole cloth; call it on every band. */
+int oc_set_pins(oc_cloth* c, int cloth, const int* idx, int n);
+int oc_reset_pins(oc_cloth* c);
 
 /* ---- stream / timing plumbing (the host side owns streams; torch passes its current stream) --- */
 /* Launch on the caller's stream (cudaStream_t).  NULL is CUDA's legacy default stream, as everywhere in the runtime

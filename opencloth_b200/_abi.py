@@ -70,9 +70,15 @@ SYMBOLS = {
     "oc_step": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "oc_sync": (ctypes.c_int, [ctypes.c_void_p]),
     "oc_download": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
+    "oc_download_normals": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
     "oc_destroy": (None, [ctypes.c_void_p]),
     "oc_last_error": (ctypes.c_char_p, []),
     "oc_set_particle": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, _P(ctypes.c_float)]),
+    "oc_set_particles": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _P(ctypes.c_int), _P(ctypes.c_int), _P(ctypes.c_float)]),
+    "oc_upload_cloth": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
+    "oc_download_cloth": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
+    "oc_set_pins": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _P(ctypes.c_int), ctypes.c_int]),
+    "oc_reset_pins": (ctypes.c_int, [ctypes.c_void_p]),
     "oc_set_stream": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "oc_reset_stream": (ctypes.c_int, [ctypes.c_void_p]),
     "oc_band_endpoint": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]),

@@ -85,6 +85,12 @@ class Cloth:
                                     xl.ctypes.data_as(ctypes.c_void_p), stride))
         return x, xl
 
+    def download_normals(self, stride=3):
+        """Per-vertex normals as the reference's lit demo computes them (UpdateNormals), shape (batch*ny*nx, stride)."""
+        n = np.empty((self.batch * self.ny * self.nx, stride), np.float32)
+        check(self._lib.oc_download_normals(self._h, n.ctypes.data_as(ctypes.c_void_p), stride))
+        return n
+
     def download_into(self, x_ptr, xl_ptr, stride=3):
         """Download into raw host pointers (ints), e.g. pinned torch tensors' data_ptr()."""
         check(self._lib.oc_download(self._h, ctypes.c_void_p(x_ptr), ctypes.c_void_p(xl_ptr) if xl_ptr else None, stride))
@@ -96,6 +102,7 @@ class Cloth:
         if x.size != self.n_local * stride or xl.size != x.size:
             raise ValueError(f"expected {self.n_local} x {stride} floats")
         check(self._lib.oc_upload(self._h, x.ctypes.data_as(ctypes.c_void_p), xl.ctypes.data_as(ctypes.c_void_p), stride))
+        # (pageable arrays: cudaMemcpyAsync has staged them before returning; nothing to wait for here)
 
     def upload_from(self, x_ptr, xl_ptr, stride=3):
         check(self._lib.oc_upload(self._h, ctypes.c_void_p(x_ptr), ctypes.c_void_p(xl_ptr), stride))
@@ -117,6 +124,35 @@ class Cloth:
         """Mouse-drag write-back of the reference (V:203-208): X[idx] = X_last[idx] = xyz."""
         v = (ctypes.c_float * 3)(*[float(t) for t in xyz])
         check(self._lib.oc_set_particle(self._h, int(cloth), int(idx), v))
+
+    def set_particles(self, cloths, indices, xyz):
+        """Many write-backs in one launch (per-environment actions of a batch)."""
+        n = len(indices)
+        a = (ctypes.c_int * max(1, n))(*[int(t) for t in cloths])
+        b = (ctypes.c_int * max(1, n))(*[int(t) for t in indices])
+        v = np.ascontiguousarray(xyz, np.float32).reshape(-1)
+        assert v.size == 3 * n
+        check(self._lib.oc_set_particles(self._h, n, a, b, v.ctypes.data_as(ctypes.POINTER(ctypes.c_float))))
+
+    def upload_cloth(self, cloth, x, x_last):
+        x = np.ascontiguousarray(x, np.float32); xl = np.ascontiguousarray(x_last, np.float32)
+        check(self._lib.oc_upload_cloth(self._h, int(cloth), x.ctypes.data_as(ctypes.c_void_p), xl.ctypes.data_as(ctypes.c_void_p), x.shape[-1]))
+        self.sync()          # x, xl are pageable temporaries
+
+    def download_cloth(self, cloth, stride=3):
+        n1 = self.rows * self.nx
+        x = np.empty((n1, stride), np.float32); xl = np.empty((n1, stride), np.float32)
+        check(self._lib.oc_download_cloth(self._h, int(cloth), x.ctypes.data_as(ctypes.c_void_p), xl.ctypes.data_as(ctypes.c_void_p), stride))
+        return x, xl
+
+    def set_pins(self, indices, cloth=-1):
+        """Replace the pinned set (the reference's literals 0 and numX, V:455, V:479-482) of one cloth (-1: all)."""
+        idx = [int(i) for i in indices]
+        arr = (ctypes.c_int * max(1, len(idx)))(*idx)
+        check(self._lib.oc_set_pins(self._h, int(cloth), arr, len(idx)))
+
+    def reset_pins(self):
+        check(self._lib.oc_reset_pins(self._h))
 
     def spring_energy(self, cloth=0):
         e = ctypes.c_double()

@@ -10,6 +10,7 @@
 #include "oc_host.h"
 #include "oc_gather.cuh"
 #include "oc_provot.cuh"
+#include "oc_normals.cuh"
 #include "oc_resident.cuh"
 #include "oc_march.cuh"
 #include "oc_march2.cuh"
@@ -66,6 +67,12 @@ struct oc_cloth {
     long long launches;
     float*    stage[2];          // device staging for upload/download
     size_t    stage_bytes;
+    cudaStream_t s_in, s_out;    // copy streams of the host <-> device pipeline (upload_impl)
+    struct {
+        cudaEvent_t ev_tail, ev_in[32], ev_step[32];
+        int up_chunks;           // an upload is queued in this many row chunks (events ev_in); 0: none pending
+        int step_chunks;         // the last substep was launched per chunk (events ev_step)
+    } pipe;
     double*   d_energy;
     unsigned long long* d_dbg;   // development counters (OC_DEBUG & 4)
     OcChain2  chain;             // tile-level dependencies between consecutive oc_k_march2 launches (oc_march2.cuh)
@@ -82,6 +89,11 @@ struct oc_cloth {
         unsigned  epoch;                // linked steps taken
     } link;
     unsigned* in_flags;          // device: 2 x OC_LINK_STRIPS words released by the neighbours' boundary tiles
+    // run-time pin sets (oc_set_pins): bitmap over batch x ny x nx particles + per-row summary; empty = reference default
+    std::vector<unsigned>* h_pins;
+    std::vector<unsigned char>* h_pin_rows;
+    unsigned* d_pins;
+    unsigned char* d_pin_rows;
 };
 #define OC_LINK_STRIPS 4096
 #define OC_CHAIN_CAP (1 << 16)
@@ -99,6 +111,9 @@ static int free_handle(oc_cloth* c)
     if (c->d_dbg) cudaFree(c->d_dbg);
     if (c->chain.flags) cudaFree(c->chain.flags);
     if (c->in_flags) cudaFree(c->in_flags);
+    if (c->d_pins) cudaFree(c->d_pins);
+    if (c->d_pin_rows) cudaFree(c->d_pin_rows);
+    delete c->h_pins; delete c->h_pin_rows;
     if (c->h_err) cudaFreeHost(c->h_err);
     for (int sd = 0; sd < 2; ++sd) for (int b = 0; b < 5; ++b) if (c->link.opened[sd][b]) cudaIpcCloseMemHandle(c->link.opened[sd][b]);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -106,6 +121,10 @@ static int free_handle(oc_cloth* c)
     if (c->ev_ready) cudaEventDestroy(c->ev_ready);
     if (c->ev_filled) cudaEventDestroy(c->ev_filled);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    if (c->s_in) cudaStreamDestroy(c->s_in);
+    if (c->s_out) cudaStreamDestroy(c->s_out);
+    if (c->pipe.ev_tail) cudaEventDestroy(c->pipe.ev_tail);
+    for (int k = 0; k < 32; ++k) { if (c->pipe.ev_in[k]) cudaEventDestroy(c->pipe.ev_in[k]); if (c->pipe.ev_step[k]) cudaEventDestroy(c->pipe.ev_step[k]); }
     delete c;
     return OC_OK;
 }
@@ -144,42 +163,49 @@ __global__ void oc_k_init(OcConst c, const float* __restrict__ xs, const float* 
     B[t] = c.integ == 0 ? v : make_float4(0.0f, 0.0f, 0.0f, oc_u2f(OC_W_PLAIN));      // X_last = X (V:259), or V = 0 (E:270)
 }
 
-// host layout (stride 3 or 4, owned rows only) -> float4 storage (owned rows inside the halo'd store)
-__global__ void oc_k_unpack(OcConst c, int row_begin, int rows, int stride,
-                            const float* __restrict__ X, const float* __restrict__ XL,
+// host layout (stride 3 or 4; cloths [hcloth0, ...) x owned rows, row-major) <-> float4 storage (owned rows inside the
+// halo'd store).  One launch covers rows [row0, row0 + rows) of cloths [cloth0, cloth0 + ncloth): the copies are cut
+// into row chunks that travel over PCIe while their neighbours are unpacked, stepped or packed (oc_upload).
+struct OcXfer { int cloth0, hcloth0, ncloth, row_own0, rows_own, row0, rows, stride; };
+__global__ void oc_k_unpack(OcConst c, OcXfer x, const float* __restrict__ X, const float* __restrict__ XL,
                             float4* __restrict__ A, float4* __restrict__ B)
 {
-    long long per = (long long)rows * c.U;
-    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= per * c.batch) return;
-    int b = (int)(t / per); long long r = t % per;
-    int j = (int)(r / c.U) + row_begin, i = (int)(r % c.U);
-    long long o = oc_index(c, b, i, j);
-    const float* x = X + t * stride; const float* l = XL + t * stride;
-    A[o] = make_float4(x[0], x[1], x[2], oc_u2f(OC_W_PLAIN));
-    B[o] = make_float4(l[0], l[1], l[2], oc_u2f(OC_W_PLAIN));
+    const long long per = (long long)x.rows * c.U;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= per * x.ncloth) return;
+    const int b = x.cloth0 + (int)(t / per); const long long r = t % per;
+    const int j = (int)(r / c.U) + x.row0, i = (int)(r % c.U);
+    const long long o = oc_index(c, b, i, j);
+    const long long h = (((long long)(b - x.hcloth0) * x.rows_own + (j - x.row_own0)) * c.U + i) * x.stride;
+    A[o] = make_float4(X[h], X[h + 1], X[h + 2], oc_u2f(OC_W_PLAIN));
+    B[o] = make_float4(XL[h], XL[h + 1], XL[h + 2], oc_u2f(OC_W_PLAIN));
 }
-
-__global__ void oc_k_pack(OcConst c, int row_begin, int rows, int stride,
-                          const float4* __restrict__ A, const float4* __restrict__ B,
+__global__ void oc_k_pack(OcConst c, OcXfer x, const float4* __restrict__ A, const float4* __restrict__ B,
                           float* __restrict__ X, float* __restrict__ XL)
 {
-    long long per = (long long)rows * c.U;
-    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= per * c.batch) return;
-    int b = (int)(t / per); long long r = t % per;
-    int j = (int)(r / c.U) + row_begin, i = (int)(r % c.U);
-    long long o = oc_index(c, b, i, j);
-    float4 a = A[o];
-    if (X) {
-        float* x = X + t * stride;
-        x[0] = a.x; x[1] = a.y; x[2] = a.z; if (stride == 4) x[3] = 1.0f;
-    }
+    const long long per = (long long)x.rows * c.U;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= per * x.ncloth) return;
+    const int b = x.cloth0 + (int)(t / per); const long long r = t % per;
+    const int j = (int)(r / c.U) + x.row0, i = (int)(r % c.U);
+    const long long o = oc_index(c, b, i, j);
+    const long long h = (((long long)(b - x.hcloth0) * x.rows_own + (j - x.row_own0)) * c.U + i) * x.stride;
+    const float4 a = A[o];
+    if (X) { X[h] = a.x; X[h + 1] = a.y; X[h + 2] = a.z; if (x.stride == 4) X[h + 3] = 1.0f; }
     if (XL) {
-        float4 q = oc_hit(a.w) ? a : B[o];                              // V:530 vs V:438
-        float* l = XL + t * stride;
-        l[0] = q.x; l[1] = q.y; l[2] = q.z; if (stride == 4) l[3] = 1.0f;
+        const float4 q = oc_hit(a.w) ? a : B[o];                        // V:530 vs V:438 (Euler integrators: B is V, never flagged)
+        XL[h] = q.x; XL[h + 1] = q.y; XL[h + 2] = q.z; if (x.stride == 4) XL[h + 3] = 1.0f;
     }
+}
+
+struct OcPoke { long long o; float x, y, z; int pad; };
+__global__ void oc_k_set_particles(float4* A, float4* B, const OcPoke* __restrict__ p, int n, int xv)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const OcPoke q = p[t];
+    const float4 v = make_float4(q.x, q.y, q.z, oc_u2f(OC_W_PLAIN));
+    A[q.o] = v; B[q.o] = xv ? make_float4(0.0f, 0.0f, 0.0f, oc_u2f(OC_W_PLAIN)) : v;
 }
 
 __global__ void oc_k_set_particle(float4* A, float4* B, long long o, float x, float y, float z, int xv)
@@ -309,6 +335,13 @@ extern "C" int oc_create(oc_cloth** out, const oc_params* p)
     OC_CREATE_CUDA(cudaHostGetDevicePointer(&k.err, c->h_err, 0));
     OC_CREATE_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
+    OC_CREATE_CUDA(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
+    OC_CREATE_CUDA(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
+    OC_CREATE_CUDA(cudaEventCreateWithFlags(&c->pipe.ev_tail, cudaEventDisableTiming));
+    for (int q = 0; q < 32; ++q) {
+        OC_CREATE_CUDA(cudaEventCreateWithFlags(&c->pipe.ev_in[q], cudaEventDisableTiming));
+        OC_CREATE_CUDA(cudaEventCreateWithFlags(&c->pipe.ev_step[q], cudaEventDisableTiming));
+    }
     OC_CREATE_CUDA(cudaEventCreate(&c->ev0));
     OC_CREATE_CUDA(cudaEventCreate(&c->ev1));
     OC_CREATE_CUDA(cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming));
@@ -399,7 +432,10 @@ extern "C" int oc_sync(oc_cloth* c)
 {
     if (!c) return oc_fail(OC_ERR_INVALID, "oc_sync: null");
     OC_CUDA(cudaSetDevice(c->dev));
-    const cudaError_t e = cudaStreamSynchronize(c->stream);
+    cudaError_t e = cudaStreamSynchronize(c->s_in);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->s_out);
+    c->pipe.up_chunks = 0;                 // everything has landed: nothing left to wait for chunk by chunk
     const int rc = check_err_word(c);
     if (rc) return rc;
     OC_CUDA(e);
@@ -412,6 +448,9 @@ extern "C" int oc_sync(oc_cloth* c)
 static int ensure_stage(oc_cloth* c, size_t bytes)
 {
     if (c->stage_bytes >= bytes) return OC_OK;
+    OC_CUDA(cudaStreamSynchronize(c->s_in));
+    OC_CUDA(cudaStreamSynchronize(c->s_out));
+    OC_CUDA(cudaStreamSynchronize(c->stream));
     if (c->stage[0]) cudaFree(c->stage[0]);
     if (c->stage[1]) cudaFree(c->stage[1]);
     c->stage[0] = c->stage[1] = nullptr; c->stage_bytes = 0;
@@ -421,43 +460,184 @@ static int ensure_stage(oc_cloth* c, size_t bytes)
     return OC_OK;
 }
 
-extern "C" int oc_upload(oc_cloth* c, const float* X, const float* X_last, int stride)
+// The host <-> device pipeline.  A cloth that arrives from the host, takes one step and goes back
+// (oc_upload, oc_step(1), oc_download — the end-to-end pattern of bench.py and of a host application that owns the
+// state) would spend its time on PCIe one direction at a time.  The three calls therefore work on row CHUNKS:
+//   oc_upload    per chunk, on a copy stream: H2D of the chunk's X and X_last rows, unpack into the float4 buffers, event
+//   oc_step      the first substep after an upload is launched chunk by chunk; chunk c waits for the upload event of
+//                chunk c+1 (its stencil reaches two rows into it) and records its own event
+//   oc_download  per chunk, on a second copy stream: waits for the chunk's step event, packs, D2H
+// so that the H2D of the later chunks, the step of the middle ones and the D2H of the early ones overlap (PCIe is
+// full duplex).  Whole single cloths only; other handles, and any other order of calls, take the plain path.
+#define OC_PIPE_MAX_CHUNKS 32
+static int pipe_chunks(const oc_cloth* c)
 {
-    if (!c || !X || !X_last) return oc_fail(OC_ERR_INVALID, "oc_upload: null");
-    if (stride != 3 && stride != 4) return oc_fail(OC_ERR_INVALID, "stride_floats must be 3 or 4");
-    OC_CUDA(cudaSetDevice(c->dev));
-    chain_break(c);
-    long long n = (long long)c->p.batch * c->rows_own * c->p.nx;
-    size_t bytes = (size_t)n * stride * sizeof(float);
-    int rc = ensure_stage(c, bytes);
-    if (rc) return rc;
-    OC_CUDA(cudaMemcpyAsync(c->stage[0], X, bytes, cudaMemcpyHostToDevice, c->stream));
-    OC_CUDA(cudaMemcpyAsync(c->stage[1], X_last, bytes, cudaMemcpyHostToDevice, c->stream));
-    oc_k_unpack<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->k, c->p.row_begin, c->rows_own, stride,
-                                                                    c->stage[0], c->stage[1], c->buf[c->q.ia], c->buf[c->q.ib]);
-    c->launches++;
-    OC_CUDA(cudaGetLastError());
-    if (c->q.band) c->q.fresh = c->q.kmax;     // halos are stale until the host exchanges them
+    static const int env = getenv("OC_PIPE_CHUNKS") ? atoi(getenv("OC_PIPE_CHUNKS")) : 0;
+    if (c->p.batch != 1 || c->q.band) return 1;
+    int n = env > 0 ? env : 16;
+    if (n > OC_PIPE_MAX_CHUNKS) n = OC_PIPE_MAX_CHUNKS;
+    while (n > 1 && c->rows_own / n < 64) n /= 2;          // chunks of at least 64 rows
+    return n;
+}
+static void chunk_rows(const oc_cloth* c, int nch, int k, int* r0, int* r1)
+{
+    *r0 = c->p.row_begin + (int)((long long)c->rows_own * k / nch);
+    *r1 = c->p.row_begin + (int)((long long)c->rows_own * (k + 1) / nch);
+}
+// every queued chunk of an upload has landed as far as the compute stream is concerned
+static int join_upload(oc_cloth* c)
+{
+    if (c->pipe.up_chunks > 0) {
+        OC_CUDA(cudaStreamWaitEvent(c->stream, c->pipe.ev_in[c->pipe.up_chunks - 1], 0));
+        c->pipe.up_chunks = 0;
+    }
+    c->pipe.step_chunks = 0;
     return OC_OK;
 }
 
+static int upload_impl(oc_cloth* c, int cloth0, int ncloth, const float* X, const float* X_last, int stride)
+{
+    if (stride != 3 && stride != 4) return oc_fail(OC_ERR_INVALID, "stride_floats must be 3 or 4");
+    OC_CUDA(cudaSetDevice(c->dev));
+    chain_break(c);
+    int rc = join_upload(c);
+    if (rc) return rc;
+    const long long n = (long long)ncloth * c->rows_own * c->p.nx;
+    rc = ensure_stage(c, (size_t)c->p.batch * c->rows_own * c->p.nx * 4 * sizeof(float));
+    if (rc) return rc;
+    const int nch = (ncloth == c->p.batch) ? pipe_chunks(c) : 1;
+    // the copy stream starts after everything queued so far (the buffers may still be in use)
+    OC_CUDA(cudaEventRecord(c->pipe.ev_tail, c->stream));
+    OC_CUDA(cudaStreamWaitEvent(c->s_in, c->pipe.ev_tail, 0));
+    for (int k = 0; k < nch; ++k) {
+        int r0, r1;
+        chunk_rows(c, nch, k, &r0, &r1);
+        const size_t off = (size_t)(r0 - c->p.row_begin) * c->p.nx * stride;            // floats; nch > 1 only for one cloth
+        const size_t cnt = (nch == 1) ? (size_t)n * stride : (size_t)(r1 - r0) * c->p.nx * stride;
+        OC_CUDA(cudaMemcpyAsync(c->stage[0] + off, X + off, cnt * sizeof(float), cudaMemcpyHostToDevice, c->s_in));
+        OC_CUDA(cudaMemcpyAsync(c->stage[1] + off, X_last + off, cnt * sizeof(float), cudaMemcpyHostToDevice, c->s_in));
+        const OcXfer x = { cloth0, cloth0, ncloth, c->p.row_begin, c->rows_own, r0, r1 - r0, stride };
+        const long long m = (long long)ncloth * (r1 - r0) * c->p.nx;
+        oc_k_unpack<<<(unsigned)((m + 255) / 256), 256, 0, c->s_in>>>(c->k, x, c->stage[0], c->stage[1], c->buf[c->q.ia], c->buf[c->q.ib]);
+        c->launches++;
+        OC_CUDA(cudaGetLastError());
+        OC_CUDA(cudaEventRecord(c->pipe.ev_in[k], c->s_in));
+    }
+    c->pipe.up_chunks = nch;
+    if (c->q.band && !c->q.linked) c->q.fresh = c->q.kmax;     // halos are stale until the host exchanges them
+    return OC_OK;
+}
+
+extern "C" int oc_upload(oc_cloth* c, const float* X, const float* X_last, int stride)
+{
+    if (!c || !X || !X_last) return oc_fail(OC_ERR_INVALID, "oc_upload: null");
+    return upload_impl(c, 0, c->p.batch, X, X_last, stride);
+}
+extern "C" int oc_upload_cloth(oc_cloth* c, int cloth, const float* X, const float* X_last, int stride)
+{
+    if (!c || !X || !X_last) return oc_fail(OC_ERR_INVALID, "oc_upload_cloth: null");
+    if (cloth < 0 || cloth >= c->p.batch) return oc_fail(OC_ERR_INVALID, "oc_upload_cloth: cloth %d of %d", cloth, c->p.batch);
+    return upload_impl(c, cloth, 1, X, X_last, stride);
+}
+
+static int download_impl(oc_cloth* c, int cloth0, int ncloth, float* X, float* X_last, int stride)
+{
+    if (stride != 3 && stride != 4) return oc_fail(OC_ERR_INVALID, "stride_floats must be 3 or 4");
+    OC_CUDA(cudaSetDevice(c->dev));
+    int rc = ensure_stage(c, (size_t)c->p.batch * c->rows_own * c->p.nx * 4 * sizeof(float));
+    if (rc) return rc;
+    const long long n = (long long)ncloth * c->rows_own * c->p.nx;
+    // chunk events of a step that was launched chunk by chunk (oc_step right after oc_upload): follow them; otherwise
+    // wait for the whole compute stream once
+    const bool piped = c->pipe.step_chunks > 1 && ncloth == c->p.batch;
+    const int nch = piped ? c->pipe.step_chunks : ((ncloth == c->p.batch) ? pipe_chunks(c) : 1);
+    if (!piped) {
+        rc = join_upload(c);
+        if (rc) return rc;
+        OC_CUDA(cudaEventRecord(c->pipe.ev_tail, c->stream));
+        OC_CUDA(cudaStreamWaitEvent(c->s_out, c->pipe.ev_tail, 0));
+    }
+    for (int k = 0; k < nch; ++k) {
+        int r0, r1;
+        chunk_rows(c, nch, k, &r0, &r1);
+        if (piped) OC_CUDA(cudaStreamWaitEvent(c->s_out, c->pipe.ev_step[k], 0));
+        const OcXfer x = { cloth0, cloth0, ncloth, c->p.row_begin, c->rows_own, r0, r1 - r0, stride };
+        const long long m = (long long)ncloth * (r1 - r0) * c->p.nx;
+        oc_k_pack<<<(unsigned)((m + 255) / 256), 256, 0, c->s_out>>>(c->k, x, c->buf[c->q.ia], c->buf[c->q.ib],
+                                                                     X ? c->stage[0] : nullptr, X_last ? c->stage[1] : nullptr);
+        c->launches++;
+        OC_CUDA(cudaGetLastError());
+        const size_t off = (size_t)(r0 - c->p.row_begin) * c->p.nx * stride;
+        const size_t cnt = (nch == 1) ? (size_t)n * stride : (size_t)(r1 - r0) * c->p.nx * stride;
+        if (X) OC_CUDA(cudaMemcpyAsync(X + off, c->stage[0] + off, cnt * sizeof(float), cudaMemcpyDeviceToHost, c->s_out));
+        if (X_last) OC_CUDA(cudaMemcpyAsync(X_last + off, c->stage[1] + off, cnt * sizeof(float), cudaMemcpyDeviceToHost, c->s_out));
+    }
+    c->pipe.step_chunks = 0;
+    // the compute stream must not run ahead of the packing (the next step overwrites what it reads)
+    OC_CUDA(cudaEventRecord(c->pipe.ev_tail, c->s_out));
+    OC_CUDA(cudaStreamWaitEvent(c->stream, c->pipe.ev_tail, 0));
+    return oc_sync(c);
+}
 extern "C" int oc_download(oc_cloth* c, float* X, float* X_last, int stride)
 {
     if (!c) return oc_fail(OC_ERR_INVALID, "oc_download: null");
+    return download_impl(c, 0, c->p.batch, X, X_last, stride);
+}
+extern "C" int oc_download_cloth(oc_cloth* c, int cloth, float* X, float* X_last, int stride)
+{
+    if (!c) return oc_fail(OC_ERR_INVALID, "oc_download_cloth: null");
+    if (cloth < 0 || cloth >= c->p.batch) return oc_fail(OC_ERR_INVALID, "oc_download_cloth: cloth %d of %d", cloth, c->p.batch);
+    return download_impl(c, cloth, 1, X, X_last, stride);
+}
+
+// Render hand-off: per-vertex normals of the current state (oc_normals.cuh), to host memory.
+extern "C" int oc_download_normals(oc_cloth* c, float* N, int stride)
+{
+    if (!c || !N) return oc_fail(OC_ERR_INVALID, "oc_download_normals: null");
     if (stride != 3 && stride != 4) return oc_fail(OC_ERR_INVALID, "stride_floats must be 3 or 4");
+    if (c->q.band) return oc_fail(OC_ERR_UNSUPPORTED, "oc_download_normals: whole-cloth handles only (a band lacks its neighbours' rows)");
     OC_CUDA(cudaSetDevice(c->dev));
-    long long n = (long long)c->p.batch * c->rows_own * c->p.nx;
-    size_t bytes = (size_t)n * stride * sizeof(float);
-    int rc = ensure_stage(c, bytes);
+    int rc = join_upload(c);
     if (rc) return rc;
-    oc_k_pack<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->k, c->p.row_begin, c->rows_own, stride,
-                                                                  c->buf[c->q.ia], c->buf[c->q.ib],
-                                                                  X ? c->stage[0] : nullptr, X_last ? c->stage[1] : nullptr);
+    rc = ensure_stage(c, (size_t)c->p.batch * c->rows_own * c->p.nx * 4 * sizeof(float));
+    if (rc) return rc;
+    dim3 blk(128, 1, 1), grd((c->p.nx + 127) / 128, c->p.ny, c->p.batch);
+    oc_k_normals<<<grd, blk, 0, c->stream>>>(c->k, c->buf[c->q.ia], c->stage[0], stride);
     c->launches++;
     OC_CUDA(cudaGetLastError());
-    if (X) OC_CUDA(cudaMemcpyAsync(X, c->stage[0], bytes, cudaMemcpyDeviceToHost, c->stream));
-    if (X_last) OC_CUDA(cudaMemcpyAsync(X_last, c->stage[1], bytes, cudaMemcpyDeviceToHost, c->stream));
+    OC_CUDA(cudaMemcpyAsync(N, c->stage[0], (size_t)c->p.batch * c->p.ny * c->p.nx * stride * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     return oc_sync(c);
+}
+
+// Many write-backs in one launch: the per-environment actions of a batch (cloth[k], idx[k]) <- xyz[3k..3k+2], V:203-208 each.
+extern "C" int oc_set_particles(oc_cloth* c, int n, const int* cloth, const int* idx, const float* xyz)
+{
+    if (!c || n < 0 || (n > 0 && (!cloth || !idx || !xyz))) return oc_fail(OC_ERR_INVALID, "oc_set_particles: null");
+    if (n == 0) return OC_OK;
+    OC_CUDA(cudaSetDevice(c->dev));
+    std::vector<OcPoke> pk;
+    pk.reserve((size_t)n);
+    for (int k = 0; k < n; ++k) {
+        if (cloth[k] < 0 || cloth[k] >= c->p.batch || idx[k] < 0 || idx[k] >= c->p.nx * c->p.ny)
+            return oc_fail(OC_ERR_INVALID, "oc_set_particles: entry %d: cloth %d / index %d out of range", k, cloth[k], idx[k]);
+        const int j = idx[k] / c->p.nx, i = idx[k] % c->p.nx;
+        if (j < c->k.row_lo || j >= c->k.row_lo + c->k.srows) continue;            // not stored by this band
+        OcPoke q = { oc_index(c->k, cloth[k], i, j), xyz[3 * k], xyz[3 * k + 1], xyz[3 * k + 2], 0 };
+        pk.push_back(q);
+    }
+    chain_break(c);
+    int rc = join_upload(c);
+    if (rc) return rc;
+    if (pk.empty()) return OC_OK;
+    OcPoke* d = nullptr;
+    OC_CUDA(cudaMallocAsync(&d, pk.size() * sizeof(OcPoke), c->stream));
+    OC_CUDA(cudaMemcpyAsync(d, pk.data(), pk.size() * sizeof(OcPoke), cudaMemcpyHostToDevice, c->stream));
+    oc_k_set_particles<<<(unsigned)((pk.size() + 127) / 128), 128, 0, c->stream>>>(c->buf[c->q.ia], c->buf[c->q.ib], d, (int)pk.size(), c->q.xv ? 1 : 0);
+    c->launches++;
+    OC_CUDA(cudaGetLastError());
+    OC_CUDA(cudaFreeAsync(d, c->stream));
+    OC_CUDA(cudaStreamSynchronize(c->stream));                                    // pk is pageable host memory
+    return OC_OK;
 }
 
 extern "C" int oc_set_particle(oc_cloth* c, int cloth, int idx, const float xyz[3])
@@ -469,9 +649,62 @@ extern "C" int oc_set_particle(oc_cloth* c, int cloth, int idx, const float xyz[
     int j = idx / c->p.nx, i = idx % c->p.nx;
     if (j < c->k.row_lo || j >= c->k.row_lo + c->k.srows) return OC_OK;      // not stored by this band
     OC_CUDA(cudaSetDevice(c->dev));
+    { const int rcj = join_upload(c); if (rcj) return rcj; }
     oc_k_set_particle<<<1, 1, 0, c->stream>>>(c->buf[c->q.ia], c->buf[c->q.ib], oc_index(c->k, cloth, i, j), xyz[0], xyz[1], xyz[2], c->q.xv ? 1 : 0);
     c->launches++;
     OC_CUDA(cudaGetLastError());
+    return OC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// run-time pin sets
+// ------------------------------------------------------------------------------------------------
+static void pins_set_bit(oc_cloth* c, int cloth, int idx, bool on)
+{
+    const long long per = (long long)c->p.nx * c->p.ny;
+    const long long bit = cloth * per + idx;
+    if (on) (*c->h_pins)[bit >> 5] |= 1u << (bit & 31); else (*c->h_pins)[bit >> 5] &= ~(1u << (bit & 31));
+}
+extern "C" int oc_set_pins(oc_cloth* c, int cloth, const int* idx, int n)
+{
+    if (!c) return oc_fail(OC_ERR_INVALID, "oc_set_pins: null");
+    if (cloth < -1 || cloth >= c->p.batch) return oc_fail(OC_ERR_INVALID, "oc_set_pins: cloth %d of %d", cloth, c->p.batch);
+    if (n < 0 || (n > 0 && !idx)) return oc_fail(OC_ERR_INVALID, "oc_set_pins: bad index list");
+    const int U = c->p.nx, V = c->p.ny, B = c->p.batch;
+    const long long per = (long long)U * V;
+    for (int k = 0; k < n; ++k) if (idx[k] < 0 || idx[k] >= per) return oc_fail(OC_ERR_INVALID, "oc_set_pins: index %d out of range", idx[k]);
+    OC_CUDA(cudaSetDevice(c->dev));
+    const size_t words = (size_t)((per * B + 31) / 32);
+    if (!c->h_pins) {
+        c->h_pins = new std::vector<unsigned>(words, 0u);
+        c->h_pin_rows = new std::vector<unsigned char>((size_t)B * V, 0);
+        for (int b = 0; b < B; ++b) { pins_set_bit(c, b, 0, true); pins_set_bit(c, b, U - 1, true); (*c->h_pin_rows)[(size_t)b * V] = 1; }   // V:455
+        OC_CUDA(cudaMalloc(&c->d_pins, words * sizeof(unsigned)));
+        OC_CUDA(cudaMalloc(&c->d_pin_rows, (size_t)B * V));
+    }
+    for (int b = (cloth < 0 ? 0 : cloth); b < (cloth < 0 ? B : cloth + 1); ++b) {
+        for (long long q = 0; q < per; ++q) pins_set_bit(c, b, (int)q, false);
+        for (int j = 0; j < V; ++j) (*c->h_pin_rows)[(size_t)b * V + j] = 0;
+        for (int k = 0; k < n; ++k) { pins_set_bit(c, b, idx[k], true); (*c->h_pin_rows)[(size_t)b * V + idx[k] / U] = 1; }
+    }
+    chain_break(c);
+    OC_CUDA(cudaStreamSynchronize(c->stream));                      // kernels in flight still read the old set
+    OC_CUDA(cudaMemcpy(c->d_pins, c->h_pins->data(), words * sizeof(unsigned), cudaMemcpyHostToDevice));
+    OC_CUDA(cudaMemcpy(c->d_pin_rows, c->h_pin_rows->data(), (size_t)B * V, cudaMemcpyHostToDevice));
+    c->k.pins = c->d_pins; c->k.pin_rows = c->d_pin_rows;
+    return OC_OK;
+}
+extern "C" int oc_reset_pins(oc_cloth* c)
+{
+    if (!c) return oc_fail(OC_ERR_INVALID, "oc_reset_pins: null");
+    OC_CUDA(cudaSetDevice(c->dev));
+    chain_break(c);
+    OC_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->d_pins) cudaFree(c->d_pins);
+    if (c->d_pin_rows) cudaFree(c->d_pin_rows);
+    delete c->h_pins; delete c->h_pin_rows;
+    c->d_pins = nullptr; c->d_pin_rows = nullptr; c->h_pins = nullptr; c->h_pin_rows = nullptr;
+    c->k.pins = nullptr; c->k.pin_rows = nullptr;
     return OC_OK;
 }
 
@@ -590,6 +823,28 @@ static int step_impl(oc_cloth* c, int n, cudaStream_t split_stream, bool want_sp
     OC_CUDA(cudaSetDevice(c->dev));
     const int kern = pick_kernel(c);
     const int kdef = c->p.substeps_per_launch > 0 ? c->p.substeps_per_launch : 1;
+    // host <-> device pipeline (upload_impl): the first substep after a chunked upload follows the chunks
+    c->pipe.step_chunks = 0;
+    const bool pipe_first = c->pipe.up_chunks > 1 && n >= 1 && !c->p.provot && !c->q.band && c->p.batch == 1 &&
+                            (kern == OC_KERNEL_MARCH2 || kern == OC_KERNEL_GATHER);
+    if (!pipe_first) { const int rcj = join_upload(c); if (rcj) return rcj; }
+    if (pipe_first) {
+        const int nch = c->pipe.up_chunks, n_call = n;
+        OcLaunch L;
+        oc_host_next_launch(c->q, n, 1, L);
+        for (int k = 0; k < nch; ++k) {
+            int r0, r1;
+            chunk_rows(c, nch, k, &r0, &r1);
+            OC_CUDA(cudaStreamWaitEvent(c->stream, c->pipe.ev_in[k + 1 < nch ? k + 1 : k], 0));      // the stencil reaches 2 rows into the next chunk
+            chain_break(c);
+            const int rc = launch_rows(c, kern, L, r0, r1);
+            if (rc) return rc;
+            OC_CUDA(cudaEventRecord(c->pipe.ev_step[k], c->stream));
+        }
+        chain_break(c);
+        c->pipe.up_chunks = 0;
+        c->pipe.step_chunks = (n_call == 1) ? nch : 0;         // a download that follows directly may go chunk by chunk
+    }
     while (n > 0) {
         int kmaxS = (kern == OC_KERNEL_MARCH) ? oc_host_pick_stages(n < kdef ? n : kdef) : (kern == OC_KERNEL_RESIDENT ? OC_RESIDENT_MAX_STEPS : 1);
         if (c->p.provot || c->q.xv) kmaxS = 1;                    // the Provot pass follows every substep; (X, V) steps are single

@@ -39,7 +39,7 @@ OC_HD float4 oc_gather_particle(const OcConst& c, const float4* __restrict__ A, 
     f3 xm = make_f3(a.x, a.y, a.z);
     f3 d  = kXV ? make_f3(0.0f, 0.0f, 0.0f) : oc_delta<M>(a, q);
     f3 vm = kXV ? make_f3(q.x, q.y, q.z) : M::velocity(d, c);
-    bool pinned = oc_pinned(c, i, j);
+    bool pinned = oc_pinned(c, b, i, j);
     f3 F = oc_base_force<M>(c, vm, pinned);
     if (!pinned) {
         // structural horizontal (V:288-291)

@@ -253,7 +253,7 @@ struct OcMarch {
         // ---- G phase: gather in the reference's order, integrate, collide, hand on ------------------
         const bool doG = kSteady || (row >= lo_s && row < hi_s);
         if (doG) {
-            const bool pinned = !kSteady && oc_pinned(c, gi, row);
+            const bool pinned = !kSteady && oc_pinned(c, ctx.bz(), gi, row);
             // F = 0 + gravity*mass (unless pinned) + DEFAULT_DAMPING*V     V:451-459
             OcF F;
             F.xy = pinned ? p_bc(0.0f) : make_float2(c.f0[0], c.f0[1]);
@@ -399,6 +399,7 @@ OC_HD void oc_march_body(Ctx& ctx, const OcConst& c,
     int st_lo = lo_s > plo_s + 1 ? lo_s : plo_s + 1; if (st_lo < 2) st_lo = 2;
     int st_hi = hi_s < V - 3 ? hi_s : V - 3;
     if (s == 0 && st_hi > in_hi - OC_MARCH_LAG) st_hi = in_hi - OC_MARCH_LAG;
+    if (st_lo < st_hi && !oc_rows_unpinned(c, ctx.bz(), st_lo, st_hi)) st_hi = st_lo;      // custom pins in these rows: generic path only
     int it_lo = st_lo - row0, it_hi = st_hi - row0;            // steady for it in [it_lo, it_hi)
     if (it_lo < 0) it_lo = 0;
     if (it_hi > n_it) it_hi = n_it;

@@ -373,7 +373,7 @@ struct OcMarch2 {
         if (doG) {
             constexpr bool kAll = kSteady;           // no predicates: edge columns are handled by the zero masks above
             const int gb = ga + 1;
-            const bool pin_a = !kSteady && oc_pinned(c, ga, row), pin_b = !kSteady && oc_pinned(c, gb, row);
+            const bool pin_a = !kSteady && oc_pinned(c, ctx.bz(), ga, row), pin_b = !kSteady && oc_pinned(c, ctx.bz(), gb, row);
             const bool ea = !pin_a, eb = !pin_b;                                  // springs act on the particle
             // existence of the horizontal neighbours of a and of b
             const bool al1 = kAll || ga - 1 >= 0, al2 = kAll || ga - 2 >= 0, ar1 = kAll || gb < U, ar2 = kAll || ga + 2 < U;
@@ -714,6 +714,7 @@ OC_HD bool oc_march2_body(Ctx& ctx, const OcConst& c, const float4* __restrict__
     // linked row bands: the two rows pushed into a neighbour's halo are taken on the generic path
     if (dep.peer.c[0] && st_lo < dep.peer.ra + 2) st_lo = dep.peer.ra + 2;
     if (dep.peer.c[1] && st_hi > dep.peer.rb - 2) st_hi = dep.peer.rb - 2;
+    if (st_lo < st_hi && !oc_rows_unpinned(c, ctx.bz(), st_lo, st_hi)) st_hi = st_lo;      // custom pins (oc_set_pins) in these rows: generic path only
     int it_lo = st_lo - row0, it_hi = st_hi - row0;
     if (it_lo < 0) it_lo = 0;
     if (it_hi > n_it) it_hi = n_it;

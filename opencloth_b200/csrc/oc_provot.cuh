@@ -46,7 +46,7 @@ template <class M>
 OC_HD void oc_provot_v_term(const OcConst& c, const float4* __restrict__ X, int b, int i, int j, int ni, int nj,
                             bool me_is_p1, float rest, f3 xm, bool pin_me, f3& v)
 {
-    const bool pin_q = oc_pinned(c, ni, nj);
+    const bool pin_q = oc_pinned(c, b, ni, nj);
     const bool upd = me_is_p1 ? !pin_me : (pin_q || !pin_me);
     if (!upd) return;
     const float4 a = X[oc_index(c, b, ni, nj)];
@@ -64,7 +64,7 @@ OC_HD float4 oc_provot_v_particle(const OcConst& c, const float4* __restrict__ X
     float4 vv = Vb[me];
     const f3 xm = make_f3(a.x, a.y, a.z);
     f3 v = make_f3(vv.x, vv.y, vv.z);
-    const bool pin = oc_pinned(c, i, j);
+    const bool pin = oc_pinned(c, b, i, j);
     // the order in which the spring list touches the particle (as in oc_gather_particle); first ends: the left / upper
     // particle of a structural or bend spring, the upper-left of a "\" shear spring, the LOWER-left of a "/" one (V:304)
     if (i - 1 >= 0) oc_provot_v_term<M>(c, X, b, i, j, i - 1, j, false, c.rh1[i - 1], xm, pin, v);
@@ -125,7 +125,7 @@ OC_HD void oc_provot_row(const OcConst& c, float4* X, int b, int j)
         f3 p = oc_ld3(row);
         for (int i = 0; i + 1 < U; ++i) {
             f3 q = oc_ld3(row + i + 1);
-            oc_provot_x_spring<M>(p, q, oc_pinned(c, i, j), oc_pinned(c, i + 1, j), rest[i]);
+            oc_provot_x_spring<M>(p, q, oc_pinned(c, b, i, j), oc_pinned(c, b, i + 1, j), rest[i]);
             oc_st3(row + i, p);
             p = q;
         }
@@ -134,8 +134,8 @@ OC_HD void oc_provot_row(const OcConst& c, float4* X, int b, int j)
         f3 p0 = oc_ld3(row), p1 = oc_ld3(row + 1);
         for (int i = 0; i + 2 < U; ++i) {
             f3 q = oc_ld3(row + i + 2);
-            oc_provot_x_spring<M>(p0, q, oc_pinned(c, i, j), oc_pinned(c, i + 2, j), rest[i]);
-            if (i == U - 3) oc_provot_x_spring<M>(p0, q, oc_pinned(c, i, j), oc_pinned(c, i + 2, j), rest[i]);       // V:313
+            oc_provot_x_spring<M>(p0, q, oc_pinned(c, b, i, j), oc_pinned(c, b, i + 2, j), rest[i]);
+            if (i == U - 3) oc_provot_x_spring<M>(p0, q, oc_pinned(c, b, i, j), oc_pinned(c, b, i + 2, j), rest[i]);       // V:313
             oc_st3(row + i, p0);
             p0 = p1; p1 = q;
         }
@@ -153,7 +153,7 @@ OC_HD void oc_provot_col(const OcConst& c, float4* X, int b, int i)
         f3 p = oc_ld3(col);
         for (int j = 0; j + 1 < V; ++j) {
             f3 q = oc_ld3(col + (long long)(j + 1) * U);
-            oc_provot_x_spring<M>(p, q, oc_pinned(c, i, j), oc_pinned(c, i, j + 1), rest[j]);
+            oc_provot_x_spring<M>(p, q, oc_pinned(c, b, i, j), oc_pinned(c, b, i, j + 1), rest[j]);
             oc_st3(col + (long long)j * U, p);
             p = q;
         }
@@ -162,8 +162,8 @@ OC_HD void oc_provot_col(const OcConst& c, float4* X, int b, int i)
         f3 p0 = oc_ld3(col), p1 = oc_ld3(col + U);
         for (int j = 0; j + 2 < V; ++j) {
             f3 q = oc_ld3(col + (long long)(j + 2) * U);
-            oc_provot_x_spring<M>(p0, q, oc_pinned(c, i, j), oc_pinned(c, i, j + 2), rest[j]);
-            if (j == V - 3) oc_provot_x_spring<M>(p0, q, oc_pinned(c, i, j), oc_pinned(c, i, j + 2), rest[j]);       // V:319
+            oc_provot_x_spring<M>(p0, q, oc_pinned(c, b, i, j), oc_pinned(c, b, i, j + 2), rest[j]);
+            if (j == V - 3) oc_provot_x_spring<M>(p0, q, oc_pinned(c, b, i, j), oc_pinned(c, b, i, j + 2), rest[j]);       // V:319
             oc_st3(col + (long long)j * U, p0);
             p0 = p1; p1 = q;
         }
@@ -193,8 +193,8 @@ OC_HD void oc_provot_shear_body(Ctx& ctx, const OcConst& c, float4* X)
                 const float rest = M::sqrt(M::add(c.dx2[col], dz2));
                 f3 a = oc_ld3(up + col), bq = oc_ld3(up + col + 1), cq = oc_ld3(dn + col), d = oc_ld3(dn + col + 1);
                 // (col, r) -> (col+1, r+1), then (col, r+1) -> (col+1, r)            V:303-304
-                oc_provot_x_spring<M>(a, d, oc_pinned(c, col, r), false, rest);
-                oc_provot_x_spring<M>(cq, bq, false, oc_pinned(c, col + 1, r), rest);
+                oc_provot_x_spring<M>(a, d, oc_pinned(c, b, col, r), oc_pinned(c, b, col + 1, r + 1), rest);
+                oc_provot_x_spring<M>(cq, bq, oc_pinned(c, b, col, r + 1), oc_pinned(c, b, col + 1, r), rest);
                 oc_st3(up + col, a); oc_st3(up + col + 1, bq); oc_st3(dn + col, cq); oc_st3(dn + col + 1, d);
             }
             ctx.sync();

@@ -109,7 +109,7 @@ OC_HD void oc_resident_body(Ctx& ctx, const OcConst& c, const float4* __restrict
             const f3 xm = make_f3(s.X(0)[p], s.X(1)[p], s.X(2)[p]);
             const f3 vm = make_f3(s.V(0)[p], s.V(1)[p], s.V(2)[p]);
             const f3 d  = make_f3(s.D(0)[p], s.D(1)[p], s.D(2)[p]);
-            const bool pinned = oc_pinned(c, i, j);
+            const bool pinned = oc_pinned(c, ctx.bx(), i, j);
             f3 F = oc_base_force<M>(c, vm, pinned);
 #define OC_ADD(t, q) { F.x = M::add(F.x, s.F(t, 0)[q]); F.y = M::add(F.y, s.F(t, 1)[q]); F.z = M::add(F.z, s.F(t, 2)[q]); }
 #define OC_SUB(t, q) { F.x = M::sub(F.x, s.F(t, 0)[q]); F.y = M::sub(F.y, s.F(t, 1)[q]); F.z = M::sub(F.z, s.F(t, 2)[q]); }

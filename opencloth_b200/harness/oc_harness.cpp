@@ -25,6 +25,26 @@
 #include <string>
 #include <vector>
 
+// NumPy .npy (format 1.0) writer: a self-describing frame for tools that cannot guess the shape of a raw dump
+static bool write_npy(const std::string& path, const float* data, size_t rows, size_t cols)
+{
+    FILE* fp = fopen(path.c_str(), "wb");
+    if (!fp) return false;
+    char dict[128];
+    int n = snprintf(dict, sizeof(dict), "{'descr': '<f4', 'fortran_order': False, 'shape': (%zu, %zu), }", rows, cols);
+    size_t total = 10 + (size_t)n + 1;                       // magic(6) + version(2) + header length(2) + dict + newline
+    size_t pad = (64 - total % 64) % 64;
+    unsigned short hlen = (unsigned short)(n + pad + 1);
+    fwrite("\x93NUMPY\x01\x00", 1, 8, fp);
+    fwrite(&hlen, 2, 1, fp);
+    fwrite(dict, 1, (size_t)n, fp);
+    for (size_t k = 0; k < pad; ++k) fputc(' ', fp);
+    fputc('\n', fp);
+    bool ok = fwrite(data, sizeof(float), rows * cols, fp) == rows * cols;
+    fclose(fp);
+    return ok;
+}
+
 static void die(const char* what)
 {
     fprintf(stderr, "oc_harness: %s: %s\n", what, oc_last_error());
@@ -36,7 +56,7 @@ int main(int argc, char** argv)
 {
     int nx = 21, ny = 21, frames = 10, substeps = 100, k = 1, exact = 1, gpus = 1, batch = 1, halo = 16, energy = 1, link = 1, devices = 0;
     int poke_idx = -1; float poke[3] = { 0, 0, 0 };
-    std::string dump;
+    std::string dump, dump_npy;
     for (int a = 1; a < argc; ++a) {
         auto is = [&](const char* f) { return !strcmp(argv[a], f) && a + 1 < argc; };
         if (is("--nx")) nx = atoi(argv[++a]);
@@ -52,10 +72,11 @@ int main(int argc, char** argv)
         else if (is("--devices")) devices = atoi(argv[++a]);
         else if (is("--energy")) energy = atoi(argv[++a]);
         else if (is("--dump")) dump = argv[++a];
+        else if (is("--dump-npy")) dump_npy = argv[++a];
         else if (is("--poke")) { if (sscanf(argv[++a], "%d,%f,%f,%f", &poke_idx, &poke[0], &poke[1], &poke[2]) != 4) { fprintf(stderr, "--poke idx,x,y,z\n"); return 1; } }
         else {
             fprintf(stderr, "usage: oc_harness [--nx N --ny N] [--frames F] [--substeps S] [--k K] [--exact 0|1] [--gpus G [--devices D] [--link 0|1]]\n"
-                            "                  [--batch B] [--halo ROWS] [--energy 0|1] [--poke idx,x,y,z] [--dump file.f32]\n");
+                            "                  [--batch B] [--halo ROWS] [--energy 0|1] [--poke idx,x,y,z] [--dump file.f32] [--dump-npy prefix]\n");
             return 1;
         }
     }
@@ -112,6 +133,31 @@ int main(int argc, char** argv)
         }
         fclose(fp);
         printf("wrote %s (%d x %d x %d float4)\n", dump.c_str(), batch, ny, nx);
+    }
+    if (!dump_npy.empty()) {        // render hand-off as self-describing frames: <prefix>_X.npy (n x 4: x,y,z,1), <prefix>_N.npy (n x 3 vertex normals)
+        const size_t total = (size_t)nx * ny * batch;
+        std::vector<float> x(total * 4);
+        size_t off = 0;
+        for (int g = 0; g < gpus; ++g) {
+            oc_params p; CK(oc_get_params(bands[g], &p));
+            CK(oc_download(bands[g], x.data() + off, nullptr, 4));
+            off += (size_t)(p.row_end - p.row_begin) * nx * batch * 4;
+        }
+        if (!write_npy(dump_npy + "_X.npy", x.data(), total, 4)) { perror("dump-npy"); return 1; }
+        // normals need the whole mesh on one handle: with row bands, a whole-cloth handle receives the gathered state
+        oc_cloth* whole = bands[0];
+        if (gpus > 1) {
+            oc_params p; CK(oc_default_params(&p, nx, ny)); p.batch = batch;
+            CK(oc_create(&whole, &p));
+            std::vector<float> x3(total * 3);
+            for (size_t q = 0; q < total; ++q) { x3[3 * q] = x[4 * q]; x3[3 * q + 1] = x[4 * q + 1]; x3[3 * q + 2] = x[4 * q + 2]; }
+            CK(oc_upload(whole, x3.data(), x3.data(), 3));
+        }
+        std::vector<float> nrm(total * 3);
+        CK(oc_download_normals(whole, nrm.data(), 3));
+        if (gpus > 1) oc_destroy(whole);
+        if (!write_npy(dump_npy + "_N.npy", nrm.data(), total, 3)) { perror("dump-npy"); return 1; }
+        printf("wrote %s_X.npy (%zu x 4) and %s_N.npy (%zu x 3)\n", dump_npy.c_str(), total, dump_npy.c_str(), total);
     }
     for (auto* b : bands) oc_destroy(b);
     return 0;

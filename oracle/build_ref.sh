@@ -80,3 +80,13 @@ cut_slice 464 477 integrate.inc           # IntegrateSemiImplicit
 cut_slice 478 502 collision.inc           # EllipsoidCollision
 g++ $CXXFLAGS -DOC_REF_SEMI_IMPLICIT -I"$REF/dep/glm" -I"$OUT/slices_semi" "$HERE/ref_shim_euler.cpp" -o "$OUT/libocref_semi.so"
 echo "build_ref: built $OUT/libocref_semi.so"
+
+# ---- UpdateNormals of the lit demo: the render hand-off's normals ------------------------------
+SRC="$REF/OpenCloth_ExplicitEuler_TextureMapped_Lit/OpenCloth_ExplicitEuler_TextureMapped_Lit/main.cpp"
+mkdir -p "$OUT/slices_lit"
+cut_slice() { sed -n "$1,$2p" "$SRC" | tr -d '\r' > "$OUT/slices_lit/$3"; }
+cut_slice  89  90 vertex_struct.inc       # struct Vertex, vertices
+cut_slice 312 328 init_indices.inc        # InitGL: triangle list
+cut_slice 684 707 update_normals.inc      # UpdateNormals
+g++ $CXXFLAGS -I"$REF/dep/glm" -I"$OUT/slices_lit" "$HERE/ref_shim_normals.cpp" -o "$OUT/libocref_normals.so"
+echo "build_ref: built $OUT/libocref_normals.so"

@@ -67,7 +67,14 @@ typedef struct oco_cloth {
     float *rv1, *rv2;           /* rest length of spring (i,j)-(i,j+1), (i,j)-(i,j+2)  [depends on j only] */
     float *dx2, *dz2;           /* fl(dx_i*dx_i), fl(dz_j*dz_j) for the shear rest length */
     float tinv[3][3];           /* the three "transformInv" vectors of V:520-527 after the /= */
+    unsigned char* pin;         /* NULL: the reference's literals (indices 0 and numX); else one byte per particle (oco_set_pins) */
 } oco_cloth;
+/* the reference's pin test `i==0 || i==numX` (V:455, V:479-482, V:498-501), generalised to a caller-supplied set for
+ * the product's oc_set_pins extension (the verbatim reference can only check the default set) */
+static inline int is_pinned(const oco_cloth* c, size_t idx)
+{
+    return c->pin ? c->pin[idx] : (idx == 0 || idx == (size_t)(c->p.nx - 1));
+}
 
 /* Default ellipsoid = translate(0,2,0) * rotate(45 deg, x) * scale(1,1,0.5) and its glm::inverse
  * (V:324-327).  Bit patterns taken from the verbatim build (tests/test_oracle.py re-checks them). */
@@ -174,7 +181,7 @@ void oco_destroy(oco_cloth* c)
 {
     if (!c) return;
     free(c->x); free(c->xl); free(c->x2); free(c->xl2); free(c->xs); free(c->zs);
-    free(c->rh1); free(c->rh2); free(c->dx2); free(c->rv1); free(c->rv2); free(c->dz2);
+    free(c->rh1); free(c->rh2); free(c->dx2); free(c->rv1); free(c->rv2); free(c->dz2); free(c->pin);
     free(c);
 }
 
@@ -187,6 +194,14 @@ int oco_set_params(oco_cloth* c, const oco_params* p)
     return 0;
 }
 
+/* n < 0: back to the reference's literals */
+void oco_set_pins(oco_cloth* c, const int* idx, int n)
+{
+    free(c->pin); c->pin = NULL;
+    if (n < 0) return;
+    c->pin = (unsigned char*)calloc(c->n, 1);
+    for (int k = 0; k < n; ++k) c->pin[idx[k]] = 1;
+}
 size_t oco_num_particles(const oco_cloth* c) { return c->n; }
 void oco_get_state(const oco_cloth* c, float* x, float* xl)
 {
@@ -254,7 +269,7 @@ static void particle_step(const oco_cloth* c, int i, int j, float* xo, float* xl
     const float* xm = PX(i, j);
     const float* xlm = PL(i, j);
     const size_t idx = (size_t)j * u + i;
-    const int pinned = (idx == 0 || idx == (size_t)(u - 1));      /* V:455, V:479-482: i!=0 && i!=numX */
+    const int pinned = is_pinned(c, idx);                         /* V:455, V:479-482: i!=0 && i!=numX */
 
     const int verlet = (p->integrator == OCO_VERLET);
 
@@ -370,7 +385,7 @@ static void provot_spring(oco_cloth* c, int i1, int j1, int i2, int j2, float re
         dx = dx * inv; dy = dy * inv; dz = dz * inv;
         dx *= dist; dy *= dist; dz *= dist;                                         /* V:497 */
         const size_t a = (size_t)j1 * u + i1, b = (size_t)j2 * u + i2;
-        const int pin1 = (a == 0 || a == (size_t)(u - 1)), pin2 = (b == 0 || b == (size_t)(u - 1));
+        const int pin1 = is_pinned(c, a), pin2 = is_pinned(c, b);
         float* t1 = c->p.integrator == OCO_VERLET ? p1 : PL(i1, j1);                /* X (V:498-505) or V (E:567-574) */
         float* t2 = c->p.integrator == OCO_VERLET ? p2 : PL(i2, j2);
         if (pin1)      { t2[0] += dx; t2[1] += dy; t2[2] += dz; }                   /* V:498-499 */

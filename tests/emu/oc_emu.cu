@@ -14,6 +14,7 @@
 #include "../../opencloth_b200/csrc/oc_host.h"
 #include "../../opencloth_b200/csrc/oc_gather.cuh"
 #include "../../opencloth_b200/csrc/oc_provot.cuh"
+#include "../../opencloth_b200/csrc/oc_normals.cuh"
 #include "../../opencloth_b200/csrc/oc_march.cuh"
 #include "../../opencloth_b200/csrc/oc_march2.cuh"
 #include "../../opencloth_b200/csrc/oc_resident.cuh"
@@ -152,6 +153,7 @@ struct EmuCloth {
     long long stored;
     int rows_own;
     long long barrier_errors;
+    std::vector<unsigned> pins; std::vector<unsigned char> pin_rows;      // oc_set_pins
     EmuCloth* nb[2];            // linked row bands: upper / lower neighbour (same process, host memory)
     unsigned link_epoch;
 };
@@ -436,6 +438,48 @@ int emu_halo_copy(void* hsrc, int side, void* hdst)
         float4* dst = d->buf[which == 0 ? d->q.ia : d->q.ib].data() + (long long)(r0d - d->k.row_lo) * U;
         memcpy(dst, src, (size_t)ns * U * sizeof(float4));
     }
+    return 0;
+}
+// per-vertex normals of the current state (oc_normals.cuh), 3 floats per vertex
+int emu_normals(void* h, float* out)
+{
+    EmuCloth* e = (EmuCloth*)h;
+    const OcConst& k = e->k;
+    if (e->q.band) return -1;
+    const float4* X = e->buf[e->q.ia].data();
+    for (int b = 0; b < k.batch; ++b)
+        for (int j = 0; j < k.V; ++j)
+            for (int i = 0; i < k.U; ++i) {
+                const f3 n = oc_vertex_normal<MathExact>(k, X, b, i, j);
+                float* o = out + (((long long)b * k.V + j) * k.U + i) * 3;
+                o[0] = n.x; o[1] = n.y; o[2] = n.z;
+            }
+    return 0;
+}
+// oc_set_pins: same bitmap + row summary as the library
+int emu_set_pins(void* h, int cloth, const int* idx, int n)
+{
+    EmuCloth* e = (EmuCloth*)h;
+    const int U = e->k.U, V = e->k.V, B = e->k.batch;
+    const long long per = (long long)U * V;
+    if (e->pins.empty()) {
+        e->pins.assign((size_t)((per * B + 31) / 32), 0u);
+        e->pin_rows.assign((size_t)B * V, 0);
+        for (int b = 0; b < B; ++b) {
+            for (int q : { 0, U - 1 }) { long long bit = b * per + q; e->pins[bit >> 5] |= 1u << (bit & 31); }
+            e->pin_rows[(size_t)b * V] = 1;
+        }
+    }
+    for (int b = (cloth < 0 ? 0 : cloth); b < (cloth < 0 ? B : cloth + 1); ++b) {
+        for (long long q = 0; q < per; ++q) { long long bit = b * per + q; e->pins[bit >> 5] &= ~(1u << (bit & 31)); }
+        for (int j = 0; j < V; ++j) e->pin_rows[(size_t)b * V + j] = 0;
+        for (int k = 0; k < n; ++k) {
+            if (idx[k] < 0 || idx[k] >= per) return -1;
+            long long bit = b * per + idx[k]; e->pins[bit >> 5] |= 1u << (bit & 31);
+            e->pin_rows[(size_t)b * V + idx[k] / U] = 1;
+        }
+    }
+    e->k.pins = e->pins.data(); e->k.pin_rows = e->pin_rows.data();
     return 0;
 }
 // Linked row bands (oc_band_link_local): h[0..n) are the bands of one cloth in row order.  Pulls the halos once; from

@@ -107,6 +107,12 @@ def main():
             run_variant(name, 64, 64, [100, 1000] + ([2000] if "noprovot" in name else []), full=False, row_stride=16)
         for name in ("euler", "verlet_provot"):
             run_variant(name, 256, 256, [100, 400], full=False, row_stride=64)
+        # vertex normals of the lit demo's UpdateNormals (first call) on states of the Verlet golden run
+        g = np.load(os.path.join(HERE, "grid_21x21.npz"))
+        out = {}
+        for cp in (100, 2000, 3000):
+            out[f"n_{cp}"] = helpers.verbatim_normals(g[f"x_{cp}"], 21, 21)
+        np.savez_compressed(os.path.join(HERE, "normals_21x21.npz"), **out)
         return
     # 1. the reference's default configuration; 1672 is the first step at which the collider acts
     run(21, 21, [1, 10, 100, 1000, 1671, 1672, 2000, 3000], full=True)

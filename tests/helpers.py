@@ -24,7 +24,7 @@ def _newer(target, *sources):
 def build_emulator():
     src = os.path.join(ROOT, "tests", "emu", "oc_emu.cu")
     csrc = os.path.join(ROOT, "opencloth_b200", "csrc")
-    deps = [src] + [os.path.join(csrc, f) for f in ("oc_core.cuh", "oc_host.h", "oc_gather.cuh", "oc_provot.cuh", "oc_march.cuh", "oc_march2.cuh", "oc_resident.cuh")]
+    deps = [src] + [os.path.join(csrc, f) for f in ("oc_core.cuh", "oc_host.h", "oc_gather.cuh", "oc_provot.cuh", "oc_normals.cuh", "oc_march.cuh", "oc_march2.cuh", "oc_resident.cuh")]
     if _newer(EMU_SO, *deps):
         return
     subprocess.check_call([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-std=c++17",
@@ -84,6 +84,7 @@ def oracle_lib():
         L.oco_default_params.argtypes = [ctypes.POINTER(OcoParams), ctypes.c_int, ctypes.c_int]
         L.oco_default_params_for.argtypes = [ctypes.POINTER(OcoParams), ctypes.c_int, ctypes.c_int, ctypes.c_int]
         L.oco_provot.argtypes = [ctypes.c_void_p]
+        L.oco_set_pins.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int), ctypes.c_int]
         L.oco_destroy.argtypes = [ctypes.c_void_p]
         L.oco_set_params.argtypes = [ctypes.c_void_p, ctypes.POINTER(OcoParams)]
         L.oco_step.argtypes = [ctypes.c_void_p, ctypes.c_int]
@@ -158,6 +159,14 @@ class Oracle:
 
     def provot(self):
         self.L.oco_provot(self.h)
+
+    def set_pins(self, indices):
+        """None: the reference's literals (0 and numX)."""
+        if indices is None:
+            self.L.oco_set_pins(self.h, None, -1)
+        else:
+            idx = [int(i) for i in indices]
+            self.L.oco_set_pins(self.h, (ctypes.c_int * max(1, len(idx)))(*idx), len(idx))
 
     def tables(self):
         t = [np.empty(self.nx, np.float32) for _ in range(2)] + [np.empty(self.ny, np.float32) for _ in range(2)] + \
@@ -312,6 +321,8 @@ def emu_lib():
                                       ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_size_t)]
         L.emu_set_order.argtypes = [ctypes.c_int]
         L.emu_set_provot_threads.argtypes = [ctypes.c_int]
+        L.emu_normals.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        L.emu_set_pins.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.c_int]
         L.emu_band_link.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int]
         L.emu_bounding_sphere.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         L.emu_check_tiling.argtypes = [ctypes.c_int] * 10
@@ -355,6 +366,15 @@ class Emu:
         xl = np.empty((self.n_local, 3), np.float32)
         self.L.emu_download(self.h, vp(x), vp(xl))
         return x, xl
+
+    def normals(self):
+        n = np.empty((self.p.batch * self.ny * self.nx, 3), np.float32)
+        assert self.L.emu_normals(self.h, vp(n)) == 0
+        return n
+
+    def set_pins(self, indices, cloth=-1):
+        idx = [int(i) for i in indices]
+        assert self.L.emu_set_pins(self.h, cloth, (ctypes.c_int * max(1, len(idx)))(*idx), len(idx)) == 0
 
     def bounding_sphere(self):
         out = np.zeros(4, np.float32)
@@ -403,3 +423,45 @@ def developed_state(nx, ny, steps):
 
 def load_golden(name):
     return np.load(os.path.join(GOLDEN, name))
+
+
+REF_NORMALS_SO = os.path.join(ROOT, "oracle", "_ref", "libocref_normals.so")
+
+
+def verbatim_normals(x, nx, ny, calls=1):
+    """The reference's own UpdateNormals (oracle/_ref/libocref_normals.so)."""
+    L = ctypes.CDLL(REF_NORMALS_SO)
+    L.ref_normals.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+    n = np.empty((nx * ny, 3), np.float32)
+    assert L.ref_normals(nx, ny, vp(np.ascontiguousarray(x, np.float32)), vp(n), calls) == 0
+    return n
+
+
+def reference_normals(x, nx, ny):
+    """UpdateNormals of the reference's lit demo (OpenCloth_ExplicitEuler_TextureMapped_Lit/.../main.cpp:684-707) on its
+    triangle list (:313-327), restated literally in float32 numpy scalars: scatter loop over the triangles in list
+    order, accumulators starting at zero (the reference's first call)."""
+    f = np.float32
+    X = np.ascontiguousarray(x, np.float32).reshape(-1, 3)
+    idx = []
+    numX, numY = nx - 1, ny - 1
+    for i in range(numY):
+        for j in range(numX):
+            i0 = i * (numX + 1) + j; i1 = i0 + 1; i2 = i0 + (numX + 1); i3 = i2 + 1
+            if (j + i) % 2:
+                idx += [i0, i2, i1, i1, i2, i3]
+            else:
+                idx += [i0, i2, i3, i0, i3, i1]
+    n = np.zeros_like(X)
+    three = f(3.0)
+    for t in range(0, len(idx), 3):
+        p1, p2, p3 = X[idx[t]], X[idx[t + 1]], X[idx[t + 2]]
+        a = p2 - p1; b = p3 - p1
+        c = np.array([f(f(a[1] * b[2]) - f(b[1] * a[2])), f(f(a[2] * b[0]) - f(b[2] * a[0])), f(f(a[0] * b[1]) - f(b[0] * a[1]))], np.float32)
+        for v in idx[t:t + 3]:
+            n[v] = n[v] + c / three
+    with np.errstate(all="ignore"):
+        for v in range(len(n)):
+            d = f(f(f(n[v][0] * n[v][0]) + f(n[v][1] * n[v][1])) + f(n[v][2] * n[v][2]))
+            n[v] = n[v] * (f(1.0) / np.sqrt(d, dtype=np.float32))
+    return n
