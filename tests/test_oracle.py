@@ -120,6 +120,40 @@ def test_oracle_matches_verbatim_reference(nx, ny, steps):
     assert o.energy() == r.energy()
 
 
+@pytest.mark.skipif(not helpers.have_ref(), reason="oracle/_ref/libocref.so not built (no /root/reference here)")
+def test_oracle_matches_verbatim_reference_at_full_size():
+    """The size the bench runs (2048 x 2048, BASELINE config 3): the restatement against the reference's own code with
+    its 25 million-entry spring list, 3 steps from the flat sheet and 3 from a rumpled one.  Everything larger rests on
+    the same per-particle code, whose only size-dependent inputs are the rest-length tables checked here as well."""
+    n = 2048
+    r = helpers.Ref(n, n)
+    o = Oracle(n, n)
+    r.step(3); o.step(3)
+    rx, rl = r.state(); ox, ol = o.state()
+    assert bitwise_equal(rx, ox) and bitwise_equal(rl, ol)
+    rng = np.random.RandomState(5)
+    x = rx.copy(); x += (2e-3 * rng.uniform(-1, 1, x.shape)).astype(np.float32)
+    r.set_state(x, rx); o.set_state(x, rx)
+    r.step(3); o.step(3)
+    rx, rl = r.state(); ox, ol = o.state()
+    assert bitwise_equal(rx, ox) and bitwise_equal(rl, ol)
+    # every rest length of the reference's list against the six 1-D tables (sampled: the list has 25 149 442 entries)
+    s = r.springs()
+    assert len(s["p1"]) == 2 * (n * (n - 1) + n * (n - 1)) + 2 * (n - 1) * (n - 1)
+    t = o.tables()
+    p1, p2, rest, ty = s["p1"], s["p2"], s["rest"], s["type"]
+    i1, j1, i2, j2 = p1 % n, p1 // n, p2 % n, p2 // n
+    exp = np.empty(len(p1), np.float32)
+    h = (j1 == j2)
+    m = (ty == 0) & h;  exp[m] = t["rh1"][i1[m]]
+    m = (ty == 0) & ~h; exp[m] = t["rv1"][j1[m]]
+    m = (ty == 2) & h;  exp[m] = t["rh2"][i1[m]]
+    m = (ty == 2) & ~h; exp[m] = t["rv2"][j1[m]]
+    m = (ty == 1)
+    exp[m] = np.sqrt(t["dx2"][np.minimum(i1[m], i2[m])] + t["dz2"][np.minimum(j1[m], j2[m])], dtype=np.float32)
+    assert (exp.view(np.uint32) == rest.view(np.uint32)).all()
+
+
 @pytest.mark.skipif(not helpers.have_ref(), reason="oracle/_ref/libocref.so not built")
 def test_oracle_matches_reference_from_perturbed_state():
     """Batched-mode style start: the sheet with a per-particle y perturbation, velocities zero."""
