@@ -239,6 +239,7 @@ int oc_band_link_local(oc_cloth* const* bands, int n);
  *   OC_MARCH_RS=n, OC_MARCH_TW=n, OC_MARCH2_WC=n   force rows per segment / window width of the marching kernels
  *   OC_DEBUG=bits     4: count fallbacks (oc_debug_counters)  8: CTA time line (oc_debug_timeline)
  *                     16: print the launch plan to stderr  (1, 2: force / suppress the fallback of oc_k_march)
+ *                     32: test hook, tile dependencies time out  64: time the upload/step/download pipeline (oc_debug_pipeline)
  * None of them changes a result. */
 
 /* ---- diagnostics ----------------------------------------------------------------------------- */
@@ -260,6 +261,10 @@ int oc_debug_counters(oc_cloth* c, unsigned long long out[4]);
  * per CTA (linear index x + gridDim.x * (y + gridDim.y * z), first 4096 CTAs): %globaltimer at entry, set-up
  * done, lead-in done, steady loop done, exit; SM id; 2 unused.  Copies min(n_words, 8*4096) words. */
 int oc_debug_timeline(oc_cloth* c, unsigned long long* out, size_t n_words);
+/* Development time line of the host <-> device pipeline (only recorded with OC_DEBUG=64 at oc_create): out[5*chunk+s] =
+ * milliseconds after the start of the last oc_upload at which chunk's H2D copy (s=0), unpack (1), step (2), pack (3) and
+ * D2H copy (4) finished.  Returns the number of chunks. */
+int oc_debug_pipeline(oc_cloth* c, float* out, int max_chunks);
 /* sizeof(oc_params) as the library was compiled, so that FFI bindings can verify their mirror */
 size_t oc_sizeof_params(void);
 /* library / device info string: "opencloth_b200 abi=1 sm=100 device=NVIDIA B200 ..." */

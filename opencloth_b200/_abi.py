@@ -95,6 +95,7 @@ SYMBOLS = {
     "oc_step_split": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, _P(ctypes.c_int)]),
     "oc_halo_exchange": (ctypes.c_int, [_P(ctypes.c_void_p), ctypes.c_int]),
     "oc_debug_counters": (ctypes.c_int, [ctypes.c_void_p, _P(ctypes.c_ulonglong)]),
+    "oc_debug_pipeline": (ctypes.c_int, [ctypes.c_void_p, _P(ctypes.c_float), ctypes.c_int]),
     "oc_debug_timeline": (ctypes.c_int, [ctypes.c_void_p, _P(ctypes.c_ulonglong), ctypes.c_size_t]),
     "oc_sizeof_params": (ctypes.c_size_t, []),
     "oc_selftest_math": (ctypes.c_int, [ctypes.c_ulonglong, ctypes.c_uint, _P(ctypes.c_ulonglong)]),

@@ -67,9 +67,12 @@ struct oc_cloth {
     long long launches;
     float*    stage[2];          // device staging for upload/download
     size_t    stage_bytes;
-    cudaStream_t s_in, s_out;    // copy streams of the host <-> device pipeline (upload_impl)
+    cudaStream_t s_in, s_out;    // copy streams of the host <-> device pipeline (upload_impl): copies only, so that the
+    cudaStream_t s_un, s_pk;     // link never waits for a kernel; the unpack / pack kernels have streams of their own
     struct {
-        cudaEvent_t ev_tail, ev_in[32], ev_step[32];
+        cudaEvent_t ev_tail, ev_cp[32], ev_in[32], ev_step[32], ev_pk[32];
+        cudaEvent_t ev_t0, ev_out[32];      // development (OC_DEBUG=64): start of an upload, D2H of a chunk done
+        bool timed; int last_chunks;
         int up_chunks;           // an upload is queued in this many row chunks (events ev_in); 0: none pending
         int step_chunks;         // the last substep was launched per chunk (events ev_step)
     } pipe;
@@ -123,8 +126,15 @@ static int free_handle(oc_cloth* c)
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     if (c->s_in) cudaStreamDestroy(c->s_in);
     if (c->s_out) cudaStreamDestroy(c->s_out);
+    if (c->s_un) cudaStreamDestroy(c->s_un);
+    if (c->s_pk) cudaStreamDestroy(c->s_pk);
     if (c->pipe.ev_tail) cudaEventDestroy(c->pipe.ev_tail);
-    for (int k = 0; k < 32; ++k) { if (c->pipe.ev_in[k]) cudaEventDestroy(c->pipe.ev_in[k]); if (c->pipe.ev_step[k]) cudaEventDestroy(c->pipe.ev_step[k]); }
+    for (int k = 0; k < 32; ++k) {
+        if (c->pipe.ev_in[k]) cudaEventDestroy(c->pipe.ev_in[k]);
+        if (c->pipe.ev_step[k]) cudaEventDestroy(c->pipe.ev_step[k]);
+        if (c->pipe.ev_cp[k]) cudaEventDestroy(c->pipe.ev_cp[k]);
+        if (c->pipe.ev_pk[k]) cudaEventDestroy(c->pipe.ev_pk[k]);
+    }
     delete c;
     return OC_OK;
 }
@@ -337,10 +347,18 @@ extern "C" int oc_create(oc_cloth** out, const oc_params* p)
     c->stream = c->own_stream;
     OC_CREATE_CUDA(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
     OC_CREATE_CUDA(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
+    OC_CREATE_CUDA(cudaStreamCreateWithFlags(&c->s_un, cudaStreamNonBlocking));
+    OC_CREATE_CUDA(cudaStreamCreateWithFlags(&c->s_pk, cudaStreamNonBlocking));
     OC_CREATE_CUDA(cudaEventCreateWithFlags(&c->pipe.ev_tail, cudaEventDisableTiming));
+    c->pipe.timed = (k.dbg & 64) != 0;
+    const unsigned evf = c->pipe.timed ? cudaEventDefault : cudaEventDisableTiming;
+    OC_CREATE_CUDA(cudaEventCreateWithFlags(&c->pipe.ev_t0, evf));
     for (int q = 0; q < 32; ++q) {
-        OC_CREATE_CUDA(cudaEventCreateWithFlags(&c->pipe.ev_in[q], cudaEventDisableTiming));
-        OC_CREATE_CUDA(cudaEventCreateWithFlags(&c->pipe.ev_step[q], cudaEventDisableTiming));
+        OC_CREATE_CUDA(cudaEventCreateWithFlags(&c->pipe.ev_in[q], evf));
+        OC_CREATE_CUDA(cudaEventCreateWithFlags(&c->pipe.ev_step[q], evf));
+        OC_CREATE_CUDA(cudaEventCreateWithFlags(&c->pipe.ev_cp[q], evf));
+        OC_CREATE_CUDA(cudaEventCreateWithFlags(&c->pipe.ev_pk[q], evf));
+        OC_CREATE_CUDA(cudaEventCreateWithFlags(&c->pipe.ev_out[q], evf));
     }
     OC_CREATE_CUDA(cudaEventCreate(&c->ev0));
     OC_CREATE_CUDA(cudaEventCreate(&c->ev1));
@@ -433,7 +451,9 @@ extern "C" int oc_sync(oc_cloth* c)
     if (!c) return oc_fail(OC_ERR_INVALID, "oc_sync: null");
     OC_CUDA(cudaSetDevice(c->dev));
     cudaError_t e = cudaStreamSynchronize(c->s_in);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->s_un);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->s_pk);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->s_out);
     c->pipe.up_chunks = 0;                 // everything has landed: nothing left to wait for chunk by chunk
     const int rc = check_err_word(c);
@@ -449,6 +469,8 @@ static int ensure_stage(oc_cloth* c, size_t bytes)
 {
     if (c->stage_bytes >= bytes) return OC_OK;
     OC_CUDA(cudaStreamSynchronize(c->s_in));
+    OC_CUDA(cudaStreamSynchronize(c->s_un));
+    OC_CUDA(cudaStreamSynchronize(c->s_pk));
     OC_CUDA(cudaStreamSynchronize(c->s_out));
     OC_CUDA(cudaStreamSynchronize(c->stream));
     if (c->stage[0]) cudaFree(c->stage[0]);
@@ -474,7 +496,7 @@ static int pipe_chunks(const oc_cloth* c)
 {
     static const int env = getenv("OC_PIPE_CHUNKS") ? atoi(getenv("OC_PIPE_CHUNKS")) : 0;
     if (c->p.batch != 1 || c->q.band) return 1;
-    int n = env > 0 ? env : 16;
+    int n = env > 0 ? env : 8;             // measured at 2048^2 (tools/e2e_sweep.py): 4: 3.15 ms, 8: 3.04, 16: 3.11, 32: 3.21 per round trip
     if (n > OC_PIPE_MAX_CHUNKS) n = OC_PIPE_MAX_CHUNKS;
     while (n > 1 && c->rows_own / n < 64) n /= 2;          // chunks of at least 64 rows
     return n;
@@ -509,6 +531,8 @@ static int upload_impl(oc_cloth* c, int cloth0, int ncloth, const float* X, cons
     // the copy stream starts after everything queued so far (the buffers may still be in use)
     OC_CUDA(cudaEventRecord(c->pipe.ev_tail, c->stream));
     OC_CUDA(cudaStreamWaitEvent(c->s_in, c->pipe.ev_tail, 0));
+    if (c->pipe.timed) OC_CUDA(cudaEventRecord(c->pipe.ev_t0, c->s_in));
+    c->pipe.last_chunks = nch;
     for (int k = 0; k < nch; ++k) {
         int r0, r1;
         chunk_rows(c, nch, k, &r0, &r1);
@@ -516,12 +540,14 @@ static int upload_impl(oc_cloth* c, int cloth0, int ncloth, const float* X, cons
         const size_t cnt = (nch == 1) ? (size_t)n * stride : (size_t)(r1 - r0) * c->p.nx * stride;
         OC_CUDA(cudaMemcpyAsync(c->stage[0] + off, X + off, cnt * sizeof(float), cudaMemcpyHostToDevice, c->s_in));
         OC_CUDA(cudaMemcpyAsync(c->stage[1] + off, X_last + off, cnt * sizeof(float), cudaMemcpyHostToDevice, c->s_in));
+        OC_CUDA(cudaEventRecord(c->pipe.ev_cp[k], c->s_in));
+        OC_CUDA(cudaStreamWaitEvent(c->s_un, c->pipe.ev_cp[k], 0));
         const OcXfer x = { cloth0, cloth0, ncloth, c->p.row_begin, c->rows_own, r0, r1 - r0, stride };
         const long long m = (long long)ncloth * (r1 - r0) * c->p.nx;
-        oc_k_unpack<<<(unsigned)((m + 255) / 256), 256, 0, c->s_in>>>(c->k, x, c->stage[0], c->stage[1], c->buf[c->q.ia], c->buf[c->q.ib]);
+        oc_k_unpack<<<(unsigned)((m + 255) / 256), 256, 0, c->s_un>>>(c->k, x, c->stage[0], c->stage[1], c->buf[c->q.ia], c->buf[c->q.ib]);
         c->launches++;
         OC_CUDA(cudaGetLastError());
-        OC_CUDA(cudaEventRecord(c->pipe.ev_in[k], c->s_in));
+        OC_CUDA(cudaEventRecord(c->pipe.ev_in[k], c->s_un));
     }
     c->pipe.up_chunks = nch;
     if (c->q.band && !c->q.linked) c->q.fresh = c->q.kmax;     // halos are stale until the host exchanges them
@@ -555,26 +581,29 @@ static int download_impl(oc_cloth* c, int cloth0, int ncloth, float* X, float* X
         rc = join_upload(c);
         if (rc) return rc;
         OC_CUDA(cudaEventRecord(c->pipe.ev_tail, c->stream));
-        OC_CUDA(cudaStreamWaitEvent(c->s_out, c->pipe.ev_tail, 0));
+        OC_CUDA(cudaStreamWaitEvent(c->s_pk, c->pipe.ev_tail, 0));
     }
     for (int k = 0; k < nch; ++k) {
         int r0, r1;
         chunk_rows(c, nch, k, &r0, &r1);
-        if (piped) OC_CUDA(cudaStreamWaitEvent(c->s_out, c->pipe.ev_step[k], 0));
+        if (piped) OC_CUDA(cudaStreamWaitEvent(c->s_pk, c->pipe.ev_step[k], 0));
         const OcXfer x = { cloth0, cloth0, ncloth, c->p.row_begin, c->rows_own, r0, r1 - r0, stride };
         const long long m = (long long)ncloth * (r1 - r0) * c->p.nx;
-        oc_k_pack<<<(unsigned)((m + 255) / 256), 256, 0, c->s_out>>>(c->k, x, c->buf[c->q.ia], c->buf[c->q.ib],
-                                                                     X ? c->stage[0] : nullptr, X_last ? c->stage[1] : nullptr);
+        oc_k_pack<<<(unsigned)((m + 255) / 256), 256, 0, c->s_pk>>>(c->k, x, c->buf[c->q.ia], c->buf[c->q.ib],
+                                                                    X ? c->stage[0] : nullptr, X_last ? c->stage[1] : nullptr);
         c->launches++;
         OC_CUDA(cudaGetLastError());
+        OC_CUDA(cudaEventRecord(c->pipe.ev_pk[k], c->s_pk));
+        OC_CUDA(cudaStreamWaitEvent(c->s_out, c->pipe.ev_pk[k], 0));
         const size_t off = (size_t)(r0 - c->p.row_begin) * c->p.nx * stride;
         const size_t cnt = (nch == 1) ? (size_t)n * stride : (size_t)(r1 - r0) * c->p.nx * stride;
         if (X) OC_CUDA(cudaMemcpyAsync(X + off, c->stage[0] + off, cnt * sizeof(float), cudaMemcpyDeviceToHost, c->s_out));
         if (X_last) OC_CUDA(cudaMemcpyAsync(X_last + off, c->stage[1] + off, cnt * sizeof(float), cudaMemcpyDeviceToHost, c->s_out));
+        if (c->pipe.timed) OC_CUDA(cudaEventRecord(c->pipe.ev_out[k], c->s_out));
     }
     c->pipe.step_chunks = 0;
     // the compute stream must not run ahead of the packing (the next step overwrites what it reads)
-    OC_CUDA(cudaEventRecord(c->pipe.ev_tail, c->s_out));
+    OC_CUDA(cudaEventRecord(c->pipe.ev_tail, c->s_pk));
     OC_CUDA(cudaStreamWaitEvent(c->stream, c->pipe.ev_tail, 0));
     return oc_sync(c);
 }
@@ -1297,6 +1326,20 @@ extern "C" int oc_debug_counters(oc_cloth* c, unsigned long long out[4])
     OC_CUDA(cudaMemcpy(out, c->d_dbg, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     OC_CUDA(cudaMemset(c->d_dbg, 0, 4 * sizeof(unsigned long long)));
     return OC_OK;
+}
+
+// Development (OC_DEBUG=64 at oc_create): milliseconds after the start of the last oc_upload at which, per chunk, the
+// H2D copy, the unpack, the step, the pack and the D2H copy finished: out[5 * chunk + stage]; returns the chunk count.
+extern "C" int oc_debug_pipeline(oc_cloth* c, float* out, int max_chunks)
+{
+    if (!c || !out || !c->pipe.timed) return 0;
+    cudaSetDevice(c->dev);
+    int n = c->pipe.last_chunks < max_chunks ? c->pipe.last_chunks : max_chunks;
+    for (int k = 0; k < n; ++k) {
+        cudaEvent_t ev[5] = { c->pipe.ev_cp[k], c->pipe.ev_in[k], c->pipe.ev_step[k], c->pipe.ev_pk[k], c->pipe.ev_out[k] };
+        for (int q = 0; q < 5; ++q) { float ms = -1.0f; if (cudaEventElapsedTime(&ms, c->pipe.ev_t0, ev[q]) != cudaSuccess) { ms = -1.0f; cudaGetLastError(); } out[5 * k + q] = ms; }
+    }
+    return n;
 }
 
 extern "C" int oc_debug_timeline(oc_cloth* c, unsigned long long* out, size_t n_words)
