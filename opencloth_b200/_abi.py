@@ -8,7 +8,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libopencloth_b200.so")
+LIB_PATH = os.environ.get("OC_LIB") or os.path.join(_HERE, "libopencloth_b200.so")      # OC_LIB: development builds (tools/)
 
 OC_OK = 0
 OC_ERR_INVALID = -1
@@ -22,6 +22,7 @@ OC_KERNEL_GATHER = 1
 OC_KERNEL_MARCH = 2
 OC_KERNEL_MARCH2 = 3
 OC_KERNEL_RESIDENT = 4
+OC_KERNEL_TWIN = 5
 
 OC_BAND_ENDPOINT_BYTES = 512
 

@@ -14,6 +14,7 @@
 #include "oc_resident.cuh"
 #include "oc_march.cuh"
 #include "oc_march2.cuh"
+#include "oc_twin.cuh"
 
 #include <cstdio>
 #include <cstdlib>
@@ -285,7 +286,7 @@ static int validate(const oc_params* p)
     if (!(p->dt > 0.0f) || !(p->mass > 0.0f)) return oc_fail(OC_ERR_INVALID, "dt and mass must be positive");
     if (p->substeps_per_launch < 0 || p->substeps_per_launch > OC_MARCH_MAX_STAGES)
         return oc_fail(OC_ERR_INVALID, "substeps_per_launch must be 0..%d", OC_MARCH_MAX_STAGES);
-    if (p->kernel < OC_KERNEL_AUTO || p->kernel > OC_KERNEL_RESIDENT) return oc_fail(OC_ERR_INVALID, "bad kernel id");
+    if (p->kernel < OC_KERNEL_AUTO || p->kernel > OC_KERNEL_TWIN) return oc_fail(OC_ERR_INVALID, "bad kernel id");
     if (p->integrator < OC_INTEGRATOR_VERLET || p->integrator > OC_INTEGRATOR_SEMI_IMPLICIT) return oc_fail(OC_ERR_INVALID, "bad integrator id %d", p->integrator);
     if (p->provot != 0 && p->provot != 1) return oc_fail(OC_ERR_INVALID, "provot must be 0 or 1");
     if ((p->integrator != OC_INTEGRATOR_VERLET || p->provot) && (p->row_begin != 0 || p->row_end != 0) && (p->row_begin > 0 || p->row_end < p->ny))
@@ -337,7 +338,7 @@ extern "C" int oc_create(oc_cloth** out, const oc_params* p)
     k.dbg_cnt = c->d_dbg;
     OC_CREATE_CUDA(cudaMalloc(&c->chain.flags, OC_CHAIN_CAP * sizeof(unsigned)));
     OC_CREATE_CUDA(cudaMemset(c->chain.flags, 0, OC_CHAIN_CAP * sizeof(unsigned)));
-    c->chain.cap = OC_CHAIN_CAP; c->chain.epoch = 0; c->chain.valid = false;
+    c->chain.cap = OC_CHAIN_CAP; c->chain.epoch = 0; c->chain.valid = false; c->chain.kind = 0;
     OC_CREATE_CUDA(cudaMalloc(&c->in_flags, 2 * OC_LINK_STRIPS * sizeof(unsigned)));
     OC_CREATE_CUDA(cudaMemset(c->in_flags, 0, 2 * OC_LINK_STRIPS * sizeof(unsigned)));
     OC_CREATE_CUDA(cudaHostAlloc(&c->h_err, sizeof(unsigned), cudaHostAllocMapped));
@@ -375,6 +376,7 @@ extern "C" int oc_create(oc_cloth** out, const oc_params* p)
     }
     rc = oc_march_configure(c->dev);
     if (rc == 0) rc = oc_march2_configure(c->dev);
+    if (rc == 0) rc = oc_twin_configure(c->dev);
     // function attributes are per device: set them at every create, for the device of this handle
     if (rc == 0) rc = (int)cudaFuncSetAttribute((const void*)&oc_k_resident<MathExact>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OcResidentSmem::bytes(OC_RESIDENT_MAX_PARTICLES));
     if (rc == 0) rc = (int)cudaFuncSetAttribute((const void*)&oc_k_resident<MathFast>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OcResidentSmem::bytes(OC_RESIDENT_MAX_PARTICLES));
@@ -743,7 +745,7 @@ extern "C" int oc_reset_pins(oc_cloth* c)
 static int pick_kernel(const oc_cloth* c)
 {
     const bool can_reside = !c->q.band && (long long)c->p.nx * c->p.ny <= OC_RESIDENT_MAX_PARTICLES;
-    if (c->link.on) return OC_KERNEL_MARCH2;             // linked row bands: the kernel that pushes its boundary rows
+    if (c->link.on) return c->p.kernel == OC_KERNEL_TWIN ? OC_KERNEL_TWIN : OC_KERNEL_MARCH2;      // linked row bands: the kernels that push their boundary rows
     if (c->p.integrator != OC_INTEGRATOR_VERLET) return OC_KERNEL_GATHER;      // state (X, V): oc_k_gather_xv
     if (c->p.provot && (c->p.kernel == OC_KERNEL_RESIDENT || c->p.kernel == OC_KERNEL_AUTO)) return OC_KERNEL_MARCH2;   // a pass after EVERY substep
     if (c->p.kernel == OC_KERNEL_RESIDENT) return can_reside ? OC_KERNEL_RESIDENT : OC_KERNEL_MARCH2;   // a cloth that does not fit one CTA's shared memory: the fastest general kernel
@@ -760,7 +762,7 @@ static int pick_kernel(const oc_cloth* c)
 static int launch_rows(oc_cloth* c, int kern, const OcLaunch& L, int ra, int rb)
 {
     if (rb <= ra) return OC_OK;
-    if (kern == OC_KERNEL_MARCH2) {
+    if (kern == OC_KERNEL_MARCH2 || kern == OC_KERNEL_TWIN) {
         int nl = 0;
         OcPeer2 peer = {};
         if (c->link.on) {
@@ -773,7 +775,7 @@ static int launch_rows(oc_cloth* c, int kern, const OcLaunch& L, int ra, int rb)
             }
             peer.epoch = ++c->link.epoch;
         }
-        cudaError_t e = oc_march2_launch(c->k, c->p.exact != 0, ra, rb, c->sm_count,
+        cudaError_t e = (kern == OC_KERNEL_TWIN ? oc_twin_launch : oc_march2_launch)(c->k, c->p.exact != 0, ra, rb, c->sm_count,
                                          c->buf[L.src_a], c->buf[L.src_b], c->buf[L.dst], c->stream, &nl, &c->chain,
                                          c->link.on ? &peer : nullptr);
         c->launches += nl;
@@ -855,7 +857,7 @@ static int step_impl(oc_cloth* c, int n, cudaStream_t split_stream, bool want_sp
     // host <-> device pipeline (upload_impl): the first substep after a chunked upload follows the chunks
     c->pipe.step_chunks = 0;
     const bool pipe_first = c->pipe.up_chunks > 1 && n >= 1 && !c->p.provot && !c->q.band && c->p.batch == 1 &&
-                            (kern == OC_KERNEL_MARCH2 || kern == OC_KERNEL_GATHER);
+                            (kern == OC_KERNEL_MARCH2 || kern == OC_KERNEL_TWIN || kern == OC_KERNEL_GATHER);
     if (!pipe_first) { const int rcj = join_upload(c); if (rcj) return rcj; }
     if (pipe_first) {
         const int nch = c->pipe.up_chunks, n_call = n;

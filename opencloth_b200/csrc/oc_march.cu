@@ -1,6 +1,7 @@
 // oc_march.cu — host side of the marching kernel: variant table, launch geometry, launch.
 #include "oc_march.cuh"
 #include "oc_march2.cuh"
+#include "oc_twin.cuh"
 #include <cstdlib>
 #include <cstdio>
 
@@ -269,7 +270,7 @@ cudaError_t oc_march2_launch(const OcConst& c, bool exact, int ra, int rb, int s
     if (can_flag) {
         dep.flags = chain->flags; dep.epoch = ++chain->epoch;
         // <= 4 segments per strip to poll; short tiles gain nothing (measured: 16-row tiles of a 1024^2 cloth lose 15 %)
-        if (chain->valid && pdl && tile_deps && oc_dep2_chainable(seg, ra, rb, chain->pseg, chain->pra, chain->prb)) {
+        if (chain->valid && chain->kind == 0 && pdl && tile_deps && oc_dep2_chainable(seg, ra, rb, chain->pseg, chain->pra, chain->prb)) {
             dep.mode = 1; dep.pra = chain->pra; dep.prb = chain->prb; dep.pseg = chain->pseg;
         }
     }
@@ -287,6 +288,201 @@ cudaError_t oc_march2_launch(const OcConst& c, bool exact, int ra, int rb, int s
     if (e == cudaSuccess) *n_launches = 1;
     if (chain) {
         chain->valid = can_flag && e == cudaSuccess;
+        chain->kind = 0;
+        chain->pra = ra; chain->prb = rb; chain->pseg = seg;
+    }
+    return e;
+}
+
+// ------------------------------------------------------------------------------------------------
+// twin-tile kernel (oc_twin.cuh), one substep per launch: one column per thread, two tiles per CTA
+// ------------------------------------------------------------------------------------------------
+extern "C" const void* oc_twin_fn_exact(int WC, int occ);
+extern "C" const void* oc_twin_fn_fast(int WC, int occ);
+static int g_occT[2][2];      // [exact][WC == 128]
+
+static size_t smemT(int WC, bool exact)
+{
+    if (WC == 64) return exact ? sizeof(OcSmemT<64, true>) : sizeof(OcSmemT<64, false>);
+    return exact ? sizeof(OcSmemT<128, true>) : sizeof(OcSmemT<128, false>);
+}
+// development: OC_TWIN_OCC = resident CTAs per SM the kernel variant is compiled for (see oc_twin_inst.cu)
+static int twin_occ_variant(int WC, bool exact)
+{
+    const char* env = getenv("OC_TWIN_OCC");
+    const int v = env ? atoi(env) : 0;
+    return (v > 0 && (exact ? oc_twin_fn_exact(WC, v) : oc_twin_fn_fast(WC, v))) ? v : 0;
+}
+static const void* twin_fn(int WC, bool exact)
+{
+    const int v = twin_occ_variant(WC, exact);
+    return exact ? oc_twin_fn_exact(WC, v) : oc_twin_fn_fast(WC, v);
+}
+static int pick_wct(int nx)
+{
+    const char* env = getenv("OC_TWIN_WC");
+    if (env && (atoi(env) == 64 || atoi(env) == 128)) return atoi(env);
+    return nx <= 64 ? 64 : 128;
+}
+
+int oc_twin_configure(int device)
+{
+    (void)device;
+    for (int e = 0; e < 2; ++e)
+        for (int w = 0; w < 2; ++w) {
+            const int WC = w ? 128 : 64;
+            const void* fn = twin_fn(WC, e != 0);
+            cudaError_t err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemT(WC, e != 0));
+            if (err != cudaSuccess) return (int)err;
+            int occ = 0;
+            err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, WC, smemT(WC, e != 0));
+            if (err != cudaSuccess) return (int)err;
+            g_occT[e][w] = occ;
+        }
+    return 0;
+}
+
+int oc_twin_nstrips(int nx)
+{
+    const int WC = pick_wct(nx);
+    const int W_out = WC - 2 * ((nx <= WC) ? 0 : 2);
+    return (nx + W_out - 1) / W_out;
+}
+
+// Segment height for `rows` rows such that the number of segments is EVEN (a CTA takes segments 2k and 2k+1) and the
+// last segment is (nearly) as tall as the others: the twins of a CTA run in lock step, so the steady loop of the last
+// pair only covers the rows its shorter tile has (measured: a last segment of 20 rows against 52 cost 3x at 2048^2).
+// Among the heights within 1/6 of `want`, the smallest shortfall of the last segment wins, then the nearest height;
+// with `linked`, the last segment keeps at least two rows (fix_last_segment).
+static int twin_even_rs(int rows, int want, bool linked)
+{
+    if (want < 1) want = 1;
+    if (want > rows) want = rows;
+    const int span = want / 6 + 1;
+    int best = 0, best_short = 1 << 30, best_d = 1 << 30;
+    for (int rs = want - span < 1 ? 1 : want - span; rs <= want + span && rs <= rows; ++rs) {
+        const int n = (rows + rs - 1) / rs;
+        if (n % 2 != 0) continue;
+        if (linked && (rows - 1) % rs + 1 < 2) continue;
+        const int shortfall = n * rs - rows, d = rs > want ? rs - want : want - rs;
+        if (shortfall < best_short || (shortfall == best_short && d < best_d)) { best = rs; best_short = shortfall; best_d = d; }
+    }
+    if (best) return best;
+    for (int d = 0; d <= rows; ++d)          // anything even
+        for (int sgn = 0; sgn < 2; ++sgn) {
+            const int rs = sgn ? want - d : want + d;
+            if (rs < 1 || rs > rows) continue;
+            const int n = (rows + rs - 1) / rs;
+            if (n % 2 != 0) continue;
+            if (linked && (rows - 1) % rs + 1 < 2) continue;
+            return rs;
+        }
+    return 0;      // rows == 1: no even cut
+}
+
+int oc_twin_plan(const OcConst& c, bool exact, bool chained, bool linked, int ra, int rb, int sm_count, int occ_hint, OcMarchPlan* pl, OcSeg2* seg, OcTwinMap* map)
+{
+    const int U = c.U;
+    const int WC = pick_wct(U);
+    const int x_halo = (U <= WC) ? 0 : 2;
+    const int W_out = WC - 2 * x_halo;
+    const int nstrips = (U + W_out - 1) / W_out;
+    const int rows = rb - ra;
+    if (rows <= 0) return -1;
+    const long long slots = (long long)sm_count * (occ_hint > 0 ? occ_hint : 1);      // CTA slots; a CTA holds two tiles
+    const int fill = OC_MARCH_LAG + 2;
+    // Batches of an even number of cloths: the twins are the same tile of two cloths (no constraint on the segments);
+    // otherwise two segments of one strip.
+    const char* pe = getenv("OC_TWIN_PAIR");
+    map->pair_cloths = (c.batch >= 2 && c.batch % 2 == 0 && !linked && !(pe && atoi(pe) == 0)) ? 1 : 0;
+    const long long zs = map->pair_cloths ? c.batch / 2 : c.batch;
+    const int per_cta = map->pair_cloths ? 1 : 2;      // segments of one strip per CTA
+    int best_rs = 0; double best = -1.0;
+    const char* env = getenv("OC_MARCH_RS");
+    const bool forced = env && atoi(env) > 0;
+    if (forced) best_rs = atoi(env) < rows ? atoi(env) : rows;
+    else for (int nseg = per_cta; nseg <= rows; nseg += per_cta) {
+        int rs = (rows + nseg - 1) / nseg;
+        if (rs < 8 && nseg > per_cta) break;
+        if (per_cta == 2) { rs = twin_even_rs(rows, rs, linked); if (rs == 0) continue; }
+        const int ns = (rows + rs - 1) / rs;
+        const long long ctas = (long long)nstrips * (ns / per_cta) * zs;
+        const long long waves = (ctas + slots - 1) / slots;
+        const double eff = (double)rows * nstrips * c.batch / ((double)waves * slots * 2 * (rs + fill));
+        if (eff > best * 1.0001) { best = eff; best_rs = rs; }
+    }
+    // chained launches: the tallest tiles that still leave ~15 % more CTAs than CTA slots (see oc_march2_plan)
+    if (chained && !forced) {
+        const long long per_seg = (long long)nstrips * zs;
+        int nseg = (int)((slots * 115 / 100 + per_seg - 1) / per_seg) * per_cta;
+        if (nseg < per_cta) nseg = per_cta;
+        const int rs = (rows + nseg - 1) / nseg;
+        if (rs >= 32) best_rs = rs;
+    }
+    if (per_cta == 2) {
+        best_rs = twin_even_rs(rows, best_rs > 0 ? best_rs : rows / 2, linked);
+        if (best_rs == 0) return -1;
+    } else {
+        if (best_rs <= 0) best_rs = rows;
+        if (linked) best_rs = fix_last_segment(rows, best_rs);
+    }
+    pl->TW = WC; pl->S = 1; pl->x_halo = x_halo; pl->W_out = W_out; pl->nstrips = nstrips;
+    pl->RS = best_rs; pl->nseg = (rows + best_rs - 1) / best_rs; pl->threads = WC; pl->smem = smemT(WC, exact);
+    seg->rs = seg->rs_e = best_rs; seg->nstrips = nstrips; seg->nseg_all = pl->nseg; seg->n_extra = 0;
+    return 0;
+}
+
+cudaError_t oc_twin_launch(const OcConst& c, bool exact, int ra, int rb, int sm_count,
+                           const float4* A, const float4* B, float4* C, cudaStream_t stream, int* n_launches, OcChain2* chain,
+                           const OcPeer2* peer)
+{
+    *n_launches = 0;
+    OcMarchPlan pl;
+    const int WC = pick_wct(c.U);
+    OcSeg2 seg;
+    OcTwinMap map;
+    static const bool pdl = !(getenv("OC_PDL") && atoi(getenv("OC_PDL")) == 0);
+    static const bool tile_deps = !(getenv("OC_TILE_DEPS") && atoi(getenv("OC_TILE_DEPS")) == 0);
+    const bool chained = pdl && tile_deps && chain && chain->flags;
+    if (oc_twin_plan(c, exact, chained, peer != nullptr, ra, rb, sm_count, g_occT[exact ? 1 : 0][WC == 128], &pl, &seg, &map) != 0) return cudaErrorInvalidValue;
+    const void* fn = twin_fn(WC, exact);
+    if (!fn) return cudaErrorInvalidDeviceFunction;
+    if (c.batch > 65535) return cudaErrorInvalidConfiguration;
+    if (c.dbg & 16) {        // development: print the segmentation once per distinct row range
+        static int last_ra = -1, last_rb = -1;
+        if (last_ra != ra || last_rb != rb) {
+            last_ra = ra; last_rb = rb;
+            fprintf(stderr, "[oc] twin plan rows [%d,%d): strips %d x segs %d; rows/segment %d; pair_cloths %d; occ %d; exact %d\n",
+                    ra, rb, seg.nstrips, seg.nseg_all, seg.rs, map.pair_cloths, g_occT[exact ? 1 : 0][WC == 128], (int)exact);
+        }
+    }
+    const int nk = map.pair_cloths ? seg.nseg_all : seg.nseg_all / 2;
+    dim3 grid(seg.nstrips * nk, 1, map.pair_cloths ? c.batch / 2 : c.batch), block(pl.threads, 1, 1);
+    OcConst cc = c;
+    int xh = pl.x_halo;
+    // dependencies on the previous launch (OcDep2), one flag per tile and cloth as for oc_k_march2
+    OcDep2 dep = {};
+    const bool can_flag = chain && chain->flags && (long long)oc_seg2_tiles(seg) * c.batch <= chain->cap;
+    if (peer && !can_flag) return cudaErrorInvalidConfiguration;
+    if (can_flag) {
+        dep.flags = chain->flags; dep.epoch = ++chain->epoch;
+        if (chain->valid && chain->kind == 1 && pdl && tile_deps && oc_dep2_chainable(seg, ra, rb, chain->pseg, chain->pra, chain->prb)) {
+            dep.mode = 1; dep.pra = chain->pra; dep.prb = chain->prb; dep.pseg = chain->pseg;
+        }
+    }
+    if (peer) { dep.peer = *peer; dep.peer.ra = ra; dep.peer.rb = rb; dep.peer.nstrips = seg.nstrips; }
+    void* args[] = { &cc, (void*)&A, (void*)&B, (void*)&C, &ra, &rb, &seg, &xh, &map, &dep };
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = pl.smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelExC(&cfg, fn, args);
+    if (e == cudaSuccess) *n_launches = 1;
+    if (chain) {
+        chain->valid = can_flag && e == cudaSuccess;
+        chain->kind = 1;
         chain->pra = ra; chain->prb = rb; chain->pseg = seg;
     }
     return e;

@@ -17,6 +17,7 @@
 #include "../../opencloth_b200/csrc/oc_normals.cuh"
 #include "../../opencloth_b200/csrc/oc_march.cuh"
 #include "../../opencloth_b200/csrc/oc_march2.cuh"
+#include "../../opencloth_b200/csrc/oc_twin.cuh"
 #include "../../opencloth_b200/csrc/oc_resident.cuh"
 
 #include <ucontext.h>
@@ -41,6 +42,7 @@ struct EmuCtx {
     int bz() const { return bz_; }
     unsigned char* smem() const { return smem_; }
     bool wait_deps(const OcDep2&, const OcConst&, int, int) const { return true; }       // the emulator runs the tiles of a launch one after the other
+    bool wait_deps_twin(const OcDep2&, const OcConst&, const OcSeg2&, const int*, const int*, const int*, const int*) const { return true; }
     void sync();
 };
 
@@ -245,6 +247,59 @@ static int emu_march2_dispatch(EmuCloth* e, const OcLaunch& L, int WC, int RS)
     return -2;
 }
 
+
+// kernel 5: twin tiles (oc_twin.cuh).  RS = rows per segment (0: two segments); bit 16 of RS: pair the cloths of a batch
+// (needs an even batch) instead of two segments of a strip.  The number of segments must be even when segments are paired.
+template <class M, int WC>
+static int emu_twin(EmuCloth* e, const OcLaunch& L, int RS)
+{
+    const OcConst& k = e->k;
+    const int x_halo = (k.U <= WC) ? 0 : 2;
+    const int W_out = WC - 2 * x_halo;
+    const int nstrips = (k.U + W_out - 1) / W_out;
+    const int rows = L.rb - L.ra;
+    OcTwinMap map; map.pair_cloths = (RS >> 16) & 1;
+    if (map.pair_cloths && k.batch % 2 != 0) return -2;
+    OcSeg2 seg;
+    seg.rs = RS & 0xffff; seg.nstrips = nstrips;
+    if (seg.rs <= 0 || seg.rs > rows) seg.rs = map.pair_cloths ? rows : (rows + 1) / 2;
+    seg.rs_e = seg.rs;
+    oc_seg2_finish(seg, rows);
+    if (!map.pair_cloths && seg.nseg_all % 2 != 0) return -2;
+    const float4* A = e->buf[L.src_a].data();
+    const float4* B = e->buf[L.src_b].data();
+    float4* C = e->buf[L.dst].data();
+    OcDep2 dep = OcDep2();
+    if (e->q.linked) {
+        for (int sd = 0; sd < 2; ++sd)
+            if (e->nb[sd]) dep.peer.c[sd] = e->nb[sd]->buf[L.dst].data() - (long long)e->nb[sd]->k.row_lo * k.U;
+        dep.peer.epoch = ++e->link_epoch; dep.peer.ra = L.ra; dep.peer.rb = L.rb; dep.peer.nstrips = nstrips;
+        if ((rows - 1) % seg.rs + 1 < 2) return -4;
+    }
+    int rc = 0;
+    const int nk = map.pair_cloths ? seg.nseg_all : seg.nseg_all / 2;
+    const int nz = map.pair_cloths ? k.batch / 2 : k.batch;
+    for (int bz = 0; bz < nz; ++bz)
+        for (int by = 0; by < nk; ++by)
+            for (int bx = 0; bx < nstrips; ++bx) {
+                int ra = L.ra, rb = L.rb;
+                rc |= run_cta(WC, bx, by, bz, sizeof(OcSmemT<WC, M::kExact>), [&](EmuCtx& ctx) {
+                    oc_twin_body<M, WC, EmuCtx>(ctx, k, A, B, C, ra, rb, seg, x_halo, map, dep);
+                });
+            }
+    return rc;
+}
+template <class M>
+static int emu_twin_dispatch(EmuCloth* e, const OcLaunch& L, int WC, int RS)
+{
+    if (WC == 8)   return emu_twin<M, 8>(e, L, RS);
+    if (WC == 16)  return emu_twin<M, 16>(e, L, RS);
+    if (WC == 32)  return emu_twin<M, 32>(e, L, RS);
+    if (WC == 64)  return emu_twin<M, 64>(e, L, RS);
+    if (WC == 128) return emu_twin<M, 128>(e, L, RS);
+    return -2;
+}
+
 // kernel 4: one CTA per cloth, all the substeps of the launch inside; TW = threads of the CTA (0: like the library)
 template <class M>
 static int emu_resident(EmuCloth* e, const OcLaunch& L, int threads)
@@ -394,7 +449,7 @@ int emu_step(void* h, int n, int kernel, int exact, int k, int TW, int RS)
     if (e->q.xv) kernel = 1;
     if (e->p.provot || e->q.xv) k = 1;
     if (e->q.band && !e->q.linked && e->q.fresh + n > e->q.kmax) return -3;
-    if (e->q.linked && kernel != 3) return -2;
+    if (e->q.linked && kernel != 3 && kernel != 5) return -2;
     int rc = 0;
     while (n > 0) {
         OcLaunch L;
@@ -407,6 +462,10 @@ int emu_step(void* h, int n, int kernel, int exact, int k, int TW, int RS)
         if (kernel == 4) {
             int r = exact ? emu_resident<MathExact>(e, L, TW) : emu_resident<MathFast>(e, L, TW);
             if (r == -2) return -2;
+            rc |= r;
+        } else if (kernel == 5) {
+            int r = exact ? emu_twin_dispatch<MathExact>(e, L, TW, RS) : emu_twin_dispatch<MathFast>(e, L, TW, RS);
+            if (r == -2 || r == -4) return r;
             rc |= r;
         } else if (kernel == 3) {
             int r = exact ? emu_march2_dispatch<MathExact>(e, L, TW, RS) : emu_march2_dispatch<MathFast>(e, L, TW, RS);

@@ -11,7 +11,7 @@ import pytest
 import helpers
 from helpers import Emu, Oracle, bitwise_equal
 
-GATHER, MARCH, MARCH2, RESIDENT = 1, 2, 3, 4
+GATHER, MARCH, MARCH2, RESIDENT, TWIN = 1, 2, 3, 4, 5
 
 
 def run_pair(nx, ny, pre, steps, **kw):
@@ -108,6 +108,58 @@ def test_march2_is_independent_of_thread_schedule(order):
         L.emu_set_order(0)
 
 
+# twin-tile kernel (oc_twin.cuh): (nx, ny, pre, steps, window columns WC = threads, rows per segment); the number of
+# segments is even (a CTA takes segments 2k and 2k+1); RS = 0: two segments
+TWIN_CASES = [
+    (21, 21, 0, 20, 32, 0), (21, 21, 1800, 60, 32, 6), (21, 21, 1800, 30, 16, 4), (37, 23, 1900, 12, 16, 6), (37, 23, 1900, 12, 64, 0),
+    (37, 23, 1900, 12, 8, 3), (64, 64, 2000, 8, 32, 11), (64, 64, 2000, 8, 64, 9), (70, 40, 1500, 8, 64, 13), (130, 20, 500, 4, 128, 5),
+    (128, 24, 500, 4, 128, 0), (3, 3, 5, 40, 16, 0), (5, 4, 5, 40, 16, 2), (4, 9, 5, 23, 16, 5), (33, 30, 1700, 10, 32, 8), (33, 31, 1700, 10, 32, 4),
+]
+
+
+@pytest.mark.parametrize("nx,ny,pre,steps,WC,RS", TWIN_CASES)
+def test_twin_kernel_body(nx, ny, pre, steps, WC, RS):
+    run_pair(nx, ny, pre, steps, kernel=TWIN, k=1, TW=WC, RS=RS)
+
+
+def test_twin_refuses_an_odd_number_of_segments():
+    e = Emu(21, 21)
+    assert helpers.emu_lib().emu_step(e.h, 1, TWIN, 1, 1, 32, 7) == -2      # 3 segments of 7 rows
+
+
+@pytest.mark.parametrize("order", [1, 2])
+def test_twin_is_independent_of_thread_schedule(order):
+    L = helpers.emu_lib()
+    L.emu_set_order(order)
+    try:
+        run_pair(37, 23, 1900, 9, kernel=TWIN, k=1, TW=16, RS=3)
+        run_pair(70, 40, 1500, 6, kernel=TWIN, k=1, TW=64, RS=10)
+    finally:
+        L.emu_set_order(0)
+
+
+@pytest.mark.parametrize("pair_cloths,B,RS", [(1, 4, 0), (1, 2, 6), (0, 3, 3), (0, 2, 9)])
+def test_twin_batched_cloths_are_independent(pair_cloths, B, RS):
+    """The twins of a CTA are two segments of one cloth, or (bit 16 of RS) the same tile of two cloths of the batch."""
+    nx, ny = 20, 17
+    rng = np.random.RandomState(11)
+    x0, xl0 = helpers.developed_state(nx, ny, 1750)
+    starts = []
+    for b in range(B):
+        x = x0.copy()
+        x[:, 1] += (1e-3 * rng.uniform(-1, 1, len(x))).astype(np.float32)
+        starts.append(x)
+    e = Emu(nx, ny, batch=B)
+    e.upload(np.concatenate(starts), np.concatenate([xl0] * B))
+    e.step(25, kernel=TWIN, TW=16, RS=RS | pair_cloths << 16)
+    ex, exl = e.download()
+    for b in range(B):
+        o = Oracle(nx, ny); o.set_state(starts[b], xl0); o.step(25)
+        ox, oxl = o.state()
+        sl = slice(b * nx * ny, (b + 1) * nx * ny)
+        assert bitwise_equal(ex[sl], ox) and bitwise_equal(exl[sl], oxl), f"cloth {b}"
+
+
 @pytest.mark.parametrize("order", [1, 2])
 def test_march_is_independent_of_thread_schedule(order):
     """No intra-phase data race: resuming the threads in reverse / pseudo-random order between
@@ -164,7 +216,7 @@ def test_batched_cloths_are_independent():
         assert bitwise_equal(ex[sl], ox) and bitwise_equal(exl[sl], oxl), f"cloth {b}"
 
 
-@pytest.mark.parametrize("nbands,halo,k,kernel", [(2, 4, 1, MARCH), (3, 8, 2, MARCH), (4, 4, 2, MARCH), (2, 6, 1, GATHER), (3, 8, 4, MARCH)])
+@pytest.mark.parametrize("nbands,halo,k,kernel", [(2, 4, 1, MARCH), (3, 8, 2, MARCH), (4, 4, 2, MARCH), (2, 6, 1, GATHER), (3, 8, 4, MARCH), (3, 8, 1, TWIN), (2, 4, 1, TWIN)])
 def test_row_bands_with_halo_exchange_equal_single_domain(nbands, halo, k, kernel):
     """Row-band decomposition: g bands with halo_rows rows of neighbour state, one
     exchange per halo_rows/2 substeps, redundant recomputation of the shrinking halo in between.
@@ -196,7 +248,7 @@ def test_row_bands_with_halo_exchange_equal_single_domain(nbands, halo, k, kerne
         exchange()
         n = per if rnd < 2 else max(1, per - 1)     # last round: a partial group
         for e in bands:
-            e.step(n, kernel=kernel, k=k, TW=32, RS=5)
+            e.step(n, kernel=kernel, k=k, TW=32, RS=0 if kernel == TWIN else 5)
         total += n
     whole.step(total)
     wx, wxl = whole.state()
@@ -206,8 +258,9 @@ def test_row_bands_with_halo_exchange_equal_single_domain(nbands, halo, k, kerne
         assert bitwise_equal(x, wx[sl]) and bitwise_equal(xl, wxl[sl]), f"band {b}"
 
 
-@pytest.mark.parametrize("nbands,WC,RS,nx", [(2, 16, 7, 23), (3, 16, 6, 37), (4, 32, 12, 23), (3, 16, 0, 30)])
-def test_linked_row_bands_push_their_boundary_rows(nbands, WC, RS, nx):
+@pytest.mark.parametrize("nbands,WC,RS,nx,kernel", [(2, 16, 7, 23, MARCH2), (3, 16, 6, 37, MARCH2), (4, 32, 12, 23, MARCH2), (3, 16, 0, 30, MARCH2),
+                                                    (2, 16, 6, 23, TWIN), (3, 16, 4, 37, TWIN), (4, 32, 6, 23, TWIN), (3, 16, 0, 30, TWIN)])
+def test_linked_row_bands_push_their_boundary_rows(nbands, WC, RS, nx, kernel):
     """Linked row bands (OcPeer2): no exchange step — every band computes exactly its owned rows, and the tiles at a
     band edge store the two rows the neighbour's stencil reaches straight into the neighbour's halo.  Same kernel
     body as the GPU; must equal the undivided cloth bit for bit, through collider contact."""
@@ -225,7 +278,7 @@ def test_linked_row_bands_push_their_boundary_rows(nbands, WC, RS, nx):
     steps = 9
     for s in range(steps):
         for e in (bands if s % 2 == 0 else bands[::-1]):       # the order of the bands within a step does not matter
-            e.step(1, kernel=MARCH2, TW=WC, RS=RS)
+            e.step(1, kernel=kernel, TW=WC, RS=RS)
     whole.step(steps)
     wx, wxl = whole.state()
     for b, e in enumerate(bands):
