@@ -91,6 +91,7 @@ struct oc_cloth {
         int       row_begin[2], row_end[2];
         void*     opened[2][5];         // cudaIpcOpenMemHandle mappings to close (nullptr: same process)
         unsigned  epoch;                // linked steps taken
+        int       rev;                  // this band launches its segments bottom to top (OcPeer2::rev): odd bands of the chain
     } link;
     unsigned* in_flags;          // device: 2 x OC_LINK_STRIPS words released by the neighbours' boundary tiles
     // run-time pin sets (oc_set_pins): bitmap over batch x ny x nx particles + per-row summary; empty = reference default
@@ -774,6 +775,7 @@ static int launch_rows(oc_cloth* c, int kern, const OcLaunch& L, int ra, int rb)
                 peer.flags_in[sd] = c->in_flags + sd * OC_LINK_STRIPS;
             }
             peer.epoch = ++c->link.epoch;
+            peer.rev = c->link.rev;
         }
         cudaError_t e = (kern == OC_KERNEL_TWIN ? oc_twin_launch : oc_march2_launch)(c->k, c->p.exact != 0, ra, rb, c->sm_count,
                                          c->buf[L.src_a], c->buf[L.src_b], c->buf[L.dst], c->stream, &nl, &c->chain,
@@ -1135,6 +1137,14 @@ extern "C" int oc_band_link(oc_cloth* c, const void* up_blob, const void* down_b
     OC_CUDA(cudaMemsetAsync(c->in_flags, 0, 2 * OC_LINK_STRIPS * sizeof(unsigned), c->stream));
     OC_CUDA(cudaStreamSynchronize(c->stream));
     c->link.epoch = 0;
+    {
+        // neighbouring bands launch their segments in opposite directions (OcPeer2::rev).  The position of the band in the
+        // chain is taken from its rows (exact for equal bands; unequal cuts may put two equal directions side by side,
+        // which costs slack, not correctness).  OC_LINK_REV=0 / 1 forces one direction everywhere (measurements).
+        const char* env = getenv("OC_LINK_REV");
+        const int rows = c->p.row_end - c->p.row_begin;
+        c->link.rev = env ? (atoi(env) == 1 ? 1 : 0) : (int)(((2LL * c->p.row_begin + rows) / (2LL * rows)) & 1);
+    }
     c->link.on = true;
     c->q.linked = true;
     return OC_OK;

@@ -218,7 +218,7 @@ int oc_march2_plan(const OcConst& c, bool exact, bool chained, bool linked, int 
     if (linked) best_rs = fix_last_segment(rows, best_rs);
     pl->TW = WC; pl->S = 1; pl->x_halo = x_halo; pl->W_out = W_out; pl->nstrips = nstrips;
     pl->RS = best_rs; pl->nseg = (rows + best_rs - 1) / best_rs; pl->threads = WC / 2; pl->smem = smem2(WC);
-    seg->rs = seg->rs_e = best_rs; seg->nstrips = nstrips; seg->nseg_all = pl->nseg; seg->n_extra = 0;
+    seg->rs = seg->rs_e = best_rs; seg->nstrips = nstrips; seg->nseg_all = pl->nseg; seg->n_extra = 0; seg->rev = 0;
     // Single-wave launch of one cloth: shorter segments for the two edge strips (OcSeg2).
     //   OC_MARCH2_EDGE = interior / edge rows per segment - 1 in percent (0 = off).
     const char* ee = getenv("OC_MARCH2_EDGE");
@@ -274,7 +274,7 @@ cudaError_t oc_march2_launch(const OcConst& c, bool exact, int ra, int rb, int s
             dep.mode = 1; dep.pra = chain->pra; dep.prb = chain->prb; dep.pseg = chain->pseg;
         }
     }
-    if (peer) { dep.peer = *peer; dep.peer.ra = ra; dep.peer.rb = rb; dep.peer.nstrips = seg.nstrips; }
+    if (peer) { dep.peer = *peer; dep.peer.ra = ra; dep.peer.rb = rb; dep.peer.nstrips = seg.nstrips; seg.rev = peer->rev; }
     void* args[] = { &cc, (void*)&A, (void*)&B, (void*)&C, &ra, &rb, &seg, &xh, &dep };
     // Programmatic dependent launch: consecutive steps are kernel -> kernel edges on one stream; the next launch's CTAs
     // are placed while this one drains and wait (griddepcontrol.wait) before they touch the state.  OC_PDL=0 turns it off.
@@ -428,7 +428,7 @@ int oc_twin_plan(const OcConst& c, bool exact, bool chained, bool linked, int ra
     }
     pl->TW = WC; pl->S = 1; pl->x_halo = x_halo; pl->W_out = W_out; pl->nstrips = nstrips;
     pl->RS = best_rs; pl->nseg = (rows + best_rs - 1) / best_rs; pl->threads = WC; pl->smem = smemT(WC, exact);
-    seg->rs = seg->rs_e = best_rs; seg->nstrips = nstrips; seg->nseg_all = pl->nseg; seg->n_extra = 0;
+    seg->rs = seg->rs_e = best_rs; seg->nstrips = nstrips; seg->nseg_all = pl->nseg; seg->n_extra = 0; seg->rev = 0;
     return 0;
 }
 
@@ -470,7 +470,7 @@ cudaError_t oc_twin_launch(const OcConst& c, bool exact, int ra, int rb, int sm_
             dep.mode = 1; dep.pra = chain->pra; dep.prb = chain->prb; dep.pseg = chain->pseg;
         }
     }
-    if (peer) { dep.peer = *peer; dep.peer.ra = ra; dep.peer.rb = rb; dep.peer.nstrips = seg.nstrips; }
+    if (peer) { dep.peer = *peer; dep.peer.ra = ra; dep.peer.rb = rb; dep.peer.nstrips = seg.nstrips; seg.rev = peer->rev; }
     void* args[] = { &cc, (void*)&A, (void*)&B, (void*)&C, &ra, &rb, &seg, &xh, &map, &dep };
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = pl.smem; cfg.stream = stream;

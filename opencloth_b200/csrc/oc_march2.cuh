@@ -61,6 +61,11 @@ struct OcPeer2 {
     unsigned        epoch;         // linked steps taken, this one included (the same number on every band)
     int             ra, rb;        // rows of this launch (= the band's owned rows)
     int             nstrips;
+    int             rev;           // this band launches its segments bottom to top.  Neighbouring bands alternate: a band's boundary
+                                   // tiles then are the FIRST of its step on one side and the LAST on the other, and so are its
+                                   // neighbour's on the facing side, which leaves every cross-GPU dependency about a whole step of
+                                   // slack (with one direction everywhere the lower band's first tiles wait for the upper band's last
+                                   // ones, and the bands drift apart by up to 1.8 steps per boundary before the reverse dependency holds them)
 };
 
 // ---- spring pair with a pair-valued first end (particles a and b of the thread) ----------------------
@@ -557,12 +562,14 @@ struct OcSeg2 {
     int nstrips;
     int nseg_all;       // segments every strip has: tiles t < nstrips * nseg_all are (t % nstrips, t / nstrips)
     int n_extra;        // further tiles, alternately of the first and the last strip (the edge strips' additional segments)
+    int rev;            // launch order of the segments: 0 top to bottom, 1 bottom to top (linked row bands alternate, see OcPeer2::rev);
+                        // flag words are indexed by position (oc_seg2_index), whatever the launch order
 };
 OC_HD int oc_seg2_tiles(const OcSeg2& g) { return g.nstrips * g.nseg_all + g.n_extra; }
 OC_HD void oc_seg2_tile(const OcSeg2& g, int t, int& bx, int& by)
 {
     const int body = g.nstrips * g.nseg_all;
-    if (t < body) { bx = t % g.nstrips; by = t / g.nstrips; }
+    if (t < body) { bx = t % g.nstrips; by = t / g.nstrips; if (g.rev) by = g.nseg_all - 1 - by; }
     else { const int e = t - body; bx = (e & 1) ? g.nstrips - 1 : 0; by = g.nseg_all + (e >> 1); }
 }
 OC_HD void oc_seg2_rows(const OcSeg2& g, int bx, int by, int ra, int rb, int& r0, int& r1)
@@ -581,7 +588,7 @@ inline void oc_seg2_finish(OcSeg2& g, int rows)
     g.nseg_all = ni; g.n_extra = 2 * (ne - ni);
 }
 
-// tile index of (strip, segment) in the 1-D grid (inverse of oc_seg2_tile)
+// index of tile (strip, segment): its flag word, and with rev == 0 its place in the 1-D grid (inverse of oc_seg2_tile)
 OC_HD int oc_seg2_index(const OcSeg2& g, int bx, int by)
 {
     return by < g.nseg_all ? bx + g.nstrips * by : g.nstrips * g.nseg_all + 2 * (by - g.nseg_all) + (bx == 0 ? 0 : 1);
@@ -818,13 +825,13 @@ struct OcDevCtx2 {          // grid = (tiles, 1, batch): the tile -> (strip, seg
         return __syncthreads_and(ok) != 0;
     }
     // after the tile's last store
-    __device__ __forceinline__ void publish(const OcDep2& d, int r0, int r1) const
+    __device__ __forceinline__ void publish(const OcDep2& d, const OcSeg2& seg, int r0, int r1) const
     {
         if (!d.flags) return;                  // (a linked band always has its local flags)
         __syncthreads();
         if (threadIdx.x == 0) {
             __threadfence();
-            asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(d.flags + (size_t)blockIdx.z * gridDim.x + blockIdx.x), "r"(d.epoch) : "memory");
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(d.flags + (size_t)blockIdx.z * gridDim.x + oc_seg2_index(seg, x, y)), "r"(d.epoch) : "memory");
             const OcPeer2* pp = oc_opaque(&d.peer);
             const bool up = pp->flags_out[0] && r0 < pp->ra + 2 && r1 > r0, dn = pp->flags_out[1] && r1 > pp->rb - 2 && r1 > r0;
             if (up | dn) {
@@ -847,7 +854,7 @@ oc_k_march2(const __grid_constant__ OcConst c, const float4* __restrict__ A, con
     if (!oc_march2_body<M, WC, OcDevCtx2>(ctx, c, A, B, C, ra, rb, seg, x_halo, dep)) return;      // a dependency timed out: nothing published
     int r0, r1;
     oc_seg2_rows(seg, ctx.x, ctx.y, ra, rb, r0, r1);
-    ctx.publish(dep, r0, r1);
+    ctx.publish(dep, seg, r0, r1);
 }
 #endif
 

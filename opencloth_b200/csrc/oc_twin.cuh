@@ -484,8 +484,8 @@ struct OcTwin {
 OC_HD void oc_twin_tiles(const OcSeg2& seg, const OcTwinMap& map, int bx, int k, int z, int ra, int rb,
                          int by[2], int bz[2], int r0[2], int r1[2])
 {
-    if (map.pair_cloths) { by[0] = by[1] = k; bz[0] = 2 * z; bz[1] = 2 * z + 1; }
-    else { by[0] = 2 * k; by[1] = 2 * k + 1; bz[0] = bz[1] = z; }      // adjacent segments: consecutive launches then finish, and depend on each other, in the same order
+    if (map.pair_cloths) { if (seg.rev) k = seg.nseg_all - 1 - k; by[0] = by[1] = k; bz[0] = 2 * z; bz[1] = 2 * z + 1; }
+    else { if (seg.rev) k = seg.nseg_all / 2 - 1 - k; by[0] = 2 * k; by[1] = 2 * k + 1; bz[0] = bz[1] = z; }      // adjacent segments: consecutive launches then finish, and depend on each other, in the same order
     oc_seg2_rows(seg, bx, by[0], ra, rb, r0[0], r1[0]);
     oc_seg2_rows(seg, bx, by[1], ra, rb, r0[1], r1[1]);
 }

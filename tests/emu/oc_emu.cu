@@ -209,7 +209,7 @@ static int emu_march2(EmuCloth* e, const OcLaunch& L, int RS)
     const int rows = L.rb - L.ra;
     // RS = rows per segment | (rows per segment of the edge strips) << 8   (0: same; see OcSeg2)
     OcSeg2 seg;
-    seg.rs = RS & 0xff; seg.rs_e = (RS >> 8) & 0xff; seg.nstrips = nstrips;
+    seg.rs = RS & 0xff; seg.rs_e = (RS >> 8) & 0xff; seg.nstrips = nstrips; seg.rev = (RS >> 17) & 1;      // bit 17: segments bottom to top
     if (seg.rs <= 0 || seg.rs > rows) seg.rs = rows;
     if (seg.rs_e <= 0) seg.rs_e = seg.rs;
     oc_seg2_finish(seg, rows);
@@ -261,7 +261,7 @@ static int emu_twin(EmuCloth* e, const OcLaunch& L, int RS)
     OcTwinMap map; map.pair_cloths = (RS >> 16) & 1;
     if (map.pair_cloths && k.batch % 2 != 0) return -2;
     OcSeg2 seg;
-    seg.rs = RS & 0xffff; seg.nstrips = nstrips;
+    seg.rs = RS & 0xffff; seg.nstrips = nstrips; seg.rev = (RS >> 17) & 1;      // bit 17: segments bottom to top
     if (seg.rs <= 0 || seg.rs > rows) seg.rs = map.pair_cloths ? rows : (rows + 1) / 2;
     seg.rs_e = seg.rs;
     oc_seg2_finish(seg, rows);
@@ -589,8 +589,8 @@ int emu_halo_region(void* h, int side, int which, int send, void** ptr, size_t* 
 int emu_check_tiling(int nstrips, int pra, int prb, int prs, int prs_e, int ra, int rb, int rs, int rs_e, int ignore_height)
 {
     OcSeg2 pseg, seg;
-    pseg.rs = prs; pseg.rs_e = prs_e; pseg.nstrips = nstrips; oc_seg2_finish(pseg, prb - pra);
-    seg.rs = rs; seg.rs_e = rs_e; seg.nstrips = nstrips; oc_seg2_finish(seg, rb - ra);
+    pseg.rs = prs; pseg.rs_e = prs_e; pseg.nstrips = nstrips; pseg.rev = 0; oc_seg2_finish(pseg, prb - pra);
+    seg.rs = rs; seg.rs_e = rs_e; seg.nstrips = nstrips; seg.rev = 0; oc_seg2_finish(seg, rb - ra);
     // coverage of this launch
     std::vector<int> cover((size_t)nstrips * (rb - ra), 0);
     for (int t = 0; t < oc_seg2_tiles(seg); ++t) {

@@ -278,7 +278,8 @@ def test_linked_row_bands_push_their_boundary_rows(nbands, WC, RS, nx, kernel):
     steps = 9
     for s in range(steps):
         for e in (bands if s % 2 == 0 else bands[::-1]):       # the order of the bands within a step does not matter
-            e.step(1, kernel=kernel, TW=WC, RS=RS)
+            # odd bands launch their segments bottom to top, as the library does (OcPeer2::rev; bit 17 of RS here)
+            e.step(1, kernel=kernel, TW=WC, RS=RS | (bands.index(e) & 1) << 17)
     whole.step(steps)
     wx, wxl = whole.state()
     for b, e in enumerate(bands):
