@@ -60,49 +60,99 @@ def cpu_model():
 # clocks: nvidia-smi sampled while the timed region runs
 # ---------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and clock-event (throttle) reasons of one GPU, sampled in a thread while the timed region runs: NVML
+    directly (nvidia-ml-py, every 2 ms — the timed region of a 20-step run lasts under 2 ms), or the recipe's
+    `nvidia-smi --query-gpu=... -lms` line when NVML cannot be loaded.  Samples inside [t0, t1] count; if the region was
+    shorter than the sampling period, the nearest sample either side of it."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
-        self.rows = []
+        self.rows = []            # (time, sm MHz, set of reason names)
+        self.smax = None
         self.proc = None
+        self.nvml = None
+        self.stop_flag = False
+        self.source = None
 
     def start(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates all GPUs of the box; CUDA_VISIBLE_DEVICES may renumber them for this process
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.gpu
+            if vis:
+                ids = [v.strip() for v in vis.split(",") if v.strip()]
+                if self.gpu < len(ids) and ids[self.gpu].isdigit():
+                    idx = int(ids[self.gpu])
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            names = (("hw_slowdown", pynvml.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", pynvml.nvmlClocksEventReasonHwThermalSlowdown),
+                     ("sw_thermal_slowdown", pynvml.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", pynvml.nvmlClocksEventReasonSwPowerCap))
+
+            def poll():
+                while not self.stop_flag:
+                    try:
+                        mhz = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                        bits = int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                        self.rows.append((time.time(), mhz, {n for n, b in names if bits & b}))
+                    except Exception:
+                        pass
+                    time.sleep(0.002)
+            self.nvml = pynvml
+            self.source = "nvml, 2 ms"
+            self.t = threading.Thread(target=poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.source = "nvidia-smi -lms 100"
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
+            t_wait = time.time()
+            while not self.rows and time.time() - t_wait < 5.0:       # nvidia-smi needs a moment before its first line
+                time.sleep(0.05)
         except Exception:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append((time.time(), line.strip()))
-
-    def stop(self, t0, t1):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, smax, reasons = [], None, set()
-        for ts, line in self.rows:
-            if ts < t0 - 0.12 or ts > t1 + 0.12:
-                continue
             f = [x.strip() for x in line.split(",")]
             if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[1])); smax = float(f[2])
+                mhz = float(f[1]); self.smax = float(f[2])
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+            reasons = {name for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8])
+                       if v.lower().startswith("active")}
+            self.rows.append((time.time(), mhz, reasons))
+
+    def stop(self, t0, t1):
+        if self.nvml is None and self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": None}
+        time.sleep(0.15 if self.proc is not None else 0.01)
+        self.stop_flag = True
+        if self.proc is not None:
+            self.proc.terminate()
+        rows = list(self.rows)
+        inside = [r for r in rows if t0 <= r[0] <= t1]
+        if not inside:                                                  # region shorter than the sampling period
+            before = [r for r in rows if r[0] < t0][-1:]
+            after = [r for r in rows if r[0] > t1][:1]
+            inside = before + after
+        sm = sorted(r[1] for r in inside)
+        reasons = set()
+        for r in inside:
+            reasons |= r[2]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.smax, "reasons": sorted(reasons), "samples": len(sm),
+                "source": self.source}
 
 
 # ---------------------------------------------------------------------------------------------

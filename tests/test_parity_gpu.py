@@ -245,10 +245,13 @@ def test_upload_download_round_trip_and_strides():
 # fast mode: tolerance of the north star
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("nx,ny", [(21, 21), (256, 256)])
-def test_fast_mode_within_tolerance(nx, ny):
+@pytest.mark.parametrize("kernel,k", [("march", 4), ("march2", 1), ("twin", 1)])
+def test_fast_mode_within_tolerance(nx, ny, kernel, k):
+    """Tolerance mode of every marching kernel (oc_k_twin's fast arithmetic differs from the others': X - X_last
+    instead of V in the ring, forces summed in production order, s = nks + rinv (kd dot rinv - nks rest))."""
     m = oc()
     o = Oracle(nx, ny)
-    c = m.Cloth(nx, ny, exact=0, substeps_per_launch=4)
+    c = m.Cloth(nx, ny, exact=0, substeps_per_launch=k, kernel=kid(m, kernel))
     o.step(100); c.step(100)
     err100 = np.abs(c.download()[0].astype(np.float64) - o.state()[0]).max() / EXTENT
     assert err100 <= 1e-5, f"fast mode: {err100:.3e} of extent after 100 steps (tolerance 1e-5)"
