@@ -456,7 +456,9 @@ def run_ours(args):
                 "config": config_of(args),
                 "detail": {"mode": args.mode + (" (bit-identical to the reference CPU path)" if exact else " (FMA/rsqrt, within 1e-5 / 1e-3 of extent)"),
                            "substeps_per_launch": args.k,
-                           "kernel": "oc_k_march2 (fused marching stencil, 2 columns/thread, packed FP32x2)" if args.k <= 1 else "oc_k_march (staged, k substeps per launch)",
+                           "kernel": ("oc_k_march (staged, k substeps per launch)" if args.k > 1 else
+                                      ("oc_k_march2 (fused marching stencil, every spring once, 2 columns/thread, packed FP32x2)" if exact else
+                                       "oc_k_stream (fused streaming gather over twin tiles, 12 springs per particle, packed FP32x2)")),
                            "l2": "state 48 B x particles per step > 126 MB L2 (no flush needed)" if particles_total * 48 / max(1, world) > 126e6 else "state fits L2",
                            "halo_rows": (2 if linked else args.halo_rows) if band is not None else 0, "exchange": exch,
                            "halo_bytes_per_step_per_gpu": (2 * 2 * nx * 16 if (band is not None and linked) else None),

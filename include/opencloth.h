@@ -43,16 +43,20 @@ typedef enum oc_status {
 } oc_status;
 
 typedef enum oc_kernel {
-    OC_KERNEL_AUTO = 0,      /* resident for small whole cloths, else march2 for one substep per launch, march for k > 1 */
+    OC_KERNEL_AUTO = 0,      /* resident for small whole cloths; else, one substep per launch: march2 in exact mode, stream in fast
+                                mode; march for k > 1 */
     OC_KERNEL_GATHER = 1,    /* one thread per particle, 12-neighbour gather from global memory */
     OC_KERNEL_MARCH = 2,     /* fused shared-memory marching stencil, one column per thread, k substeps per launch */
     OC_KERNEL_MARCH2 = 3,    /* the same with two columns per thread (one substep per launch) */
     OC_KERNEL_RESIDENT = 4,  /* small whole cloths (<= 1536 particles): one CTA per cloth keeps the state in shared memory
                                 and takes all the substeps of an oc_step call in one launch; larger cloths and row
                                 bands are served by OC_KERNEL_MARCH2 */
-    OC_KERNEL_TWIN = 5       /* marching stencil, one column per thread, every packed FP32x2 operation spans the same column of
+    OC_KERNEL_TWIN = 5,      /* marching stencil, one column per thread, every packed FP32x2 operation spans the same column of
                                 TWO independent tiles (two row segments of a strip, or two cloths of a batch); one substep
                                 per launch; whole cloths, batches, row bands and linked row bands */
+    OC_KERNEL_STREAM = 6     /* streaming gather over twin tiles: every particle evaluates all of its twelve springs itself
+                                from a shared-memory ring of rows (no force exchange, small per-thread state, many resident
+                                warps); same coverage as OC_KERNEL_TWIN */
 } oc_kernel;
 
 /* The reference's explicit integrators on this spring net.  "E:" =

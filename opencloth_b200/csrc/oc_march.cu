@@ -2,6 +2,7 @@
 #include "oc_march.cuh"
 #include "oc_march2.cuh"
 #include "oc_twin.cuh"
+#include "oc_stream.cuh"
 #include <cstdlib>
 #include <cstdio>
 
@@ -299,52 +300,61 @@ cudaError_t oc_march2_launch(const OcConst& c, bool exact, int ra, int rb, int s
 // ------------------------------------------------------------------------------------------------
 extern "C" const void* oc_twin_fn_exact(int WC, int occ);
 extern "C" const void* oc_twin_fn_fast(int WC, int occ);
-static int g_occT[2][2];      // [exact][WC == 128]
+extern "C" const void* oc_stream_fn_exact(int WC, int occ);
+extern "C" const void* oc_stream_fn_fast(int WC, int occ);
+// variant: 0 = oc_k_twin, 1 = oc_k_stream (same tiles, same launch protocol)
+static int g_occT[2][2][2];      // [variant][exact][WC == 128]
 
-static size_t smemT(int WC, bool exact)
+static size_t smemT(int WC, bool exact, int variant)
 {
+    if (variant == 1) {
+        if (WC == 64) return exact ? sizeof(OcSmemS<64, true>) : sizeof(OcSmemS<64, false>);
+        return exact ? sizeof(OcSmemS<128, true>) : sizeof(OcSmemS<128, false>);
+    }
     if (WC == 64) return exact ? sizeof(OcSmemT<64, true>) : sizeof(OcSmemT<64, false>);
     return exact ? sizeof(OcSmemT<128, true>) : sizeof(OcSmemT<128, false>);
 }
-// development: OC_TWIN_OCC = resident CTAs per SM the kernel variant is compiled for (see oc_twin_inst.cu)
-static int twin_occ_variant(int WC, bool exact)
+static int pick_wct(int nx, int variant)
 {
-    const char* env = getenv("OC_TWIN_OCC");
-    const int v = env ? atoi(env) : 0;
-    return (v > 0 && (exact ? oc_twin_fn_exact(WC, v) : oc_twin_fn_fast(WC, v))) ? v : 0;
-}
-static const void* twin_fn(int WC, bool exact)
-{
-    const int v = twin_occ_variant(WC, exact);
-    return exact ? oc_twin_fn_exact(WC, v) : oc_twin_fn_fast(WC, v);
-}
-static int pick_wct(int nx)
-{
-    const char* env = getenv("OC_TWIN_WC");
+    const char* env = getenv(variant == 1 ? "OC_STREAM_WC" : "OC_TWIN_WC");
     if (env && (atoi(env) == 64 || atoi(env) == 128)) return atoi(env);
     return nx <= 64 ? 64 : 128;
+}
+static const void* twin_fn_v(int WC, bool exact, int variant, int v)
+{
+    if (variant == 1) return exact ? oc_stream_fn_exact(WC, v) : oc_stream_fn_fast(WC, v);
+    return exact ? oc_twin_fn_exact(WC, v) : oc_twin_fn_fast(WC, v);
+}
+// development: OC_TWIN_OCC / OC_STREAM_OCC = resident CTAs per SM the kernel variant is compiled for (see the *_inst.cu)
+static const void* twin_fn(int WC, bool exact, int variant)
+{
+    const char* env = getenv(variant == 1 ? "OC_STREAM_OCC" : "OC_TWIN_OCC");
+    const int v = env ? atoi(env) : 0;
+    const void* fn = v > 0 ? twin_fn_v(WC, exact, variant, v) : nullptr;
+    return fn ? fn : twin_fn_v(WC, exact, variant, 0);
 }
 
 int oc_twin_configure(int device)
 {
     (void)device;
-    for (int e = 0; e < 2; ++e)
-        for (int w = 0; w < 2; ++w) {
-            const int WC = w ? 128 : 64;
-            const void* fn = twin_fn(WC, e != 0);
-            cudaError_t err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemT(WC, e != 0));
-            if (err != cudaSuccess) return (int)err;
-            int occ = 0;
-            err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, WC, smemT(WC, e != 0));
-            if (err != cudaSuccess) return (int)err;
-            g_occT[e][w] = occ;
-        }
+    for (int variant = 0; variant < 2; ++variant)
+        for (int e = 0; e < 2; ++e)
+            for (int w = 0; w < 2; ++w) {
+                const int WC = w ? 128 : 64;
+                const void* fn = twin_fn(WC, e != 0, variant);
+                cudaError_t err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemT(WC, e != 0, variant));
+                if (err != cudaSuccess) return (int)err;
+                int occ = 0;
+                err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, WC, smemT(WC, e != 0, variant));
+                if (err != cudaSuccess) return (int)err;
+                g_occT[variant][e][w] = occ;
+            }
     return 0;
 }
 
 int oc_twin_nstrips(int nx)
 {
-    const int WC = pick_wct(nx);
+    const int WC = pick_wct(nx, 0);
     const int W_out = WC - 2 * ((nx <= WC) ? 0 : 2);
     return (nx + W_out - 1) / W_out;
 }
@@ -380,10 +390,10 @@ static int twin_even_rs(int rows, int want, bool linked)
     return 0;      // rows == 1: no even cut
 }
 
-int oc_twin_plan(const OcConst& c, bool exact, bool chained, bool linked, int ra, int rb, int sm_count, int occ_hint, OcMarchPlan* pl, OcSeg2* seg, OcTwinMap* map)
+int oc_twin_plan(const OcConst& c, bool exact, bool chained, bool linked, int ra, int rb, int sm_count, int occ_hint, OcMarchPlan* pl, OcSeg2* seg, OcTwinMap* map, int variant)
 {
     const int U = c.U;
-    const int WC = pick_wct(U);
+    const int WC = pick_wct(U, variant);
     const int x_halo = (U <= WC) ? 0 : 2;
     const int W_out = WC - 2 * x_halo;
     const int nstrips = (U + W_out - 1) / W_out;
@@ -427,33 +437,33 @@ int oc_twin_plan(const OcConst& c, bool exact, bool chained, bool linked, int ra
         if (linked) best_rs = fix_last_segment(rows, best_rs);
     }
     pl->TW = WC; pl->S = 1; pl->x_halo = x_halo; pl->W_out = W_out; pl->nstrips = nstrips;
-    pl->RS = best_rs; pl->nseg = (rows + best_rs - 1) / best_rs; pl->threads = WC; pl->smem = smemT(WC, exact);
+    pl->RS = best_rs; pl->nseg = (rows + best_rs - 1) / best_rs; pl->threads = WC; pl->smem = smemT(WC, exact, variant);
     seg->rs = seg->rs_e = best_rs; seg->nstrips = nstrips; seg->nseg_all = pl->nseg; seg->n_extra = 0; seg->rev = 0;
     return 0;
 }
 
 cudaError_t oc_twin_launch(const OcConst& c, bool exact, int ra, int rb, int sm_count,
                            const float4* A, const float4* B, float4* C, cudaStream_t stream, int* n_launches, OcChain2* chain,
-                           const OcPeer2* peer)
+                           const OcPeer2* peer, int variant)
 {
     *n_launches = 0;
     OcMarchPlan pl;
-    const int WC = pick_wct(c.U);
+    const int WC = pick_wct(c.U, variant);
     OcSeg2 seg;
     OcTwinMap map;
     static const bool pdl = !(getenv("OC_PDL") && atoi(getenv("OC_PDL")) == 0);
     static const bool tile_deps = !(getenv("OC_TILE_DEPS") && atoi(getenv("OC_TILE_DEPS")) == 0);
     const bool chained = pdl && tile_deps && chain && chain->flags;
-    if (oc_twin_plan(c, exact, chained, peer != nullptr, ra, rb, sm_count, g_occT[exact ? 1 : 0][WC == 128], &pl, &seg, &map) != 0) return cudaErrorInvalidValue;
-    const void* fn = twin_fn(WC, exact);
+    if (oc_twin_plan(c, exact, chained, peer != nullptr, ra, rb, sm_count, g_occT[variant][exact ? 1 : 0][WC == 128], &pl, &seg, &map, variant) != 0) return cudaErrorInvalidValue;
+    const void* fn = twin_fn(WC, exact, variant);
     if (!fn) return cudaErrorInvalidDeviceFunction;
     if (c.batch > 65535) return cudaErrorInvalidConfiguration;
     if (c.dbg & 16) {        // development: print the segmentation once per distinct row range
         static int last_ra = -1, last_rb = -1;
         if (last_ra != ra || last_rb != rb) {
             last_ra = ra; last_rb = rb;
-            fprintf(stderr, "[oc] twin plan rows [%d,%d): strips %d x segs %d; rows/segment %d; pair_cloths %d; occ %d; exact %d\n",
-                    ra, rb, seg.nstrips, seg.nseg_all, seg.rs, map.pair_cloths, g_occT[exact ? 1 : 0][WC == 128], (int)exact);
+            fprintf(stderr, "[oc] %s plan rows [%d,%d): strips %d x segs %d; rows/segment %d; pair_cloths %d; CTAs/SM %d; exact %d\n", variant ? "stream" : "twin",
+                    ra, rb, seg.nstrips, seg.nseg_all, seg.rs, map.pair_cloths, g_occT[variant][exact ? 1 : 0][WC == 128], (int)exact);
         }
     }
     const int nk = map.pair_cloths ? seg.nseg_all : seg.nseg_all / 2;
@@ -466,7 +476,7 @@ cudaError_t oc_twin_launch(const OcConst& c, bool exact, int ra, int rb, int sm_
     if (peer && !can_flag) return cudaErrorInvalidConfiguration;
     if (can_flag) {
         dep.flags = chain->flags; dep.epoch = ++chain->epoch;
-        if (chain->valid && chain->kind == 1 && pdl && tile_deps && oc_dep2_chainable(seg, ra, rb, chain->pseg, chain->pra, chain->prb)) {
+        if (chain->valid && chain->kind == 1 + variant && pdl && tile_deps && oc_dep2_chainable(seg, ra, rb, chain->pseg, chain->pra, chain->prb)) {
             dep.mode = 1; dep.pra = chain->pra; dep.prb = chain->prb; dep.pseg = chain->pseg;
         }
     }
@@ -482,7 +492,7 @@ cudaError_t oc_twin_launch(const OcConst& c, bool exact, int ra, int rb, int sm_
     if (e == cudaSuccess) *n_launches = 1;
     if (chain) {
         chain->valid = can_flag && e == cudaSuccess;
-        chain->kind = 1;
+        chain->kind = 1 + variant;
         chain->pra = ra; chain->prb = rb; chain->pseg = seg;
     }
     return e;

@@ -69,10 +69,12 @@ OC_HD void oc_cp_async16(void* smem_dst, const void* gsrc)
 }
 OC_HD void oc_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 OC_HD void oc_cp_async_wait()   { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+template <int N> OC_HD void oc_cp_async_wait_n() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }      // all but the newest N groups
 #else
 OC_HD void oc_cp_async16(void* smem_dst, const void* gsrc) { *reinterpret_cast<float4*>(smem_dst) = *reinterpret_cast<const float4*>(gsrc); }
 OC_HD void oc_cp_async_commit() {}
 OC_HD void oc_cp_async_wait() {}
+template <int N> OC_HD void oc_cp_async_wait_n() {}
 #endif
 
 // position (x) and velocity (v) of two particles as pairs

@@ -867,7 +867,7 @@ struct OcChain2 {
     unsigned* flags; int cap;      // device flag words
     unsigned  epoch;
     bool      valid;               // the previous stream operation of the handle was the launch described below
-    int       kind;                // ... of 0 = oc_k_march2, 1 = oc_k_twin (a chain never crosses kernels)
+    int       kind;                // ... of 0 = oc_k_march2, 1 = oc_k_twin, 2 = oc_k_stream (a chain never crosses kernels)
     int       pra, prb;
     OcSeg2    pseg;
 };

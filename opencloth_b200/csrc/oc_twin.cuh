@@ -643,6 +643,20 @@ struct OcDevCtxT {          // grid = (strips * tile pairs per strip, 1, batch o
     __device__ __forceinline__ int bz() const { return blockIdx.z; }
     __device__ __forceinline__ void sync() const { __syncthreads(); }
     __device__ __forceinline__ unsigned char* smem() const { extern __shared__ __align__(16) unsigned char oc_dyn_smem[]; return oc_dyn_smem; }
+    // split-phase CTA barrier (mbarrier in shared memory): arrive now, wait for everybody's arrival later (oc_stream.cuh)
+    __device__ __forceinline__ void bar_init(unsigned long long* b, int count) const
+    {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"((unsigned)__cvta_generic_to_shared(b)), "r"(count) : "memory");
+    }
+    __device__ __forceinline__ void bar_arrive(unsigned long long* b) const
+    {
+        asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" :: "r"((unsigned)__cvta_generic_to_shared(b)) : "memory");
+    }
+    __device__ __forceinline__ void bar_wait(unsigned long long* b, unsigned parity) const
+    {
+        asm volatile("{\n\t.reg .pred p;\n\tOC_BAR_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra OC_BAR_DONE;\n\tbra OC_BAR_WAIT;\n\tOC_BAR_DONE:\n\t}"
+                     :: "r"((unsigned)__cvta_generic_to_shared(b)), "r"(parity) : "memory");
+    }
     // like OcDevCtx2::wait_deps, for both tiles: warp 0 polls for tile 0, warp 1 for tile 1
     __device__ __forceinline__ bool wait_deps_twin(const OcDep2& d, const OcConst& c, const OcSeg2& seg, const int by[2], const int bz[2],
                                                    const int r0[2], const int r1[2]) const
@@ -707,10 +721,10 @@ oc_k_twin(const __grid_constant__ OcConst c, const float4* __restrict__ A, const
 
 // ---- host side (oc_march.cu) -------------------------------------------------------------------
 int  oc_twin_configure(int device);
-int  oc_twin_plan(const OcConst& c, bool exact, bool chained, bool linked, int ra, int rb, int sm_count, int occ_hint, OcMarchPlan* plan, OcSeg2* seg, OcTwinMap* map);
+int  oc_twin_plan(const OcConst& c, bool exact, bool chained, bool linked, int ra, int rb, int sm_count, int occ_hint, OcMarchPlan* plan, OcSeg2* seg, OcTwinMap* map, int variant = 0);
 int  oc_twin_nstrips(int nx);
 #ifdef __CUDACC__
 cudaError_t oc_twin_launch(const OcConst& c, bool exact, int ra, int rb, int sm_count,
                            const float4* A, const float4* B, float4* C, cudaStream_t stream, int* n_launches, OcChain2* chain,
-                           const OcPeer2* peer = nullptr);
+                           const OcPeer2* peer = nullptr, int variant = 0);      // variant 1: oc_k_stream (oc_stream.cuh)
 #endif

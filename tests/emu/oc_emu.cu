@@ -18,6 +18,7 @@
 #include "../../opencloth_b200/csrc/oc_march.cuh"
 #include "../../opencloth_b200/csrc/oc_march2.cuh"
 #include "../../opencloth_b200/csrc/oc_twin.cuh"
+#include "../../opencloth_b200/csrc/oc_stream.cuh"
 #include "../../opencloth_b200/csrc/oc_resident.cuh"
 
 #include <ucontext.h>
@@ -43,6 +44,10 @@ struct EmuCtx {
     unsigned char* smem() const { return smem_; }
     bool wait_deps(const OcDep2&, const OcConst&, int, int) const { return true; }       // the emulator runs the tiles of a launch one after the other
     bool wait_deps_twin(const OcDep2&, const OcConst&, const OcSeg2&, const int*, const int*, const int*, const int*) const { return true; }
+    // split-phase barrier (oc_stream.cuh): modelled as a barrier at the WAIT (all threads have arrived by then; stricter than the hardware)
+    void bar_init(unsigned long long*, int) const {}
+    void bar_arrive(unsigned long long*) const {}
+    void bar_wait(unsigned long long*, unsigned) { sync(); }
     void sync();
 };
 
@@ -250,7 +255,7 @@ static int emu_march2_dispatch(EmuCloth* e, const OcLaunch& L, int WC, int RS)
 
 // kernel 5: twin tiles (oc_twin.cuh).  RS = rows per segment (0: two segments); bit 16 of RS: pair the cloths of a batch
 // (needs an even batch) instead of two segments of a strip.  The number of segments must be even when segments are paired.
-template <class M, int WC>
+template <class M, int WC, int kVariant>
 static int emu_twin(EmuCloth* e, const OcLaunch& L, int RS)
 {
     const OcConst& k = e->k;
@@ -283,20 +288,25 @@ static int emu_twin(EmuCloth* e, const OcLaunch& L, int RS)
         for (int by = 0; by < nk; ++by)
             for (int bx = 0; bx < nstrips; ++bx) {
                 int ra = L.ra, rb = L.rb;
-                rc |= run_cta(WC, bx, by, bz, sizeof(OcSmemT<WC, M::kExact>), [&](EmuCtx& ctx) {
-                    oc_twin_body<M, WC, EmuCtx>(ctx, k, A, B, C, ra, rb, seg, x_halo, map, dep);
-                });
+                if (kVariant == 1)
+                    rc |= run_cta(WC, bx, by, bz, sizeof(OcSmemS<WC, M::kExact>), [&](EmuCtx& ctx) {
+                        oc_stream_body<M, WC, EmuCtx>(ctx, k, A, B, C, ra, rb, seg, x_halo, map, dep);
+                    });
+                else
+                    rc |= run_cta(WC, bx, by, bz, sizeof(OcSmemT<WC, M::kExact>), [&](EmuCtx& ctx) {
+                        oc_twin_body<M, WC, EmuCtx>(ctx, k, A, B, C, ra, rb, seg, x_halo, map, dep);
+                    });
             }
     return rc;
 }
-template <class M>
+template <class M, int kVariant>
 static int emu_twin_dispatch(EmuCloth* e, const OcLaunch& L, int WC, int RS)
 {
-    if (WC == 8)   return emu_twin<M, 8>(e, L, RS);
-    if (WC == 16)  return emu_twin<M, 16>(e, L, RS);
-    if (WC == 32)  return emu_twin<M, 32>(e, L, RS);
-    if (WC == 64)  return emu_twin<M, 64>(e, L, RS);
-    if (WC == 128) return emu_twin<M, 128>(e, L, RS);
+    if (WC == 8)   return emu_twin<M, 8, kVariant>(e, L, RS);
+    if (WC == 16)  return emu_twin<M, 16, kVariant>(e, L, RS);
+    if (WC == 32)  return emu_twin<M, 32, kVariant>(e, L, RS);
+    if (WC == 64)  return emu_twin<M, 64, kVariant>(e, L, RS);
+    if (WC == 128) return emu_twin<M, 128, kVariant>(e, L, RS);
     return -2;
 }
 
@@ -449,7 +459,7 @@ int emu_step(void* h, int n, int kernel, int exact, int k, int TW, int RS)
     if (e->q.xv) kernel = 1;
     if (e->p.provot || e->q.xv) k = 1;
     if (e->q.band && !e->q.linked && e->q.fresh + n > e->q.kmax) return -3;
-    if (e->q.linked && kernel != 3 && kernel != 5) return -2;
+    if (e->q.linked && kernel != 3 && kernel != 5 && kernel != 6) return -2;
     int rc = 0;
     while (n > 0) {
         OcLaunch L;
@@ -463,8 +473,12 @@ int emu_step(void* h, int n, int kernel, int exact, int k, int TW, int RS)
             int r = exact ? emu_resident<MathExact>(e, L, TW) : emu_resident<MathFast>(e, L, TW);
             if (r == -2) return -2;
             rc |= r;
+        } else if (kernel == 6) {
+            int r = exact ? emu_twin_dispatch<MathExact, 1>(e, L, TW, RS) : emu_twin_dispatch<MathFast, 1>(e, L, TW, RS);
+            if (r == -2 || r == -4) return r;
+            rc |= r;
         } else if (kernel == 5) {
-            int r = exact ? emu_twin_dispatch<MathExact>(e, L, TW, RS) : emu_twin_dispatch<MathFast>(e, L, TW, RS);
+            int r = exact ? emu_twin_dispatch<MathExact, 0>(e, L, TW, RS) : emu_twin_dispatch<MathFast, 0>(e, L, TW, RS);
             if (r == -2 || r == -4) return r;
             rc |= r;
         } else if (kernel == 3) {

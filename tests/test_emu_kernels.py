@@ -11,7 +11,7 @@ import pytest
 import helpers
 from helpers import Emu, Oracle, bitwise_equal
 
-GATHER, MARCH, MARCH2, RESIDENT, TWIN = 1, 2, 3, 4, 5
+GATHER, MARCH, MARCH2, RESIDENT, TWIN, STREAM = 1, 2, 3, 4, 5, 6
 
 
 def run_pair(nx, ny, pre, steps, **kw):
@@ -117,9 +117,11 @@ TWIN_CASES = [
 ]
 
 
+@pytest.mark.parametrize("kernel", [TWIN, STREAM])
 @pytest.mark.parametrize("nx,ny,pre,steps,WC,RS", TWIN_CASES)
-def test_twin_kernel_body(nx, ny, pre, steps, WC, RS):
-    run_pair(nx, ny, pre, steps, kernel=TWIN, k=1, TW=WC, RS=RS)
+def test_twin_kernel_body(nx, ny, pre, steps, WC, RS, kernel):
+    """oc_k_twin and oc_k_stream (the streaming gather kernel runs on the same twin tiles)"""
+    run_pair(nx, ny, pre, steps, kernel=kernel, k=1, TW=WC, RS=RS)
 
 
 def test_twin_refuses_an_odd_number_of_segments():
@@ -127,19 +129,21 @@ def test_twin_refuses_an_odd_number_of_segments():
     assert helpers.emu_lib().emu_step(e.h, 1, TWIN, 1, 1, 32, 7) == -2      # 3 segments of 7 rows
 
 
+@pytest.mark.parametrize("kernel", [TWIN, STREAM])
 @pytest.mark.parametrize("order", [1, 2])
-def test_twin_is_independent_of_thread_schedule(order):
+def test_twin_is_independent_of_thread_schedule(order, kernel):
     L = helpers.emu_lib()
     L.emu_set_order(order)
     try:
-        run_pair(37, 23, 1900, 9, kernel=TWIN, k=1, TW=16, RS=3)
-        run_pair(70, 40, 1500, 6, kernel=TWIN, k=1, TW=64, RS=10)
+        run_pair(37, 23, 1900, 9, kernel=kernel, k=1, TW=16, RS=3)
+        run_pair(70, 40, 1500, 6, kernel=kernel, k=1, TW=64, RS=10)
     finally:
         L.emu_set_order(0)
 
 
+@pytest.mark.parametrize("kernel", [TWIN, STREAM])
 @pytest.mark.parametrize("pair_cloths,B,RS", [(1, 4, 0), (1, 2, 6), (0, 3, 3), (0, 2, 9)])
-def test_twin_batched_cloths_are_independent(pair_cloths, B, RS):
+def test_twin_batched_cloths_are_independent(pair_cloths, B, RS, kernel):
     """The twins of a CTA are two segments of one cloth, or (bit 16 of RS) the same tile of two cloths of the batch."""
     nx, ny = 20, 17
     rng = np.random.RandomState(11)
@@ -151,7 +155,7 @@ def test_twin_batched_cloths_are_independent(pair_cloths, B, RS):
         starts.append(x)
     e = Emu(nx, ny, batch=B)
     e.upload(np.concatenate(starts), np.concatenate([xl0] * B))
-    e.step(25, kernel=TWIN, TW=16, RS=RS | pair_cloths << 16)
+    e.step(25, kernel=kernel, TW=16, RS=RS | pair_cloths << 16)
     ex, exl = e.download()
     for b in range(B):
         o = Oracle(nx, ny); o.set_state(starts[b], xl0); o.step(25)
@@ -216,7 +220,7 @@ def test_batched_cloths_are_independent():
         assert bitwise_equal(ex[sl], ox) and bitwise_equal(exl[sl], oxl), f"cloth {b}"
 
 
-@pytest.mark.parametrize("nbands,halo,k,kernel", [(2, 4, 1, MARCH), (3, 8, 2, MARCH), (4, 4, 2, MARCH), (2, 6, 1, GATHER), (3, 8, 4, MARCH), (3, 8, 1, TWIN), (2, 4, 1, TWIN)])
+@pytest.mark.parametrize("nbands,halo,k,kernel", [(2, 4, 1, MARCH), (3, 8, 2, MARCH), (4, 4, 2, MARCH), (2, 6, 1, GATHER), (3, 8, 4, MARCH), (3, 8, 1, TWIN), (2, 4, 1, TWIN), (3, 8, 1, STREAM), (2, 4, 1, STREAM)])
 def test_row_bands_with_halo_exchange_equal_single_domain(nbands, halo, k, kernel):
     """Row-band decomposition: g bands with halo_rows rows of neighbour state, one
     exchange per halo_rows/2 substeps, redundant recomputation of the shrinking halo in between.
@@ -248,7 +252,7 @@ def test_row_bands_with_halo_exchange_equal_single_domain(nbands, halo, k, kerne
         exchange()
         n = per if rnd < 2 else max(1, per - 1)     # last round: a partial group
         for e in bands:
-            e.step(n, kernel=kernel, k=k, TW=32, RS=0 if kernel == TWIN else 5)
+            e.step(n, kernel=kernel, k=k, TW=32, RS=0 if kernel in (TWIN, STREAM) else 5)
         total += n
     whole.step(total)
     wx, wxl = whole.state()
@@ -259,7 +263,8 @@ def test_row_bands_with_halo_exchange_equal_single_domain(nbands, halo, k, kerne
 
 
 @pytest.mark.parametrize("nbands,WC,RS,nx,kernel", [(2, 16, 7, 23, MARCH2), (3, 16, 6, 37, MARCH2), (4, 32, 12, 23, MARCH2), (3, 16, 0, 30, MARCH2),
-                                                    (2, 16, 6, 23, TWIN), (3, 16, 4, 37, TWIN), (4, 32, 6, 23, TWIN), (3, 16, 0, 30, TWIN)])
+                                                    (2, 16, 6, 23, TWIN), (3, 16, 4, 37, TWIN), (4, 32, 6, 23, TWIN), (3, 16, 0, 30, TWIN),
+                                                    (2, 16, 6, 23, STREAM), (3, 16, 4, 37, STREAM), (4, 32, 6, 23, STREAM), (3, 16, 0, 30, STREAM)])
 def test_linked_row_bands_push_their_boundary_rows(nbands, WC, RS, nx, kernel):
     """Linked row bands (OcPeer2): no exchange step — every band computes exactly its owned rows, and the tiles at a
     band edge store the two rows the neighbour's stencil reaches straight into the neighbour's halo.  Same kernel

@@ -31,7 +31,7 @@ def golden(name):
 
 
 def kid(m, kernel):
-    return {"march": m.OC_KERNEL_MARCH, "gather": m.OC_KERNEL_GATHER, "march2": m.OC_KERNEL_MARCH2, "resident": m.OC_KERNEL_RESIDENT, "twin": m.OC_KERNEL_TWIN}[kernel]
+    return {"march": m.OC_KERNEL_MARCH, "gather": m.OC_KERNEL_GATHER, "march2": m.OC_KERNEL_MARCH2, "resident": m.OC_KERNEL_RESIDENT, "twin": m.OC_KERNEL_TWIN, "stream": m.OC_KERNEL_STREAM}[kernel]
 
 
 def nbad(a, b):
@@ -42,7 +42,7 @@ def nbad(a, b):
 # golden vectors of the verbatim reference
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("name", ["grid_21x21.npz", "grid_37x23.npz", "grid_64x64.npz", "grid_256x256.npz"])
-@pytest.mark.parametrize("kernel,k", [("march", 1), ("march", 4), ("gather", 1), ("march2", 1), ("resident", 1), ("twin", 1)])
+@pytest.mark.parametrize("kernel,k", [("march", 1), ("march", 4), ("gather", 1), ("march2", 1), ("resident", 1), ("twin", 1), ("stream", 1)])
 def test_cuda_matches_reference_golden(name, kernel, k):
     g, meta = golden(name)
     nx, ny = meta["nx"], meta["ny"]
@@ -78,7 +78,7 @@ def test_energy_trajectory_matches_reference():
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("nx,ny,pre,steps", [(3, 3, 0, 300), (4, 7, 0, 300), (21, 21, 1650, 400), (37, 23, 1800, 300),
                                              (100, 61, 1500, 200), (129, 40, 800, 100), (300, 200, 600, 100), (1000, 37, 300, 50)])
-@pytest.mark.parametrize("kernel,k", [("march", 1), ("march", 2), ("march", 8), ("gather", 1), ("march2", 1), ("resident", 1), ("twin", 1)])
+@pytest.mark.parametrize("kernel,k", [("march", 1), ("march", 2), ("march", 8), ("gather", 1), ("march2", 1), ("resident", 1), ("twin", 1), ("stream", 1)])
 def test_cuda_matches_oracle_bitwise(nx, ny, pre, steps, kernel, k):
     m = oc()
     x0, xl0 = helpers.developed_state(nx, ny, pre)
@@ -168,7 +168,7 @@ def test_large_grid_matches_oracle_2048():
 
 
 @pytest.mark.parametrize("nx,ny,steps,kernel", [(2048, 2048, 3000, "march2"), (4096, 1200, 600, "march2"), (1100, 5000, 600, "march2"),
-                                                (2048, 2048, 2400, "twin"), (1100, 5000, 600, "twin")])
+                                                (2048, 2048, 2400, "twin"), (1100, 5000, 600, "twin"), (2048, 2048, 2400, "stream"), (1100, 5000, 600, "stream")])
 def test_chained_launches_match_gather_kernel_full_size(nx, ny, steps, kernel):
     """Consecutive oc_k_march2 launches are chained by programmatic dependent launch and per-tile flags instead
     of a barrier between steps (OcDep2; active for tiles of >= 32 rows, i.e. only at full size).  The gather
@@ -206,7 +206,7 @@ def test_chained_launches_match_gather_kernel_full_size(nx, ny, steps, kernel):
     a.close(); g.close()
 
 
-@pytest.mark.parametrize("kernel,batch", [("march2", 96), ("twin", 96), ("twin", 33)])
+@pytest.mark.parametrize("kernel,batch", [("march2", 96), ("twin", 96), ("twin", 33), ("stream", 96), ("stream", 33)])
 def test_chained_launches_batched_cloths_match_gather_kernel(kernel, batch):
     """The same for a batch (BASELINE config 5 shape): the tile flags are per cloth, every cloth one 128-row tile
     (oc_k_twin: a CTA takes the same tile of two cloths, or with an odd batch two 64-row tiles of one cloth)."""
@@ -245,7 +245,7 @@ def test_upload_download_round_trip_and_strides():
 # fast mode: tolerance of the north star
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("nx,ny", [(21, 21), (256, 256)])
-@pytest.mark.parametrize("kernel,k", [("march", 4), ("march2", 1), ("twin", 1)])
+@pytest.mark.parametrize("kernel,k", [("march", 4), ("march2", 1), ("twin", 1), ("stream", 1)])
 def test_fast_mode_within_tolerance(nx, ny, kernel, k):
     """Tolerance mode of every marching kernel (oc_k_twin's fast arithmetic differs from the others': X - X_last
     instead of V in the ring, forces summed in production order, s = nks + rinv (kd dot rinv - nks rest))."""
@@ -294,7 +294,7 @@ def test_floor_clamp_and_collider_are_exercised():
     ox, oxl = o.state()
     assert (ox[:, 1] == 0.0).sum() > 0, "test does not reach the floor"
     assert int((ox == oxl).all(1).sum()) > 10, "test does not reach the collider"
-    for kern, k in ((m.OC_KERNEL_MARCH, 4), (m.OC_KERNEL_MARCH2, 1), (m.OC_KERNEL_TWIN, 1)):
+    for kern, k in ((m.OC_KERNEL_MARCH, 4), (m.OC_KERNEL_MARCH2, 1), (m.OC_KERNEL_TWIN, 1), (m.OC_KERNEL_STREAM, 1)):
         c = m.Cloth(nx, ny, substeps_per_launch=k, kernel=kern, **kw)
         c.step(1200)
         x, xl = c.download()
@@ -314,7 +314,7 @@ def test_batched_cloths_match_per_cloth_oracle():
         rng = np.random.RandomState(1234 + b)
         X0[b] = base
         X0[b, :, 1] += (1e-3 * rng.uniform(-1, 1, nx * ny)).astype(np.float32)
-    for k, kern in ((1, m.OC_KERNEL_MARCH), (4, m.OC_KERNEL_MARCH), (1, m.OC_KERNEL_MARCH2), (1, m.OC_KERNEL_TWIN)):
+    for k, kern in ((1, m.OC_KERNEL_MARCH), (4, m.OC_KERNEL_MARCH), (1, m.OC_KERNEL_MARCH2), (1, m.OC_KERNEL_TWIN), (1, m.OC_KERNEL_STREAM)):
         c = m.Cloth(nx, ny, batch=B, substeps_per_launch=k, kernel=kern)
         c.upload(X0.reshape(-1, 3), X0.reshape(-1, 3))
         c.step(60)
@@ -327,7 +327,7 @@ def test_batched_cloths_match_per_cloth_oracle():
         c.close()
 
 
-@pytest.mark.parametrize("nbands,halo,k,kern", [(2, 4, 1, 2), (4, 8, 4, 2), (3, 16, 8, 2), (8, 8, 2, 2), (4, 8, 1, 3), (4, 8, 1, 5)])
+@pytest.mark.parametrize("nbands,halo,k,kern", [(2, 4, 1, 2), (4, 8, 4, 2), (3, 16, 8, 2), (8, 8, 2, 2), (4, 8, 1, 3), (4, 8, 1, 5), (4, 8, 1, 6)])
 def test_row_bands_single_process_equal_whole_cloth(nbands, halo, k, kern):
     """SURVEY.md 8(e) on one device: g band handles exchanging halos with oc_halo_exchange
     (device-to-device copies ordered by events) must equal the undivided cloth bitwise."""
@@ -366,7 +366,7 @@ def test_row_bands_single_process_equal_whole_cloth(nbands, halo, k, kern):
     whole.close()
 
 
-@pytest.mark.parametrize("nx,ny,nbands,halo,kernel", [(2304, 4096, 2, 16, "march2"), (4100, 3000, 3, 24, "march2"), (2304, 4096, 2, 16, "twin")])
+@pytest.mark.parametrize("nx,ny,nbands,halo,kernel", [(2304, 4096, 2, 16, "march2"), (4100, 3000, 3, 24, "march2"), (2304, 4096, 2, 16, "twin"), (2304, 4096, 2, 16, "stream")])
 def test_row_bands_chained_full_size(nx, ny, nbands, halo, kernel):
     """Row bands at a size where the launches of a band are chained tile by tile (OcDep2) although the row range,
     and with it the tiling, shrinks with every substep of a group: bitwise equal to the undivided cloth stepped
@@ -406,7 +406,7 @@ def test_row_bands_chained_full_size(nx, ny, nbands, halo, kernel):
 
 
 @pytest.mark.parametrize("nx,ny,nbands,steps,kernel", [(512, 384, 3, 60, "auto"), (200, 64, 4, 40, "auto"), (2304, 2048, 2, 120, "auto"), (1100, 1536, 4, 90, "auto"),
-                                                       (512, 384, 3, 60, "twin"), (2304, 2048, 2, 120, "twin")])
+                                                       (512, 384, 3, 60, "twin"), (2304, 2048, 2, 120, "twin"), (512, 384, 3, 60, "stream"), (2304, 2048, 2, 120, "stream")])
 def test_linked_row_bands_equal_whole_cloth(nx, ny, nbands, steps, kernel):
     """Linked row bands (the multi-GPU path: in-kernel peer stores of the boundary rows + flag words between the
     bands' tiles, no exchange step), here with all bands on ONE device in one process — the same kernel path and the

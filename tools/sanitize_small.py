@@ -9,7 +9,7 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import opencloth_b200 as oc  # noqa: E402
 
-for kernel, k in ((1, 1), (2, 1), (2, 4), (3, 1), (4, 1), (5, 1)):
+for kernel, k in ((1, 1), (2, 1), (2, 4), (3, 1), (4, 1), (5, 1), (6, 1)):
     for exact in (1, 0):
         for nx, ny, batch in ((150, 70, 1), (37, 23, 3), (260, 40, 1), (21, 21, 2)):
             c = oc.Cloth(nx, ny, batch=batch, kernel=kernel, exact=exact, substeps_per_launch=k)
@@ -31,7 +31,7 @@ for b in bands:
     b.download()
 print("bands ok")
 # linked row bands on one device (peer stores into the neighbour's halo, flag words; odd bands launch bottom to top)
-for kernel in (3, 5):
+for kernel in (3, 5, 6):
     lb = [oc.Cloth(150, 96, row_begin=32 * b, row_end=32 * (b + 1), halo_rows=2, kernel=kernel) for b in range(3)]
     oc.link_bands_local(lb)
     for _ in range(6):

@@ -43,7 +43,7 @@ if __name__ == "__main__":
             for exact in [int(t) for t in a.modes.split(",")]:
                 for k in ([int(t) for t in a.ks.split(",")] if kern == 2 else [1]):
                     us, ups = run(nx, ny, b, kern, exact, k, a.steps)
-                    print(json.dumps(dict(grid=g, kernel={1: "gather", 2: "march", 3: "march2", 5: "twin"}[kern], exact=exact, k=k,
+                    print(json.dumps(dict(grid=g, kernel={1: "gather", 2: "march", 3: "march2", 5: "twin", 6: "stream"}[kern], exact=exact, k=k,
                                           us_per_step=round(us, 2), gupdates_s=round(ups / 1e9, 3),
                                           roofline_frac_48B=round(ups * 48 / 1e9 / PEAK, 4),
                                           rs=os.environ.get("OC_MARCH_RS", "auto"))), flush=True)
