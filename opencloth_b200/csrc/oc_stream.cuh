@@ -51,6 +51,10 @@ struct OcSmemS {
     unsigned long long bar;                          // split-phase barrier of the row pipeline (mbarrier)
 };
 
+// a * b + c.  Exact mode: product and sum rounded separately (see p_sump); fast mode: one explicit FFMA2, so that the steady
+// and the generic path of the kernel round alike and a result never depends on the tiling
+template <class M> OC_HD float2 oc_ma(float2 a, float2 b, float2 c, float one) { return M::kExact ? p_sump<M>(p_mul(a, b), c, one) : p_fma(a, b, c); }
+
 // per-column rest lengths of a thread (exact: lengths / squared lengths; fast: lengths are pre-multiplied by -Ks)
 struct OcStreamCol { float rh1m, rh1i, rh2m, rh2i, dx2m, dx2i; };
 // per-row rest lengths of one tile
@@ -178,12 +182,13 @@ struct OcStream {
     template <bool kAll, bool kMask>
     OC_HD void spring(OcPair3& F, const OcPV2& me, const OcPV2& n, float2 rest, float2 nks, float2 kd, bool p0, bool p1, float mask, OcRange& rg)
     {
-        if (M::kExact || !kAll) {
+        if (M::kExact) {
             OcPair3 f = oc_spring_twin<M>(me.x, me.v, n.x, n.v, rest, nks, kd, c.one, rg);
             if (kMask) { const float2 m = p_bc(mask); f.x = p_mul(f.x, m); f.y = p_mul(f.y, m); f.z = p_mul(f.z, m); }
             oc_acc2<M, kAll>(F, f, p0, p1, false, c.one);
         } else {
-            // fast mode, no predicates: F += s * dp, 15 packed operations and two MUFU per spring pair
+            // fast mode: F += s * dp fused, 15 packed operations and two MUFU per spring pair; the generic path applies the
+            // same fused operation per half under its predicate, so both paths round alike
             OcPair3 dp, dv;
             dp.x = p_sub(me.x.x, n.x.x); dp.y = p_sub(me.x.y, n.x.y); dp.z = p_sub(me.x.z, n.x.z);
             dv.x = p_sub(me.v.x, n.v.x); dv.y = p_sub(me.v.y, n.v.y); dv.z = p_sub(me.v.z, n.v.z);
@@ -193,7 +198,11 @@ struct OcStream {
             const float2 u    = p_fma(p_mul(kd, dot), rinv, p_neg(rest));
             float2 sc         = p_fma(u, rinv, nks);
             if (kMask) sc = p_mul(sc, p_bc(mask));
-            F.x = p_fma(sc, dp.x, F.x); F.y = p_fma(sc, dp.y, F.y); F.z = p_fma(sc, dp.z, F.z);
+            if (kAll) { F.x = p_fma(sc, dp.x, F.x); F.y = p_fma(sc, dp.y, F.y); F.z = p_fma(sc, dp.z, F.z); }
+            else {
+                if (p0) { F.x.x = MathFast::fma(sc.x, dp.x.x, F.x.x); F.y.x = MathFast::fma(sc.x, dp.y.x, F.y.x); F.z.x = MathFast::fma(sc.x, dp.z.x, F.z.x); }
+                if (p1) { F.x.y = MathFast::fma(sc.y, dp.x.y, F.x.y); F.y.y = MathFast::fma(sc.y, dp.y.y, F.y.y); F.z.y = MathFast::fma(sc.y, dp.z.y, F.z.y); }
+            }
         }
     }
 
@@ -253,9 +262,9 @@ struct OcStream {
             F.y = make_float2(pin_0 ? 0.0f : c.f0[1], pin_1 ? 0.0f : c.f0[1]);
             F.z = make_float2(pin_0 ? 0.0f : c.f0[2], pin_1 ? 0.0f : c.f0[2]);
             const float2 damp = p_bc(M::kExact ? c.damping : damp_dt);
-            F.x = p_sump<M>(p_mul(damp, me.v.x), F.x, c.one);
-            F.y = p_sump<M>(p_mul(damp, me.v.y), F.y, c.one);
-            F.z = p_sump<M>(p_mul(damp, me.v.z), F.z, c.one);
+            F.x = oc_ma<M>(damp, me.v.x, F.x, c.one);
+            F.y = oc_ma<M>(damp, me.v.y, F.y, c.one);
+            F.z = oc_ma<M>(damp, me.v.z, F.z, c.one);
             // the twelve springs in the order the reference's list touches the particle (V:286-320, oc_gather.cuh)
             spring<kAll, kMask>(F, me, ld(s0, ci - 1),  p_bc(K.rh1m), nS, kS, e0 && l1, e1 && l1, mL1, rg);                          // 1  (i-1, j)
             spring<kAll, kMask>(F, me, ld(s0, ci + 1),  p_bc(K.rh1i), nS, kS, e0 && r1, e1 && r1, mR1, rg);                          // 2  (i+1, j)
@@ -323,9 +332,9 @@ struct OcStream {
             }
             // ---- IntegrateVerlet (V:428-444) + EllipsoidCollision (V:509-533), both tiles ----------------
             OcPair3 n;
-            n.x = p_sump<M>(p_mul(p_bc(c.dt2m), F.x), p_add(me.x.x, dme.x), c.one);
-            n.y = p_sump<M>(p_mul(p_bc(c.dt2m), F.y), p_add(me.x.y, dme.y), c.one);
-            n.z = p_sump<M>(p_mul(p_bc(c.dt2m), F.z), p_add(me.x.z, dme.z), c.one);
+            n.x = oc_ma<M>(p_bc(c.dt2m), F.x, p_add(me.x.x, dme.x), c.one);
+            n.y = oc_ma<M>(p_bc(c.dt2m), F.y, p_add(me.x.y, dme.y), c.one);
+            n.z = oc_ma<M>(p_bc(c.dt2m), F.z, p_add(me.x.z, dme.z), c.one);
             if (n.y.x < 0.0f) n.y.x = 0.0f;
             if (n.y.y < 0.0f) n.y.y = 0.0f;
             bool hit_0 = false, hit_1 = false;
@@ -333,10 +342,10 @@ struct OcStream {
             const float2 e2 = p_fma(ez, ez, p_fma(ey, ey, p_mul(ex, ex)));
             if ((e2.x <= c.bs_r2) | (e2.y <= c.bs_r2)) {
                 OcPair3 p0;         // X_0 = inverse_ellipsoid * vec4(X,1) - center, rows x, y, z for (tile 0, tile 1)
-                p0.x = p_sub(p_add(p_sump<M>(p_mul(p_bc(c.im[0][2]), n.z), p_sump<M>(p_mul(p_bc(c.im[0][1]), n.y), p_mul(p_bc(c.im[0][0]), n.x), c.one), c.one), p_bc(c.im[0][3])), p_bc(c.center[0]));
-                p0.y = p_sub(p_add(p_sump<M>(p_mul(p_bc(c.im[1][2]), n.z), p_sump<M>(p_mul(p_bc(c.im[1][1]), n.y), p_mul(p_bc(c.im[1][0]), n.x), c.one), c.one), p_bc(c.im[1][3])), p_bc(c.center[1]));
-                p0.z = p_sub(p_add(p_sump<M>(p_mul(p_bc(c.im[2][2]), n.z), p_sump<M>(p_mul(p_bc(c.im[2][1]), n.y), p_mul(p_bc(c.im[2][0]), n.x), c.one), c.one), p_bc(c.im[2][3])), p_bc(c.center[2]));
-                const float2 sq = p_sump<M>(p_mul(p0.z, p0.z), p_sump<M>(p_mul(p0.y, p0.y), p_mul(p0.x, p0.x), c.one), c.one);
+                p0.x = p_sub(p_add(oc_ma<M>(p_bc(c.im[0][2]), n.z, oc_ma<M>(p_bc(c.im[0][1]), n.y, p_mul(p_bc(c.im[0][0]), n.x), c.one), c.one), p_bc(c.im[0][3])), p_bc(c.center[0]));
+                p0.y = p_sub(p_add(oc_ma<M>(p_bc(c.im[1][2]), n.z, oc_ma<M>(p_bc(c.im[1][1]), n.y, p_mul(p_bc(c.im[1][0]), n.x), c.one), c.one), p_bc(c.im[1][3])), p_bc(c.center[1]));
+                p0.z = p_sub(p_add(oc_ma<M>(p_bc(c.im[2][2]), n.z, oc_ma<M>(p_bc(c.im[2][1]), n.y, p_mul(p_bc(c.im[2][0]), n.x), c.one), c.one), p_bc(c.im[2][3])), p_bc(c.center[2]));
+                const float2 sq = oc_ma<M>(p0.z, p0.z, oc_ma<M>(p0.y, p0.y, p_mul(p0.x, p0.x), c.one), c.one);
                 hit_0 = sq.x < 1.0f; hit_1 = sq.y < 1.0f;                                           // V:513-514 (see oc_core.cuh)
 #ifdef __CUDA_ARCH__
                 if ((c.dbg & 4) && (hit_0 | hit_1)) { atomicAdd(c.dbg_cnt + 3, 1ull); if ((threadIdx.x & 31) == __ffs(__activemask()) - 1) atomicAdd(c.dbg_cnt + 3, 1ull << 32); }

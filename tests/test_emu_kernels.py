@@ -164,6 +164,20 @@ def test_twin_batched_cloths_are_independent(pair_cloths, B, RS, kernel):
         assert bitwise_equal(ex[sl], ox) and bitwise_equal(exl[sl], oxl), f"cloth {b}"
 
 
+def test_stream_fast_mode_does_not_depend_on_the_tiling():
+    """oc_k_stream's tolerance mode rounds alike on its steady and generic paths (one explicit fused multiply-add per
+    term on both), so a result is independent of window width, rows per tile and of which rows are tile edges —
+    which is what lets bench.py compare row bands with the whole cloth bit for bit in fast mode too."""
+    nx, ny = 37, 30
+    x0, xl0 = helpers.developed_state(nx, ny, 1700)
+    ref = None
+    for WC, RS in ((64, 0), (16, 5), (8, 3), (32, 15)):
+        e = Emu(nx, ny); e.upload(x0, xl0); e.step(12, kernel=STREAM, exact=0, TW=WC, RS=RS)
+        got = e.download()
+        ref = ref or got
+        assert bitwise_equal(got[0], ref[0]) and bitwise_equal(got[1], ref[1]), (WC, RS)
+
+
 @pytest.mark.parametrize("order", [1, 2])
 def test_march_is_independent_of_thread_schedule(order):
     """No intra-phase data race: resuming the threads in reverse / pseudo-random order between

@@ -263,6 +263,54 @@ def test_fast_mode_within_tolerance(nx, ny, kernel, k):
     c.close()
 
 
+def test_fast_mode_within_tolerance_at_bench_size():
+    """The tolerance mode at the size bench.py runs (2048 x 2048, AUTO = oc_k_stream) against the oracle (OpenMP restatement,
+    pinned to the verbatim reference at this size by tests/test_oracle.py): north-star bound 1e-5 of the extent after 100
+    steps."""
+    m = oc()
+    n = 2048
+    o = Oracle(n, n)
+    c = m.Cloth(n, n, exact=0)
+    o.step(100); c.step(100)
+    err = np.abs(c.download()[0].astype(np.float64) - o.state()[0]).max() / EXTENT
+    assert err <= 1e-5, f"fast mode at 2048^2: {err:.3e} of extent after 100 steps (tolerance 1e-5)"
+    c.close(); o.close()
+
+
+def test_fast_mode_linked_bands_equal_whole_cloth_bitwise():
+    """Tolerance mode (AUTO = oc_k_stream): the kernel rounds alike on its steady and generic paths, so three linked row
+    bands, a different window width and a batch of two give exactly the bits of the whole single cloth."""
+    m = oc()
+    nx, ny, steps = 700, 384, 80
+    whole = m.Cloth(nx, ny, exact=0)
+    whole.step(40)
+    wx, wxl = whole.download()
+    cuts = [0, 128, 256, 384]
+    bands = []
+    for b in range(3):
+        c = m.Cloth(nx, ny, row_begin=cuts[b], row_end=cuts[b + 1], halo_rows=2, exact=0)
+        sl = slice(cuts[b] * nx, cuts[b + 1] * nx)
+        c.upload(wx[sl], wxl[sl])
+        bands.append(c)
+    m.link_bands_local(bands)
+    pair = m.Cloth(nx, ny, batch=2, exact=0)
+    pair.upload(np.concatenate([wx, wx]), np.concatenate([wxl, wxl]))
+    for s in range(steps):
+        for c in bands:
+            c.step(1)
+    whole.step(steps); pair.step(steps)
+    wx, wxl = whole.download()
+    for b, c in enumerate(bands):
+        x, xl = c.download()
+        sl = slice(cuts[b] * nx, cuts[b + 1] * nx)
+        assert bitwise_equal(x, wx[sl]) and bitwise_equal(xl, wxl[sl]), f"band {b}: {nbad(x, wx[sl])} particles differ"
+        c.close()
+    px, pxl = pair.download()
+    n = nx * ny
+    assert bitwise_equal(px[:n], wx) and bitwise_equal(px[n:], wx) and bitwise_equal(pxl[n:], wxl)
+    whole.close(); pair.close()
+
+
 # ---------------------------------------------------------------------------------------------
 # parameters, interaction, batches, bands
 # ---------------------------------------------------------------------------------------------
