@@ -24,15 +24,6 @@
 #include "oc_march.cuh"
 
 
-// Rows in flight per CTA: the row a CTA publishes at the end of an iteration was requested OC_M2_DEPTH iterations earlier.
-// Depth 0 = one row in flight per CTA.  That happens to sit exactly at Little's law for the fast kernel (4 CTAs x 128 particles
-// per loaded memory latency of ~1870 cycles = 0.27 updates per clock and SM, tools/microbench/strip_copy.cu), but it is a
-// coincidence: with depth 1 the rates do not move (fast 62.7 / 74.1 G updates/s at 2048^2 / 8192^2 against 63.1 / 74.2) and
-// exact mode loses 5 % to the registers (255 + spills).  Measured on B200, round 2 (profiles/r2/march2_prefetch_depth.log).
-#ifndef OC_M2_DEPTH
-#define OC_M2_DEPTH 0
-#endif
-
 template <int WC>
 struct OcSmem2 {
     float X[6][OC_RING][WC + 4];        // x, y, z, vx, vy, vz     slot = row & 3, index = window column + 2
@@ -41,7 +32,7 @@ struct OcSmem2 {
     float FH1[3][2][WC / 2 + 2];        // f(+1,0) of each thread's b column, index = thread + 1
     float FDb[3][OC_RING][WC / 2 + 2];  // f(+1,+1) of the b column
     float FAa[3][OC_RING][WC / 2 + 2];  // f(-1,+1) of the a column
-    float4 stage[OC_M2_DEPTH + 1][4][WC / 2];      // landing zones of the asynchronous row loads: A[a], B[a], A[b], B[b] per thread
+    float4 stage[4][WC / 2];            // landing zone of the asynchronous row loads: A[a], B[a], A[b], B[b] per thread
 };
 
 // Linked row bands (multi-GPU): the cloth is cut into row bands, one handle per GPU, and the bands are
@@ -274,24 +265,6 @@ struct OcMarch2 {
         *reinterpret_cast<float2*>(&s.Dd[2][sl][pa]) = d.z;
     }
 
-    // asynchronous global loads of the row that iteration `jt` publishes (both columns) into landing zone jt mod (DEPTH + 1);
-    // always one cp.async group, empty if the row is not loaded (columns of the window outside the cloth get a benign
-    // far-away particle at rest)
-    OC_HD void request(int jt, bool interior)
-    {
-        Smem& s = *sm;
-        const int lrow = first + jt;
-        if (lrow >= in_lo && lrow < in_hi) {
-            const int z = jt % (OC_M2_DEPTH + 1);
-            const long long o = goff + (long long)lrow * U;
-            if (interior || oka) { oc_cp_async16(&s.stage[z][0][i], A + o); oc_cp_async16(&s.stage[z][1][i], B + o); }
-            else s.stage[z][0][i] = s.stage[z][1][i] = make_float4(1.0e3f + 8.0f * (float)pa, 1.0e3f, 1.0e3f + 8.0f * (float)(lrow & 63), oc_u2f(OC_W_PLAIN));
-            if (interior || okb) { oc_cp_async16(&s.stage[z][2][i], A + o + 1); oc_cp_async16(&s.stage[z][3][i], B + o + 1); }
-            else s.stage[z][2][i] = s.stage[z][3][i] = make_float4(1.0e3f + 8.0f * (float)(pa + 1), 1.0e3f, 1.0e3f + 8.0f * (float)(lrow & 63), oc_u2f(OC_W_PLAIN));
-        }
-        oc_cp_async_commit();
-    }
-
     template <bool kSteady, bool kInterior>
     OC_HD void iter(int it)
     {
@@ -304,7 +277,14 @@ struct OcMarch2 {
         // ---- asynchronous global loads of row lrow (both columns) into the thread's landing zone ------
         // (columns of the window outside the cloth get a benign far-away particle at rest)
         const bool doL = kSteady || (lrow >= in_lo && lrow < in_hi);
-        request(it + OC_M2_DEPTH, kInterior);          // row lrow + OC_M2_DEPTH (this iteration publishes row lrow, requested OC_M2_DEPTH iterations ago)
+        if (doL) {
+            const long long o = goff + (long long)lrow * U;
+            if (kInterior || oka) { oc_cp_async16(&s.stage[0][i], A + o); oc_cp_async16(&s.stage[1][i], B + o); }
+            else s.stage[0][i] = s.stage[1][i] = make_float4(1.0e3f + 8.0f * (float)pa, 1.0e3f, 1.0e3f + 8.0f * (float)(lrow & 63), oc_u2f(OC_W_PLAIN));
+            if (kInterior || okb) { oc_cp_async16(&s.stage[2][i], A + o + 1); oc_cp_async16(&s.stage[3][i], B + o + 1); }
+            else s.stage[2][i] = s.stage[3][i] = make_float4(1.0e3f + 8.0f * (float)(pa + 1), 1.0e3f, 1.0e3f + 8.0f * (float)(lrow & 63), oc_u2f(OC_W_PLAIN));
+            oc_cp_async_commit();
+        }
         const float rv1_j = rv1_n, rv2_j = rv2_n, dz2_j = dz2_n;
         {
             int r = row + 1;
@@ -552,9 +532,8 @@ struct OcMarch2 {
 
         // ---- publish the loaded row ------------------------------------------------------------------
         if (doL) {
-            oc_cp_async_wait_n<OC_M2_DEPTH>();
-            const int z = it % (OC_M2_DEPTH + 1);
-            publish(sl, s.stage[z][0][i], s.stage[z][1][i], s.stage[z][2][i], s.stage[z][3][i]);      // lrow = row + 4: same slot
+            oc_cp_async_wait();
+            publish(sl, s.stage[0][i], s.stage[1][i], s.stage[2][i], s.stage[3][i]);      // lrow = row + 4: same slot
         }
     }
 };
@@ -753,7 +732,6 @@ OC_HD bool oc_march2_body(Ctx& ctx, const OcConst& c, const float4* __restrict__
     if ((c.dbg & 8) && i == 0) oc_timeline_mark(c, 1);       // development: CTA timeline (OC_DEBUG=8)
 #endif
     if (!ctx.wait_deps(dep, c, r0, r1)) return false;
-    for (int jt = 0; jt < OC_M2_DEPTH; ++jt) m.request(jt, interior);      // the rows the first iterations publish
     int it = 0;
     for (int phase = 0; phase < 2; ++phase) {
         const int end = phase == 0 ? it_lo : n_it;
