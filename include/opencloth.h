@@ -54,9 +54,10 @@ typedef enum oc_kernel {
     OC_KERNEL_TWIN = 5,      /* marching stencil, one column per thread, every packed FP32x2 operation spans the same column of
                                 TWO independent tiles (two row segments of a strip, or two cloths of a batch); one substep
                                 per launch; whole cloths, batches, row bands and linked row bands */
-    OC_KERNEL_STREAM = 6     /* streaming gather over twin tiles: every particle evaluates all of its twelve springs itself
+    OC_KERNEL_STREAM = 6,    /* streaming gather over twin tiles: every particle evaluates all of its twelve springs itself
                                 from a shared-memory ring of rows (no force exchange, small per-thread state, many resident
                                 warps); same coverage as OC_KERNEL_TWIN */
+    OC_KERNEL_STREAM2 = 7    /* the same with two adjacent columns per thread: a third of the neighbour loads is shared */
 } oc_kernel;
 
 /* The reference's explicit integrators on this spring net.  "E:" =

@@ -288,7 +288,7 @@ static int validate(const oc_params* p)
     if (!(p->dt > 0.0f) || !(p->mass > 0.0f)) return oc_fail(OC_ERR_INVALID, "dt and mass must be positive");
     if (p->substeps_per_launch < 0 || p->substeps_per_launch > OC_MARCH_MAX_STAGES)
         return oc_fail(OC_ERR_INVALID, "substeps_per_launch must be 0..%d", OC_MARCH_MAX_STAGES);
-    if (p->kernel < OC_KERNEL_AUTO || p->kernel > OC_KERNEL_STREAM) return oc_fail(OC_ERR_INVALID, "bad kernel id");
+    if (p->kernel < OC_KERNEL_AUTO || p->kernel > OC_KERNEL_STREAM2) return oc_fail(OC_ERR_INVALID, "bad kernel id");
     if (p->integrator < OC_INTEGRATOR_VERLET || p->integrator > OC_INTEGRATOR_SEMI_IMPLICIT) return oc_fail(OC_ERR_INVALID, "bad integrator id %d", p->integrator);
     if (p->provot != 0 && p->provot != 1) return oc_fail(OC_ERR_INVALID, "provot must be 0 or 1");
     if ((p->integrator != OC_INTEGRATOR_VERLET || p->provot) && (p->row_begin != 0 || p->row_end != 0) && (p->row_begin > 0 || p->row_end < p->ny))
@@ -747,7 +747,7 @@ extern "C" int oc_reset_pins(oc_cloth* c)
 static int pick_kernel(const oc_cloth* c)
 {
     const bool can_reside = !c->q.band && (long long)c->p.nx * c->p.ny <= OC_RESIDENT_MAX_PARTICLES;
-    if (c->link.on) return (c->p.kernel == OC_KERNEL_TWIN || c->p.kernel == OC_KERNEL_STREAM) ? c->p.kernel : ((c->p.kernel == OC_KERNEL_AUTO && !c->p.exact) ? OC_KERNEL_STREAM : OC_KERNEL_MARCH2);      // linked row bands: the kernels that push their boundary rows
+    if (c->link.on) return (c->p.kernel == OC_KERNEL_TWIN || c->p.kernel == OC_KERNEL_STREAM || c->p.kernel == OC_KERNEL_STREAM2) ? c->p.kernel : ((c->p.kernel == OC_KERNEL_AUTO && !c->p.exact) ? OC_KERNEL_STREAM : OC_KERNEL_MARCH2);      // linked row bands: the kernels that push their boundary rows
     if (c->p.integrator != OC_INTEGRATOR_VERLET) return OC_KERNEL_GATHER;      // state (X, V): oc_k_gather_xv
     if (c->p.provot && (c->p.kernel == OC_KERNEL_RESIDENT || c->p.kernel == OC_KERNEL_AUTO)) return OC_KERNEL_MARCH2;   // a pass after EVERY substep
     if (c->p.kernel == OC_KERNEL_RESIDENT) return can_reside ? OC_KERNEL_RESIDENT : OC_KERNEL_MARCH2;   // a cloth that does not fit one CTA's shared memory: the fastest general kernel
@@ -768,8 +768,8 @@ static int pick_kernel(const oc_cloth* c)
 static int launch_rows(oc_cloth* c, int kern, const OcLaunch& L, int ra, int rb)
 {
     if (rb <= ra) return OC_OK;
-    if ((kern == OC_KERNEL_TWIN || kern == OC_KERNEL_STREAM) && rb - ra < 2) kern = OC_KERNEL_MARCH2;      // (a single row cannot be cut into two tiles)
-    if (kern == OC_KERNEL_MARCH2 || kern == OC_KERNEL_TWIN || kern == OC_KERNEL_STREAM) {
+    if ((kern == OC_KERNEL_TWIN || kern == OC_KERNEL_STREAM || kern == OC_KERNEL_STREAM2) && rb - ra < 2) kern = OC_KERNEL_MARCH2;      // (a single row cannot be cut into two tiles)
+    if (kern == OC_KERNEL_MARCH2 || kern == OC_KERNEL_TWIN || kern == OC_KERNEL_STREAM || kern == OC_KERNEL_STREAM2) {
         int nl = 0;
         OcPeer2 peer = {};
         if (c->link.on) {
@@ -787,7 +787,7 @@ static int launch_rows(oc_cloth* c, int kern, const OcLaunch& L, int ra, int rb)
             ? oc_march2_launch(c->k, c->p.exact != 0, ra, rb, c->sm_count, c->buf[L.src_a], c->buf[L.src_b], c->buf[L.dst], c->stream, &nl, &c->chain,
                                c->link.on ? &peer : nullptr)
             : oc_twin_launch(c->k, c->p.exact != 0, ra, rb, c->sm_count, c->buf[L.src_a], c->buf[L.src_b], c->buf[L.dst], c->stream, &nl, &c->chain,
-                             c->link.on ? &peer : nullptr, kern == OC_KERNEL_STREAM ? 1 : 0);
+                             c->link.on ? &peer : nullptr, kern == OC_KERNEL_STREAM2 ? 2 : (kern == OC_KERNEL_STREAM ? 1 : 0));
         c->launches += nl;
         if (e != cudaSuccess) return oc_fail(OC_ERR_CUDA, "march2 kernel launch failed: %s", cudaGetErrorString(e));
     } else if (kern == OC_KERNEL_RESIDENT) {
@@ -867,7 +867,7 @@ static int step_impl(oc_cloth* c, int n, cudaStream_t split_stream, bool want_sp
     // host <-> device pipeline (upload_impl): the first substep after a chunked upload follows the chunks
     c->pipe.step_chunks = 0;
     const bool pipe_first = c->pipe.up_chunks > 1 && n >= 1 && !c->p.provot && !c->q.band && c->p.batch == 1 &&
-                            (kern == OC_KERNEL_MARCH2 || kern == OC_KERNEL_TWIN || kern == OC_KERNEL_STREAM || kern == OC_KERNEL_GATHER);
+                            (kern == OC_KERNEL_MARCH2 || kern == OC_KERNEL_TWIN || kern == OC_KERNEL_STREAM || kern == OC_KERNEL_STREAM2 || kern == OC_KERNEL_GATHER);
     if (!pipe_first) { const int rcj = join_upload(c); if (rcj) return rcj; }
     if (pipe_first) {
         const int nch = c->pipe.up_chunks, n_call = n;

@@ -3,6 +3,7 @@
 #include "oc_march2.cuh"
 #include "oc_twin.cuh"
 #include "oc_stream.cuh"
+#include "oc_stream2.cuh"
 #include <cstdlib>
 #include <cstdio>
 
@@ -302,11 +303,14 @@ extern "C" const void* oc_twin_fn_exact(int WC, int occ);
 extern "C" const void* oc_twin_fn_fast(int WC, int occ);
 extern "C" const void* oc_stream_fn_exact(int WC, int occ);
 extern "C" const void* oc_stream_fn_fast(int WC, int occ);
-// variant: 0 = oc_k_twin, 1 = oc_k_stream (same tiles, same launch protocol)
-static int g_occT[2][2][2];      // [variant][exact][WC == 128]
+extern "C" const void* oc_stream2_fn_exact(int WC, int occ);
+extern "C" const void* oc_stream2_fn_fast(int WC, int occ);
+// variant: 0 = oc_k_twin, 1 = oc_k_stream, 2 = oc_k_stream2 (same tiles, same launch protocol)
+static int g_occT[3][2][2];      // [variant][exact][WC == 128]
 
 static size_t smemT(int WC, bool exact, int variant)
 {
+    if (variant == 2) return exact ? sizeof(OcSmemS2<128, true>) : sizeof(OcSmemS2<128, false>);
     if (variant == 1) {
         if (WC == 64) return exact ? sizeof(OcSmemS<64, true>) : sizeof(OcSmemS<64, false>);
         return exact ? sizeof(OcSmemS<128, true>) : sizeof(OcSmemS<128, false>);
@@ -316,19 +320,21 @@ static size_t smemT(int WC, bool exact, int variant)
 }
 static int pick_wct(int nx, int variant)
 {
+    if (variant == 2) return 128;          // two columns per thread: 64 threads, the smallest CTA the dependency polling allows
     const char* env = getenv(variant == 1 ? "OC_STREAM_WC" : "OC_TWIN_WC");
     if (env && (atoi(env) == 64 || atoi(env) == 128)) return atoi(env);
     return nx <= 64 ? 64 : 128;
 }
 static const void* twin_fn_v(int WC, bool exact, int variant, int v)
 {
+    if (variant == 2) return exact ? oc_stream2_fn_exact(WC, v) : oc_stream2_fn_fast(WC, v);
     if (variant == 1) return exact ? oc_stream_fn_exact(WC, v) : oc_stream_fn_fast(WC, v);
     return exact ? oc_twin_fn_exact(WC, v) : oc_twin_fn_fast(WC, v);
 }
 // development: OC_TWIN_OCC / OC_STREAM_OCC = resident CTAs per SM the kernel variant is compiled for (see the *_inst.cu)
 static const void* twin_fn(int WC, bool exact, int variant)
 {
-    const char* env = getenv(variant == 1 ? "OC_STREAM_OCC" : "OC_TWIN_OCC");
+    const char* env = getenv(variant == 2 ? "OC_STREAM2_OCC" : (variant == 1 ? "OC_STREAM_OCC" : "OC_TWIN_OCC"));
     const int v = env ? atoi(env) : 0;
     const void* fn = v > 0 ? twin_fn_v(WC, exact, variant, v) : nullptr;
     return fn ? fn : twin_fn_v(WC, exact, variant, 0);
@@ -337,15 +343,17 @@ static const void* twin_fn(int WC, bool exact, int variant)
 int oc_twin_configure(int device)
 {
     (void)device;
-    for (int variant = 0; variant < 2; ++variant)
+    for (int variant = 0; variant < 3; ++variant)
         for (int e = 0; e < 2; ++e)
             for (int w = 0; w < 2; ++w) {
                 const int WC = w ? 128 : 64;
+                g_occT[variant][e][w] = 0;
+                if (variant == 2 && WC != 128) continue;
                 const void* fn = twin_fn(WC, e != 0, variant);
                 cudaError_t err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemT(WC, e != 0, variant));
                 if (err != cudaSuccess) return (int)err;
                 int occ = 0;
-                err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, WC, smemT(WC, e != 0, variant));
+                err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, variant == 2 ? WC / 2 : WC, smemT(WC, e != 0, variant));
                 if (err != cudaSuccess) return (int)err;
                 g_occT[variant][e][w] = occ;
             }
@@ -437,7 +445,7 @@ int oc_twin_plan(const OcConst& c, bool exact, bool chained, bool linked, int ra
         if (linked) best_rs = fix_last_segment(rows, best_rs);
     }
     pl->TW = WC; pl->S = 1; pl->x_halo = x_halo; pl->W_out = W_out; pl->nstrips = nstrips;
-    pl->RS = best_rs; pl->nseg = (rows + best_rs - 1) / best_rs; pl->threads = WC; pl->smem = smemT(WC, exact, variant);
+    pl->RS = best_rs; pl->nseg = (rows + best_rs - 1) / best_rs; pl->threads = variant == 2 ? WC / 2 : WC; pl->smem = smemT(WC, exact, variant);
     seg->rs = seg->rs_e = best_rs; seg->nstrips = nstrips; seg->nseg_all = pl->nseg; seg->n_extra = 0; seg->rev = 0;
     return 0;
 }
@@ -462,7 +470,7 @@ cudaError_t oc_twin_launch(const OcConst& c, bool exact, int ra, int rb, int sm_
         static int last_ra = -1, last_rb = -1;
         if (last_ra != ra || last_rb != rb) {
             last_ra = ra; last_rb = rb;
-            fprintf(stderr, "[oc] %s plan rows [%d,%d): strips %d x segs %d; rows/segment %d; pair_cloths %d; CTAs/SM %d; exact %d\n", variant ? "stream" : "twin",
+            fprintf(stderr, "[oc] %s plan rows [%d,%d): strips %d x segs %d; rows/segment %d; pair_cloths %d; CTAs/SM %d; exact %d\n", variant == 2 ? "stream2" : (variant ? "stream" : "twin"),
                     ra, rb, seg.nstrips, seg.nseg_all, seg.rs, map.pair_cloths, g_occT[variant][exact ? 1 : 0][WC == 128], (int)exact);
         }
     }

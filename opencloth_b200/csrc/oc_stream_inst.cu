@@ -1,6 +1,7 @@
 // oc_stream_inst.cu — instantiations of the streaming gather kernel, one object per mode.
 // occ = resident CTAs per SM the registers are capped for (0: the default of the width).
 #include "oc_stream.cuh"
+#include "oc_stream2.cuh"
 
 #if OC_INST_EXACT
 typedef MathExact OcInstMath;
@@ -27,4 +28,20 @@ extern "C" const void* oc_stream_fn_fast(int WC, int occ)
         }
     }
     return nullptr;
+}
+
+// oc_k_stream2 (two columns per thread, 64 threads per 128-column window)
+#if OC_INST_EXACT
+extern "C" const void* oc_stream2_fn_exact(int WC, int occ)
+#else
+extern "C" const void* oc_stream2_fn_fast(int WC, int occ)
+#endif
+{
+    if (WC != 128) return nullptr;
+    switch (occ) {
+    case 4: return (const void*)&oc_k_stream2<OcInstMath, 128, 4>;
+    case 5: return (const void*)&oc_k_stream2<OcInstMath, 128, 5>;
+    case 0: case 6: return (const void*)&oc_k_stream2<OcInstMath, 128, 6>;
+    default: return nullptr;
+    }
 }

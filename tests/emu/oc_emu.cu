@@ -19,6 +19,7 @@
 #include "../../opencloth_b200/csrc/oc_march2.cuh"
 #include "../../opencloth_b200/csrc/oc_twin.cuh"
 #include "../../opencloth_b200/csrc/oc_stream.cuh"
+#include "../../opencloth_b200/csrc/oc_stream2.cuh"
 #include "../../opencloth_b200/csrc/oc_resident.cuh"
 
 #include <ucontext.h>
@@ -288,7 +289,11 @@ static int emu_twin(EmuCloth* e, const OcLaunch& L, int RS)
         for (int by = 0; by < nk; ++by)
             for (int bx = 0; bx < nstrips; ++bx) {
                 int ra = L.ra, rb = L.rb;
-                if (kVariant == 1)
+                if (kVariant == 2)
+                    rc |= run_cta(WC / 2, bx, by, bz, sizeof(OcSmemS2<WC, M::kExact>), [&](EmuCtx& ctx) {
+                        oc_stream2_body<M, WC, EmuCtx>(ctx, k, A, B, C, ra, rb, seg, x_halo, map, dep);
+                    });
+                else if (kVariant == 1)
                     rc |= run_cta(WC, bx, by, bz, sizeof(OcSmemS<WC, M::kExact>), [&](EmuCtx& ctx) {
                         oc_stream_body<M, WC, EmuCtx>(ctx, k, A, B, C, ra, rb, seg, x_halo, map, dep);
                     });
@@ -459,7 +464,7 @@ int emu_step(void* h, int n, int kernel, int exact, int k, int TW, int RS)
     if (e->q.xv) kernel = 1;
     if (e->p.provot || e->q.xv) k = 1;
     if (e->q.band && !e->q.linked && e->q.fresh + n > e->q.kmax) return -3;
-    if (e->q.linked && kernel != 3 && kernel != 5 && kernel != 6) return -2;
+    if (e->q.linked && kernel != 3 && kernel != 5 && kernel != 6 && kernel != 7) return -2;
     int rc = 0;
     while (n > 0) {
         OcLaunch L;
@@ -472,6 +477,10 @@ int emu_step(void* h, int n, int kernel, int exact, int k, int TW, int RS)
         if (kernel == 4) {
             int r = exact ? emu_resident<MathExact>(e, L, TW) : emu_resident<MathFast>(e, L, TW);
             if (r == -2) return -2;
+            rc |= r;
+        } else if (kernel == 7) {
+            int r = exact ? emu_twin_dispatch<MathExact, 2>(e, L, TW, RS) : emu_twin_dispatch<MathFast, 2>(e, L, TW, RS);
+            if (r == -2 || r == -4) return r;
             rc |= r;
         } else if (kernel == 6) {
             int r = exact ? emu_twin_dispatch<MathExact, 1>(e, L, TW, RS) : emu_twin_dispatch<MathFast, 1>(e, L, TW, RS);

@@ -24,7 +24,7 @@ def _newer(target, *sources):
 def build_emulator():
     src = os.path.join(ROOT, "tests", "emu", "oc_emu.cu")
     csrc = os.path.join(ROOT, "opencloth_b200", "csrc")
-    deps = [src] + [os.path.join(csrc, f) for f in ("oc_core.cuh", "oc_host.h", "oc_gather.cuh", "oc_provot.cuh", "oc_normals.cuh", "oc_march.cuh", "oc_march2.cuh", "oc_twin.cuh", "oc_stream.cuh", "oc_resident.cuh")]
+    deps = [src] + [os.path.join(csrc, f) for f in ("oc_core.cuh", "oc_host.h", "oc_gather.cuh", "oc_provot.cuh", "oc_normals.cuh", "oc_march.cuh", "oc_march2.cuh", "oc_twin.cuh", "oc_stream.cuh", "oc_stream2.cuh", "oc_resident.cuh")]
     if _newer(EMU_SO, *deps):
         return
     subprocess.check_call([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-std=c++17",

@@ -11,7 +11,7 @@ import pytest
 import helpers
 from helpers import Emu, Oracle, bitwise_equal
 
-GATHER, MARCH, MARCH2, RESIDENT, TWIN, STREAM = 1, 2, 3, 4, 5, 6
+GATHER, MARCH, MARCH2, RESIDENT, TWIN, STREAM, STREAM2 = 1, 2, 3, 4, 5, 6, 7
 
 
 def run_pair(nx, ny, pre, steps, **kw):
@@ -117,7 +117,7 @@ TWIN_CASES = [
 ]
 
 
-@pytest.mark.parametrize("kernel", [TWIN, STREAM])
+@pytest.mark.parametrize("kernel", [TWIN, STREAM, STREAM2])
 @pytest.mark.parametrize("nx,ny,pre,steps,WC,RS", TWIN_CASES)
 def test_twin_kernel_body(nx, ny, pre, steps, WC, RS, kernel):
     """oc_k_twin and oc_k_stream (the streaming gather kernel runs on the same twin tiles)"""
@@ -129,7 +129,7 @@ def test_twin_refuses_an_odd_number_of_segments():
     assert helpers.emu_lib().emu_step(e.h, 1, TWIN, 1, 1, 32, 7) == -2      # 3 segments of 7 rows
 
 
-@pytest.mark.parametrize("kernel", [TWIN, STREAM])
+@pytest.mark.parametrize("kernel", [TWIN, STREAM, STREAM2])
 @pytest.mark.parametrize("order", [1, 2])
 def test_twin_is_independent_of_thread_schedule(order, kernel):
     L = helpers.emu_lib()
@@ -141,7 +141,7 @@ def test_twin_is_independent_of_thread_schedule(order, kernel):
         L.emu_set_order(0)
 
 
-@pytest.mark.parametrize("kernel", [TWIN, STREAM])
+@pytest.mark.parametrize("kernel", [TWIN, STREAM, STREAM2])
 @pytest.mark.parametrize("pair_cloths,B,RS", [(1, 4, 0), (1, 2, 6), (0, 3, 3), (0, 2, 9)])
 def test_twin_batched_cloths_are_independent(pair_cloths, B, RS, kernel):
     """The twins of a CTA are two segments of one cloth, or (bit 16 of RS) the same tile of two cloths of the batch."""
@@ -176,6 +176,11 @@ def test_stream_fast_mode_does_not_depend_on_the_tiling():
         got = e.download()
         ref = ref or got
         assert bitwise_equal(got[0], ref[0]) and bitwise_equal(got[1], ref[1]), (WC, RS)
+    # oc_k_stream2 (two columns per thread) does the same arithmetic per particle in the same order: the same bits
+    for WC, RS in ((64, 0), (16, 5)):
+        e = Emu(nx, ny); e.upload(x0, xl0); e.step(12, kernel=STREAM2, exact=0, TW=WC, RS=RS)
+        got = e.download()
+        assert bitwise_equal(got[0], ref[0]) and bitwise_equal(got[1], ref[1]), ("stream2", WC, RS)
 
 
 @pytest.mark.parametrize("order", [1, 2])
@@ -234,7 +239,7 @@ def test_batched_cloths_are_independent():
         assert bitwise_equal(ex[sl], ox) and bitwise_equal(exl[sl], oxl), f"cloth {b}"
 
 
-@pytest.mark.parametrize("nbands,halo,k,kernel", [(2, 4, 1, MARCH), (3, 8, 2, MARCH), (4, 4, 2, MARCH), (2, 6, 1, GATHER), (3, 8, 4, MARCH), (3, 8, 1, TWIN), (2, 4, 1, TWIN), (3, 8, 1, STREAM), (2, 4, 1, STREAM)])
+@pytest.mark.parametrize("nbands,halo,k,kernel", [(2, 4, 1, MARCH), (3, 8, 2, MARCH), (4, 4, 2, MARCH), (2, 6, 1, GATHER), (3, 8, 4, MARCH), (3, 8, 1, TWIN), (2, 4, 1, TWIN), (3, 8, 1, STREAM), (2, 4, 1, STREAM), (3, 8, 1, STREAM2)])
 def test_row_bands_with_halo_exchange_equal_single_domain(nbands, halo, k, kernel):
     """Row-band decomposition: g bands with halo_rows rows of neighbour state, one
     exchange per halo_rows/2 substeps, redundant recomputation of the shrinking halo in between.
@@ -266,7 +271,7 @@ def test_row_bands_with_halo_exchange_equal_single_domain(nbands, halo, k, kerne
         exchange()
         n = per if rnd < 2 else max(1, per - 1)     # last round: a partial group
         for e in bands:
-            e.step(n, kernel=kernel, k=k, TW=32, RS=0 if kernel in (TWIN, STREAM) else 5)
+            e.step(n, kernel=kernel, k=k, TW=32, RS=0 if kernel in (TWIN, STREAM, STREAM2) else 5)
         total += n
     whole.step(total)
     wx, wxl = whole.state()
@@ -278,7 +283,7 @@ def test_row_bands_with_halo_exchange_equal_single_domain(nbands, halo, k, kerne
 
 @pytest.mark.parametrize("nbands,WC,RS,nx,kernel", [(2, 16, 7, 23, MARCH2), (3, 16, 6, 37, MARCH2), (4, 32, 12, 23, MARCH2), (3, 16, 0, 30, MARCH2),
                                                     (2, 16, 6, 23, TWIN), (3, 16, 4, 37, TWIN), (4, 32, 6, 23, TWIN), (3, 16, 0, 30, TWIN),
-                                                    (2, 16, 6, 23, STREAM), (3, 16, 4, 37, STREAM), (4, 32, 6, 23, STREAM), (3, 16, 0, 30, STREAM)])
+                                                    (2, 16, 6, 23, STREAM), (3, 16, 4, 37, STREAM), (4, 32, 6, 23, STREAM), (3, 16, 0, 30, STREAM), (2, 16, 6, 23, STREAM2), (3, 16, 4, 37, STREAM2), (4, 32, 6, 23, STREAM2)])
 def test_linked_row_bands_push_their_boundary_rows(nbands, WC, RS, nx, kernel):
     """Linked row bands (OcPeer2): no exchange step — every band computes exactly its owned rows, and the tiles at a
     band edge store the two rows the neighbour's stencil reaches straight into the neighbour's halo.  Same kernel

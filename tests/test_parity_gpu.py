@@ -31,7 +31,7 @@ def golden(name):
 
 
 def kid(m, kernel):
-    return {"march": m.OC_KERNEL_MARCH, "gather": m.OC_KERNEL_GATHER, "march2": m.OC_KERNEL_MARCH2, "resident": m.OC_KERNEL_RESIDENT, "twin": m.OC_KERNEL_TWIN, "stream": m.OC_KERNEL_STREAM}[kernel]
+    return {"march": m.OC_KERNEL_MARCH, "gather": m.OC_KERNEL_GATHER, "march2": m.OC_KERNEL_MARCH2, "resident": m.OC_KERNEL_RESIDENT, "twin": m.OC_KERNEL_TWIN, "stream": m.OC_KERNEL_STREAM, "stream2": m.OC_KERNEL_STREAM2}[kernel]
 
 
 def nbad(a, b):
@@ -42,7 +42,7 @@ def nbad(a, b):
 # golden vectors of the verbatim reference
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("name", ["grid_21x21.npz", "grid_37x23.npz", "grid_64x64.npz", "grid_256x256.npz"])
-@pytest.mark.parametrize("kernel,k", [("march", 1), ("march", 4), ("gather", 1), ("march2", 1), ("resident", 1), ("twin", 1), ("stream", 1)])
+@pytest.mark.parametrize("kernel,k", [("march", 1), ("march", 4), ("gather", 1), ("march2", 1), ("resident", 1), ("twin", 1), ("stream", 1), ("stream2", 1)])
 def test_cuda_matches_reference_golden(name, kernel, k):
     g, meta = golden(name)
     nx, ny = meta["nx"], meta["ny"]
@@ -78,7 +78,7 @@ def test_energy_trajectory_matches_reference():
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("nx,ny,pre,steps", [(3, 3, 0, 300), (4, 7, 0, 300), (21, 21, 1650, 400), (37, 23, 1800, 300),
                                              (100, 61, 1500, 200), (129, 40, 800, 100), (300, 200, 600, 100), (1000, 37, 300, 50)])
-@pytest.mark.parametrize("kernel,k", [("march", 1), ("march", 2), ("march", 8), ("gather", 1), ("march2", 1), ("resident", 1), ("twin", 1), ("stream", 1)])
+@pytest.mark.parametrize("kernel,k", [("march", 1), ("march", 2), ("march", 8), ("gather", 1), ("march2", 1), ("resident", 1), ("twin", 1), ("stream", 1), ("stream2", 1)])
 def test_cuda_matches_oracle_bitwise(nx, ny, pre, steps, kernel, k):
     m = oc()
     x0, xl0 = helpers.developed_state(nx, ny, pre)
@@ -168,7 +168,7 @@ def test_large_grid_matches_oracle_2048():
 
 
 @pytest.mark.parametrize("nx,ny,steps,kernel", [(2048, 2048, 3000, "march2"), (4096, 1200, 600, "march2"), (1100, 5000, 600, "march2"),
-                                                (2048, 2048, 2400, "twin"), (1100, 5000, 600, "twin"), (2048, 2048, 2400, "stream"), (1100, 5000, 600, "stream")])
+                                                (2048, 2048, 2400, "twin"), (1100, 5000, 600, "twin"), (2048, 2048, 2400, "stream"), (1100, 5000, 600, "stream"), (1100, 5000, 600, "stream2")])
 def test_chained_launches_match_gather_kernel_full_size(nx, ny, steps, kernel):
     """Consecutive oc_k_march2 launches are chained by programmatic dependent launch and per-tile flags instead
     of a barrier between steps (OcDep2; active for tiles of >= 32 rows, i.e. only at full size).  The gather
@@ -206,7 +206,7 @@ def test_chained_launches_match_gather_kernel_full_size(nx, ny, steps, kernel):
     a.close(); g.close()
 
 
-@pytest.mark.parametrize("kernel,batch", [("march2", 96), ("twin", 96), ("twin", 33), ("stream", 96), ("stream", 33)])
+@pytest.mark.parametrize("kernel,batch", [("march2", 96), ("twin", 96), ("twin", 33), ("stream", 96), ("stream", 33), ("stream2", 96)])
 def test_chained_launches_batched_cloths_match_gather_kernel(kernel, batch):
     """The same for a batch (BASELINE config 5 shape): the tile flags are per cloth, every cloth one 128-row tile
     (oc_k_twin: a CTA takes the same tile of two cloths, or with an odd batch two 64-row tiles of one cloth)."""
@@ -308,7 +308,12 @@ def test_fast_mode_linked_bands_equal_whole_cloth_bitwise():
     px, pxl = pair.download()
     n = nx * ny
     assert bitwise_equal(px[:n], wx) and bitwise_equal(px[n:], wx) and bitwise_equal(pxl[n:], wxl)
-    whole.close(); pair.close()
+    # oc_k_stream2 (two columns per thread) does the same arithmetic per particle in the same order
+    two = m.Cloth(nx, ny, exact=0, kernel=m.OC_KERNEL_STREAM2)
+    two.step(40 + steps)
+    tx, txl = two.download()
+    assert bitwise_equal(tx, wx) and bitwise_equal(txl, wxl)
+    whole.close(); pair.close(); two.close()
 
 
 # ---------------------------------------------------------------------------------------------
@@ -454,7 +459,7 @@ def test_row_bands_chained_full_size(nx, ny, nbands, halo, kernel):
 
 
 @pytest.mark.parametrize("nx,ny,nbands,steps,kernel", [(512, 384, 3, 60, "auto"), (200, 64, 4, 40, "auto"), (2304, 2048, 2, 120, "auto"), (1100, 1536, 4, 90, "auto"),
-                                                       (512, 384, 3, 60, "twin"), (2304, 2048, 2, 120, "twin"), (512, 384, 3, 60, "stream"), (2304, 2048, 2, 120, "stream")])
+                                                       (512, 384, 3, 60, "twin"), (2304, 2048, 2, 120, "twin"), (512, 384, 3, 60, "stream"), (2304, 2048, 2, 120, "stream"), (512, 384, 3, 60, "stream2")])
 def test_linked_row_bands_equal_whole_cloth(nx, ny, nbands, steps, kernel):
     """Linked row bands (the multi-GPU path: in-kernel peer stores of the boundary rows + flag words between the
     bands' tiles, no exchange step), here with all bands on ONE device in one process — the same kernel path and the
