@@ -296,8 +296,11 @@ def run_ours(args):
         particles_total = nx * ny
     else:
         linked = args.exchange == "linked"
+        # fast mode: every handle of the run (bands, the whole cloth of the parity check) uses oc_k_stream, whose result does
+        # not depend on the decomposition; AUTO would pick it anyway at 8192^2 / N <= 8
+        band_kernel = oc.OC_KERNEL_AUTO if exact else oc.OC_KERNEL_STREAM
         band = B.CudaBand(nx, ny, world, rank, 2 if linked else args.halo_rows, local, exact=exact,
-                          substeps_per_launch=1 if linked else args.k)
+                          substeps_per_launch=1 if linked else args.k, kernel=band_kernel)
         cloth = band.cloth
         particles_total = nx * ny
     # a non-default torch stream: the library launches on it and torch events time it
@@ -382,7 +385,7 @@ def run_ours(args):
             dist.all_gather_object(every, mine)
             if rank == 0:
                 # the independent cross-check kernel (one thread per particle, 12-neighbour gather, scalar exact math)
-                whole = oc.Cloth(nx, ny, device=local, exact=exact, kernel=oc.OC_KERNEL_GATHER if exact else oc.OC_KERNEL_AUTO)
+                whole = oc.Cloth(nx, ny, device=local, exact=exact, kernel=oc.OC_KERNEL_GATHER if exact else oc.OC_KERNEL_STREAM)
                 whole.step(steps_taken)
                 wx, wl = whole.download()
                 whole.close()

@@ -44,7 +44,7 @@ typedef enum oc_status {
 
 typedef enum oc_kernel {
     OC_KERNEL_AUTO = 0,      /* resident for small whole cloths; else, one substep per launch: march2 in exact mode, stream in fast
-                                mode; march for k > 1 */
+                                mode from about three million particles per handle (march2 below); march for k > 1 */
     OC_KERNEL_GATHER = 1,    /* one thread per particle, 12-neighbour gather from global memory */
     OC_KERNEL_MARCH = 2,     /* fused shared-memory marching stencil, one column per thread, k substeps per launch */
     OC_KERNEL_MARCH2 = 3,    /* the same with two columns per thread (one substep per launch) */

@@ -744,10 +744,11 @@ extern "C" int oc_reset_pins(oc_cloth* c)
 // ------------------------------------------------------------------------------------------------
 // step
 // ------------------------------------------------------------------------------------------------
+static bool oc_stream_pays(const oc_cloth* c) { return (long long)c->p.nx * c->rows_own * c->p.batch >= (3LL << 20); }
 static int pick_kernel(const oc_cloth* c)
 {
     const bool can_reside = !c->q.band && (long long)c->p.nx * c->p.ny <= OC_RESIDENT_MAX_PARTICLES;
-    if (c->link.on) return (c->p.kernel == OC_KERNEL_TWIN || c->p.kernel == OC_KERNEL_STREAM || c->p.kernel == OC_KERNEL_STREAM2) ? c->p.kernel : ((c->p.kernel == OC_KERNEL_AUTO && !c->p.exact) ? OC_KERNEL_STREAM : OC_KERNEL_MARCH2);      // linked row bands: the kernels that push their boundary rows
+    if (c->link.on) return (c->p.kernel == OC_KERNEL_TWIN || c->p.kernel == OC_KERNEL_STREAM || c->p.kernel == OC_KERNEL_STREAM2) ? c->p.kernel : ((c->p.kernel == OC_KERNEL_AUTO && !c->p.exact && oc_stream_pays(c)) ? OC_KERNEL_STREAM : OC_KERNEL_MARCH2);      // linked row bands: the kernels that push their boundary rows
     if (c->p.integrator != OC_INTEGRATOR_VERLET) return OC_KERNEL_GATHER;      // state (X, V): oc_k_gather_xv
     if (c->p.provot && (c->p.kernel == OC_KERNEL_RESIDENT || c->p.kernel == OC_KERNEL_AUTO)) return OC_KERNEL_MARCH2;   // a pass after EVERY substep
     if (c->p.kernel == OC_KERNEL_RESIDENT) return can_reside ? OC_KERNEL_RESIDENT : OC_KERNEL_MARCH2;   // a cloth that does not fit one CTA's shared memory: the fastest general kernel
@@ -760,8 +761,11 @@ static int pick_kernel(const oc_cloth* c)
     if (c->p.substeps_per_launch > 1) return OC_KERNEL_MARCH;
     // one substep per launch.  Exact mode: every spring once, two columns per thread (oc_k_march2; the bit-exact arithmetic is
     // FMA-pipe heavy, so halving it wins).  Fast mode: the streaming gather kernel (oc_k_stream; twice the spring arithmetic,
-    // no force exchange, three times the resident warps) is 3-8 % ahead.
-    return c->p.exact ? OC_KERNEL_MARCH2 : OC_KERNEL_STREAM;
+    // no force exchange, more resident warps) is 1-7 % ahead from about three million particles per handle (2048^2: 66.8
+    // against 63.0 G updates/s; 512 x 128^2: 70.8 against 66.9); below that its CTAs of two tiles leave too few rows per tile
+    // (1536^2: 49.0 against 51.7; 1024^2: 31 against 41).  DESIGN.md 4.2-4.3.
+    if (c->p.exact) return OC_KERNEL_MARCH2;
+    return oc_stream_pays(c) ? OC_KERNEL_STREAM : OC_KERNEL_MARCH2;
 }
 
 // one launch: rows [ra, rb) of the launch descriptor's destination, S substeps

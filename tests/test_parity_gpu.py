@@ -278,22 +278,23 @@ def test_fast_mode_within_tolerance_at_bench_size():
 
 
 def test_fast_mode_linked_bands_equal_whole_cloth_bitwise():
-    """Tolerance mode (AUTO = oc_k_stream): the kernel rounds alike on its steady and generic paths, so three linked row
-    bands, a different window width and a batch of two give exactly the bits of the whole single cloth."""
+    """Tolerance mode of oc_k_stream (AUTO's choice for large handles): the kernel rounds alike on its steady and generic
+    paths, so three linked row bands and a batch of two give exactly the bits of the whole single cloth."""
     m = oc()
     nx, ny, steps = 700, 384, 80
-    whole = m.Cloth(nx, ny, exact=0)
+    K = m.OC_KERNEL_STREAM
+    whole = m.Cloth(nx, ny, exact=0, kernel=K)
     whole.step(40)
     wx, wxl = whole.download()
     cuts = [0, 128, 256, 384]
     bands = []
     for b in range(3):
-        c = m.Cloth(nx, ny, row_begin=cuts[b], row_end=cuts[b + 1], halo_rows=2, exact=0)
+        c = m.Cloth(nx, ny, row_begin=cuts[b], row_end=cuts[b + 1], halo_rows=2, exact=0, kernel=K)
         sl = slice(cuts[b] * nx, cuts[b + 1] * nx)
         c.upload(wx[sl], wxl[sl])
         bands.append(c)
     m.link_bands_local(bands)
-    pair = m.Cloth(nx, ny, batch=2, exact=0)
+    pair = m.Cloth(nx, ny, batch=2, exact=0, kernel=K)
     pair.upload(np.concatenate([wx, wx]), np.concatenate([wxl, wxl]))
     for s in range(steps):
         for c in bands:
