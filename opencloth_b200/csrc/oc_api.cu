@@ -500,15 +500,29 @@ static int pipe_chunks(const oc_cloth* c)
 {
     static const int env = getenv("OC_PIPE_CHUNKS") ? atoi(getenv("OC_PIPE_CHUNKS")) : 0;
     if (c->p.batch != 1 || c->q.band) return 1;
-    int n = env > 0 ? env : 8;             // measured at 2048^2 (tools/e2e_sweep.py): 4: 3.15 ms, 8: 3.04, 16: 3.11, 32: 3.21 per round trip
+    int n = env > 0 ? env : 10;            // measured at 2048^2 (tools/run_e2e.sh), ms per round trip: equal chunks 4: 3.15, 8: 3.02, 16: 3.15, 32: 3.21;
+                                           // tapered (chunk_rows) 8: 3.10, 10: 2.95, 12: 2.96, 16: 3.11
     if (n > OC_PIPE_MAX_CHUNKS) n = OC_PIPE_MAX_CHUNKS;
-    while (n > 1 && c->rows_own / n < 64) n /= 2;          // chunks of at least 64 rows
+    while (n > 1 && c->rows_own / n < 64) n = n > 8 ? 8 : n / 2;          // chunks of 64 rows on average (a tapered end chunk: >= 8)
     return n;
+}
+// Rows of chunk k.  The chunks are TAPERED: the round trip is the H2D time of the whole cloth plus the time the last chunk
+// still needs afterwards (unpack, step, pack, its own D2H), and symmetrically the D2H link idles until the first chunk is
+// through; small chunks at both ends shorten that fill and drain, large ones in the middle keep the per-copy overhead low.
+// Weights 1, 2, 4, 8, 8, ..., 8, 4, 2, 1 (OC_PIPE_TAPER=0: equal chunks).
+static int chunk_weight(int nch, int k)
+{
+    static const bool taper = !(getenv("OC_PIPE_TAPER") && atoi(getenv("OC_PIPE_TAPER")) == 0);
+    if (!taper) return 1;
+    const int d = k < nch - 1 - k ? k : nch - 1 - k;          // distance from the nearer end
+    return d >= 3 ? 8 : (1 << d);
 }
 static void chunk_rows(const oc_cloth* c, int nch, int k, int* r0, int* r1)
 {
-    *r0 = c->p.row_begin + (int)((long long)c->rows_own * k / nch);
-    *r1 = c->p.row_begin + (int)((long long)c->rows_own * (k + 1) / nch);
+    long long tot = 0, lo = 0, hi = 0;
+    for (int j = 0; j < nch; ++j) { const int w = chunk_weight(nch, j); if (j < k) lo += w; if (j <= k) hi += w; tot += w; }
+    *r0 = c->p.row_begin + (int)((long long)c->rows_own * lo / tot);
+    *r1 = c->p.row_begin + (int)((long long)c->rows_own * hi / tot);
 }
 // every queued chunk of an upload has landed as far as the compute stream is concerned
 static int join_upload(oc_cloth* c)
