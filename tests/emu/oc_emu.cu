@@ -10,17 +10,38 @@
 //
 // Host arithmetic is IEEE binary32 without contraction (-ffp-contract=off), which is exactly what
 // the device intrinsics of MathExact compute, so exact-mode results must equal the GPU's.
+// The file is compiled in PARTS (-DEMU_PART=k, tests/helpers.py builds them in parallel and links them): part 0 is the fiber
+// machinery, the handle and the C entry points; parts 1-5 each hold the instantiations of one marching kernel's body, which
+// dominate the compile time.  Without EMU_PART everything lands in one translation unit.
+#ifndef EMU_PART
+#define EMU_PART -1
+#endif
+#define EMU_HAS(p) (EMU_PART == -1 || EMU_PART == (p))
+#if EMU_PART == -1
+#define EMU_LOCAL static
+#else
+#define EMU_LOCAL
+#endif
+
 #include "../../opencloth_b200/csrc/oc_core.cuh"
 #include "../../opencloth_b200/csrc/oc_host.h"
-#include "../../opencloth_b200/csrc/oc_gather.cuh"
-#include "../../opencloth_b200/csrc/oc_provot.cuh"
-#include "../../opencloth_b200/csrc/oc_normals.cuh"
+#if EMU_HAS(0)
+#include "../../opencloth_b200/csrc/oc_gather.cuh"      // (holds non-template kernels: one part only)
+#endif
+#if EMU_HAS(0)
+#include "../../opencloth_b200/csrc/oc_provot.cuh"      // (holds non-template kernels: one part only)
+#endif
+#if EMU_HAS(0)
+#include "../../opencloth_b200/csrc/oc_normals.cuh"      // (holds non-template kernels: one part only)
+#endif
 #include "../../opencloth_b200/csrc/oc_march.cuh"
 #include "../../opencloth_b200/csrc/oc_march2.cuh"
 #include "../../opencloth_b200/csrc/oc_twin.cuh"
 #include "../../opencloth_b200/csrc/oc_stream.cuh"
 #include "../../opencloth_b200/csrc/oc_stream2.cuh"
-#include "../../opencloth_b200/csrc/oc_resident.cuh"
+#if EMU_HAS(0)
+#include "../../opencloth_b200/csrc/oc_resident.cuh"      // (holds non-template kernels: one part only)
+#endif
 
 #include <ucontext.h>
 #include <cstdlib>
@@ -28,6 +49,7 @@
 #include <cstring>
 #include <vector>
 #include <functional>
+
 
 // ------------------------------------------------------------------------------------------------
 // fiber CTA
@@ -63,6 +85,7 @@ struct EmuCta {
     int cur;
 };
 
+#if EMU_HAS(0)
 static EmuCta* g_cta = nullptr;
 // Order in which the scheduler resumes the fibers between two barriers: 0 = ascending tid,
 // 1 = descending, 2 = pseudo-random per round.  A kernel without intra-phase data races gives
@@ -88,7 +111,7 @@ static void fiber_main()
 }
 
 // run one CTA of nthreads threads; returns 0, or -1 if the threads disagree on the barrier count
-static int run_cta(int nthreads, int bx, int by, int bz, size_t smem_bytes, const std::function<void(EmuCtx&)>& body)
+EMU_LOCAL int run_cta(int nthreads, int bx, int by, int bz, size_t smem_bytes, const std::function<void(EmuCtx&)>& body)
 {
     static EmuCta cta;              // stacks are reused between CTAs
     EmuCta* c = &cta;
@@ -149,6 +172,10 @@ static int run_cta(int nthreads, int bx, int by, int bz, size_t smem_bytes, cons
     return rc;
 }
 
+#else
+int run_cta(int nthreads, int bx, int by, int bz, size_t smem_bytes, const std::function<void(EmuCtx&)>& body);
+#endif
+
 // ------------------------------------------------------------------------------------------------
 // emulated handle: same state as the C-ABI handle, host memory
 // ------------------------------------------------------------------------------------------------
@@ -166,6 +193,7 @@ struct EmuCloth {
     unsigned link_epoch;
 };
 
+#if EMU_HAS(1)
 template <class M, int S, int TW>
 static int emu_march(EmuCloth* e, const OcLaunch& L, int RS, int x_halo)
 {
@@ -205,6 +233,12 @@ static int emu_march_dispatch(EmuCloth* e, const OcLaunch& L, int TW, int RS)
     return -2;
 }
 
+int emu_disp_march(EmuCloth* e, const OcLaunch& L, int exact, int TW, int RS) { return exact ? emu_march_dispatch<MathExact>(e, L, TW, RS) : emu_march_dispatch<MathFast>(e, L, TW, RS); }
+#else
+int emu_disp_march(EmuCloth* e, const OcLaunch& L, int exact, int TW, int RS);
+#endif
+
+#if EMU_HAS(2)
 template <class M, int WC>
 static int emu_march2(EmuCloth* e, const OcLaunch& L, int RS)
 {
@@ -253,7 +287,13 @@ static int emu_march2_dispatch(EmuCloth* e, const OcLaunch& L, int WC, int RS)
     return -2;
 }
 
+int emu_disp_march2(EmuCloth* e, const OcLaunch& L, int exact, int WC, int RS) { return exact ? emu_march2_dispatch<MathExact>(e, L, WC, RS) : emu_march2_dispatch<MathFast>(e, L, WC, RS); }
+#else
+int emu_disp_march2(EmuCloth* e, const OcLaunch& L, int exact, int WC, int RS);
+#endif
 
+
+#if EMU_HAS(3) || EMU_HAS(4) || EMU_HAS(5)
 // kernel 5: twin tiles (oc_twin.cuh).  RS = rows per segment (0: two segments); bit 16 of RS: pair the cloths of a batch
 // (needs an even batch) instead of two segments of a strip.  The number of segments must be even when segments are paired.
 template <class M, int WC, int kVariant>
@@ -315,6 +355,24 @@ static int emu_twin_dispatch(EmuCloth* e, const OcLaunch& L, int WC, int RS)
     return -2;
 }
 
+#endif
+#if EMU_HAS(3)
+int emu_disp_twin(EmuCloth* e, const OcLaunch& L, int exact, int WC, int RS) { return exact ? emu_twin_dispatch<MathExact, 0>(e, L, WC, RS) : emu_twin_dispatch<MathFast, 0>(e, L, WC, RS); }
+#else
+int emu_disp_twin(EmuCloth* e, const OcLaunch& L, int exact, int WC, int RS);
+#endif
+#if EMU_HAS(4)
+int emu_disp_stream(EmuCloth* e, const OcLaunch& L, int exact, int WC, int RS) { return exact ? emu_twin_dispatch<MathExact, 1>(e, L, WC, RS) : emu_twin_dispatch<MathFast, 1>(e, L, WC, RS); }
+#else
+int emu_disp_stream(EmuCloth* e, const OcLaunch& L, int exact, int WC, int RS);
+#endif
+#if EMU_HAS(5)
+int emu_disp_stream2(EmuCloth* e, const OcLaunch& L, int exact, int WC, int RS) { return exact ? emu_twin_dispatch<MathExact, 2>(e, L, WC, RS) : emu_twin_dispatch<MathFast, 2>(e, L, WC, RS); }
+#else
+int emu_disp_stream2(EmuCloth* e, const OcLaunch& L, int exact, int WC, int RS);
+#endif
+
+#if EMU_HAS(0)
 // kernel 4: one CTA per cloth, all the substeps of the launch inside; TW = threads of the CTA (0: like the library)
 template <class M>
 static int emu_resident(EmuCloth* e, const OcLaunch& L, int threads)
@@ -479,23 +537,23 @@ int emu_step(void* h, int n, int kernel, int exact, int k, int TW, int RS)
             if (r == -2) return -2;
             rc |= r;
         } else if (kernel == 7) {
-            int r = exact ? emu_twin_dispatch<MathExact, 2>(e, L, TW, RS) : emu_twin_dispatch<MathFast, 2>(e, L, TW, RS);
+            int r = emu_disp_stream2(e, L, exact, TW, RS);
             if (r == -2 || r == -4) return r;
             rc |= r;
         } else if (kernel == 6) {
-            int r = exact ? emu_twin_dispatch<MathExact, 1>(e, L, TW, RS) : emu_twin_dispatch<MathFast, 1>(e, L, TW, RS);
+            int r = emu_disp_stream(e, L, exact, TW, RS);
             if (r == -2 || r == -4) return r;
             rc |= r;
         } else if (kernel == 5) {
-            int r = exact ? emu_twin_dispatch<MathExact, 0>(e, L, TW, RS) : emu_twin_dispatch<MathFast, 0>(e, L, TW, RS);
+            int r = emu_disp_twin(e, L, exact, TW, RS);
             if (r == -2 || r == -4) return r;
             rc |= r;
         } else if (kernel == 3) {
-            int r = exact ? emu_march2_dispatch<MathExact>(e, L, TW, RS) : emu_march2_dispatch<MathFast>(e, L, TW, RS);
+            int r = emu_disp_march2(e, L, exact, TW, RS);
             if (r == -2) return -2;
             rc |= r;
         } else if (kernel == 2) {
-            int r = exact ? emu_march_dispatch<MathExact>(e, L, TW, RS) : emu_march_dispatch<MathFast>(e, L, TW, RS);
+            int r = emu_disp_march(e, L, exact, TW, RS);
             if (r == -2) return -2;
             rc |= r;
         } else {
@@ -671,3 +729,5 @@ int emu_halo_refreshed(void* h) { ((EmuCloth*)h)->q.fresh = 0; return 0; }
 int emu_halo_budget(void* h) { EmuCloth* e = (EmuCloth*)h; return e->q.band ? e->q.kmax - e->q.fresh : 0x7fffffff; }
 
 } // extern "C"
+
+#endif      // EMU_HAS(0)

@@ -27,9 +27,21 @@ def build_emulator():
     deps = [src] + [os.path.join(csrc, f) for f in ("oc_core.cuh", "oc_host.h", "oc_gather.cuh", "oc_provot.cuh", "oc_normals.cuh", "oc_march.cuh", "oc_march2.cuh", "oc_twin.cuh", "oc_stream.cuh", "oc_stream2.cuh", "oc_resident.cuh")]
     if _newer(EMU_SO, *deps):
         return
-    subprocess.check_call([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-std=c++17",
-                           "-Xcompiler", "-fPIC,-ffp-contract=off,-O2", "-diag-suppress", "20011,20014",
-                           "-shared", src, "-o", EMU_SO])
+    # six parts compiled in parallel (tests/emu/oc_emu.cu, EMU_PART): the kernel-body instantiations dominate the compile time
+    objdir = os.path.join(ROOT, "tests", "emu", "build")
+    os.makedirs(objdir, exist_ok=True)
+    flags = ["-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-std=c++17", "-Xcompiler", "-fPIC,-ffp-contract=off,-O2",
+             "-diag-suppress", "20011,20014"]
+    procs, objs = [], []
+    for part in range(6):
+        obj = os.path.join(objdir, f"oc_emu_{part}.o")
+        objs.append(obj)
+        procs.append(subprocess.Popen([NVCC] + flags + [f"-DEMU_PART={part}", "-c", src, "-o", obj]))
+    for pr in procs:
+        if pr.wait() != 0:
+            raise RuntimeError("building the CPU kernel emulator failed")
+    subprocess.check_call([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared"] + objs + ["-o", EMU_SO])
+
 
 
 def ensure_built():
