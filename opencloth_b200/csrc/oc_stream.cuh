@@ -43,6 +43,17 @@ OC_HD int oc_sslot(int x) { return (OC_SRING & (OC_SRING - 1)) == 0 ? (x & (OC_S
 #define OC_STREAM_DEPTH 0          // measured on B200: 0: 72.6, 1: 70.7, 2: 68.8, 4: 62 G updates/s (8192^2, fast): the rows are not what it waits for
 #endif
 
+// OC_STREAM_WIN (an experiment of round 2, off by default): in fast mode the steady loop keeps rows r-2 .. r+2 of the thread's
+// OWN column in registers (the thread published them itself) and reads only the other columns from the ring: 48 instead of
+// 78 LDS.64 per iteration, and the barrier wait moves from "before the last spring" to "before publishing" (rows r-2 / r+2
+// are only read in the own column).  1: one copy of the loop, the window moves (48 MOV); 2: loop unrolled by five, the window
+// rotates by renaming.  Same bits.  Measured on B200 (profiles/r2/stream_window_rates.log, r2_stream_fast_window_2048.md):
+// 27 % fewer shared-memory wavefronts and NO gain - 1: 64.1 / 74.4 against 66.7 / 75.4 G updates/s (2048^2 / 8192^2);
+// 2: 34.8 / 53.0 (a 54 KB loop body: instruction fetch).  So the shared-memory data pipe is not what bounds this kernel.
+#ifndef OC_STREAM_WIN
+#define OC_STREAM_WIN 0
+#endif
+
 template <int WC, bool kExact>
 struct OcSmemS {
     float2 X[kExact ? 9 : 6][OC_SRING][WC + 4];      // x, y, z, then vx, vy, vz, dx, dy, dz (exact) or dx, dy, dz (fast); slot = iteration mod OC_SRING
@@ -128,6 +139,9 @@ struct OcStream {
     float ydt, kdt_struct, kdt_shear, kdt_bend, damp_dt;
     long long goff0, dOff;
     const OcPeer2* peer;
+    static constexpr bool kWin = !M::kExact && OC_STREAM_WIN;
+    OcPV2 W0, W1, W2, W3, W4;                // register window of the own column (kWin): sub-iteration p keeps row r-2+k in W[(p+k) mod 5]
+    template <int K> OC_HD OcPV2& win() { return K == 0 ? W0 : (K == 1 ? W1 : (K == 2 ? W2 : (K == 3 ? W3 : W4))); }
 
     OC_HD OcStream(Ctx& ctx_, const OcConst& c_) : ctx(ctx_), c(c_) {}
 
@@ -141,19 +155,22 @@ struct OcStream {
     static OC_HD float4 benign(int ci_, int lrow) { return make_float4(1.0e3f + 8.0f * (float)ci_, 1.0e3f, 1.0e3f + 8.0f * (float)(lrow & 63), oc_u2f(OC_W_PLAIN)); }
 
     // One loaded row (both tiles) into ring slot sl: position, then X - X_last (fast) or V and X - X_last (exact)
-    OC_HD void publish(int sl, const float4 la0, const float4 lq0, const float4 la1, const float4 lq1)
+    OC_HD OcPV2 publish(int sl, const float4 la0, const float4 lq0, const float4 la1, const float4 lq1)
     {
         Smem& s = *sm;
+        OcPV2 r;
         OcPair3 d;
         d.x = make_float2(M::sub(la0.x, lq0.x), M::sub(la1.x, lq1.x));
         d.y = make_float2(M::sub(la0.y, lq0.y), M::sub(la1.y, lq1.y));
         d.z = make_float2(M::sub(la0.z, lq0.z), M::sub(la1.z, lq1.z));
         if (oc_hit(la0.w)) { d.x.x = 0.0f; d.y.x = 0.0f; d.z.x = 0.0f; }       // X_last == X (V:530)
         if (oc_hit(la1.w)) { d.x.y = 0.0f; d.y.y = 0.0f; d.z.y = 0.0f; }
-        s.X[0][sl][ci] = make_float2(la0.x, la1.x);
-        s.X[1][sl][ci] = make_float2(la0.y, la1.y);
-        s.X[2][sl][ci] = make_float2(la0.z, la1.z);
-        if (!M::kExact) { s.X[3][sl][ci] = d.x; s.X[4][sl][ci] = d.y; s.X[5][sl][ci] = d.z; return; }
+        r.x.x = make_float2(la0.x, la1.x); r.x.y = make_float2(la0.y, la1.y); r.x.z = make_float2(la0.z, la1.z);
+        r.v = d;
+        s.X[0][sl][ci] = r.x.x;
+        s.X[1][sl][ci] = r.x.y;
+        s.X[2][sl][ci] = r.x.z;
+        if (!M::kExact) { s.X[3][sl][ci] = d.x; s.X[4][sl][ci] = d.y; s.X[5][sl][ci] = d.z; return r; }
         OcPair3 v;
 #ifdef __CUDA_ARCH__
         {
@@ -175,6 +192,8 @@ struct OcStream {
         constexpr int kE = M::kExact ? 1 : 0;      // (indices that exist in both layouts; reached in exact mode only)
         s.X[3][sl][ci] = v.x; s.X[4][sl][ci] = v.y; s.X[5][sl][ci] = v.z;
         s.X[6 * kE][sl][ci] = d.x; s.X[7 * kE][sl][ci] = d.y; s.X[8 * kE][sl][ci] = d.z;
+        r.v = v;
+        return r;
     }
 
     // spring of the particle pair `me` with neighbour pair n; adds the force to F.  p0 / p1: the spring acts on tile 0 / 1
@@ -206,9 +225,13 @@ struct OcStream {
         }
     }
 
-    template <bool kSteady, bool kInterior>
+    // kPh >= 0: sub-iteration kPh of the unrolled steady loop with the register window; -1: everything from the ring
+    template <bool kSteady, bool kInterior, int kPh = -1>
     OC_HD void iter(int it)
     {
+        static_assert(kPh < 0 || (kSteady && kWin), "the register window belongs to the steady loop of fast mode");
+        constexpr bool kW = kPh >= 0;
+        constexpr int kP = kW ? kPh : 0;
         Smem& s = *sm;
         const int row_0 = row0 + it, row_1 = row_0 + dRow;
         const int prow_0 = row_0 + OC_STREAM_AHEAD, prow_1 = row_1 + OC_STREAM_AHEAD;                 // rows published by this iteration
@@ -236,7 +259,7 @@ struct OcStream {
         if (doG0 | doG1) {
             constexpr bool kAll = kSteady;
             constexpr bool kMask = kSteady && !kInterior;
-            const OcPV2 me = ld(s0, ci);
+            const OcPV2 me = kW ? win<(kP + 2) % 5>() : ld(s0, ci);
             OcPair3 dme;
             if (M::kExact) { constexpr int kE = M::kExact ? 1 : 0; dme.x = s.X[6 * kE][s0][ci]; dme.y = s.X[7 * kE][s0][ci]; dme.z = s.X[8 * kE][s0][ci]; }
             else dme = me.v;
@@ -268,8 +291,8 @@ struct OcStream {
             // the twelve springs in the order the reference's list touches the particle (V:286-320, oc_gather.cuh)
             spring<kAll, kMask>(F, me, ld(s0, ci - 1),  p_bc(K.rh1m), nS, kS, e0 && l1, e1 && l1, mL1, rg);                          // 1  (i-1, j)
             spring<kAll, kMask>(F, me, ld(s0, ci + 1),  p_bc(K.rh1i), nS, kS, e0 && r1, e1 && r1, mR1, rg);                          // 2  (i+1, j)
-            spring<kAll, false>(F, me, ld(sm1, ci),     tV1m, nS, kS, e0 && u1_0, e1 && u1_1, 1.0f, rg);                             // 3  (i, j-1)
-            spring<kAll, false>(F, me, ld(sp1, ci),     tV1,  nS, kS, e0 && d1_0, e1 && d1_1, 1.0f, rg);                             // 4  (i, j+1)
+            spring<kAll, false>(F, me, kW ? win<(kP + 1) % 5>() : ld(sm1, ci), tV1m, nS, kS, e0 && u1_0, e1 && u1_1, 1.0f, rg);      // 3  (i, j-1)
+            spring<kAll, false>(F, me, kW ? win<(kP + 3) % 5>() : ld(sp1, ci), tV1,  nS, kS, e0 && d1_0, e1 && d1_1, 1.0f, rg);      // 4  (i, j+1)
             spring<kAll, kMask>(F, me, ld(sm1, ci - 1), rUL, nSh, kSh, e0 && l1 && u1_0, e1 && l1 && u1_1, mL1, rg);                 // 5  (i-1, j-1)
             spring<kAll, kMask>(F, me, ld(sm1, ci + 1), rUR, nSh, kSh, e0 && r1 && u1_0, e1 && r1 && u1_1, mR1, rg);                 // 6  (i+1, j-1)
             spring<kAll, kMask>(F, me, ld(sp1, ci - 1), rLL, nSh, kSh, e0 && l1 && d1_0, e1 && l1 && d1_1, mL1, rg);                 // 7  (i-1, j+1)
@@ -287,11 +310,12 @@ struct OcStream {
                 }
             }
             {
-                const OcPV2 nu = ld(sm2, ci);
+                const OcPV2 nu = kW ? win<kP>() : ld(sm2, ci);
                 spring<kAll, false>(F, me, nu, tV2m, nB, kB, e0 && u2_0, e1 && u2_1, 1.0f, rg);                                      // 12 (i, j-2)
-                // row + 2 was published at the end of the previous iteration: the only read that needs its barrier
-                ctx.bar_wait(&s.bar, (unsigned)(it - it_first) & 1u); waited = true;
-                const OcPV2 nd = ld(sp2, ci);
+                // row + 2 was published at the end of the previous iteration: the only read that needs its barrier (with the
+                // register window nothing does: rows +-2 are only read in the own column, and the wait moves down to the publish)
+                if (!kW) { ctx.bar_wait(&s.bar, (unsigned)(it - it_first) & 1u); waited = true; }
+                const OcPV2 nd = kW ? win<(kP + 4) % 5>() : ld(sp2, ci);
                 spring<kAll, false>(F, me, nd, tV2,  nB, kB, e0 && d2_0, e1 && d2_1, 1.0f, rg);                                      // 13 (i, j+2)
                 if (!kSteady) {                                                                                                 // 14 last bend spring of the column twice (V:319)
                     spring<false, false>(F, me, nd, tV2,  nB, kB, e0 && row_0 == V - 3, e1 && row_1 == V - 3, 1.0f, rg);
@@ -430,7 +454,11 @@ struct OcStream {
             const bool pub1 = kSteady ? (kInterior || ok) : (prow_1 >= in_lo1 && prow_1 < in_hi1 && ok);
             const float4 la0 = pub0 ? s.stage[zp][0][i] : benign(ci, prow_0), lq0 = pub0 ? s.stage[zp][1][i] : benign(ci, prow_0);
             const float4 la1 = pub1 ? s.stage[zp][2][i] : benign(ci, prow_1), lq1 = pub1 ? s.stage[zp][3][i] : benign(ci, prow_1);
-            publish(sp3, la0, lq0, la1, lq1);
+            const OcPV2 pv = publish(sp3, la0, lq0, la1, lq1);
+            if (kW) {
+                if (OC_STREAM_WIN == 2) win<kP>() = pv;                  // row r+3 takes the place of row r-2 (unrolled loop: renaming)
+                else { W0 = W1; W1 = W2; W2 = W3; W3 = W4; W4 = pv; }    // one copy of the loop: the window moves
+            }
         }
         ctx.bar_arrive(&s.bar);                   // phase it + 1 of the barrier: this thread has put its part of row prow into the ring
     }
@@ -534,8 +562,29 @@ OC_HD bool oc_stream_body(Ctx& ctx, const OcConst& c, const float4* __restrict__
         if ((c.dbg & 8) && i == 0) oc_timeline_mark(c, phase == 0 ? 2 : 4);
 #endif
         if (phase == 0) {
-            if (interior) for (; it < it_hi; ++it) m.template iter<true, true>(it);
-            else          for (; it < it_hi; ++it) m.template iter<true, false>(it);
+            if (OcStream<M, WC, Ctx>::kWin) {
+                constexpr int kW0 = OcStream<M, WC, Ctx>::kWin ? 0 : -1, kW1 = kW0 < 0 ? -1 : 1, kW2 = kW0 < 0 ? -1 : 2, kW3 = kW0 < 0 ? -1 : 3, kW4 = kW0 < 0 ? -1 : 4;
+                if (OC_STREAM_WIN == 2) {
+                    // unrolled by five (the window rotates by renaming): the remainder first, from the ring
+                    const int rem = (it_hi - it) % 5;
+                    if (interior) { for (int e = it + rem; it < e; ++it) m.template iter<true, true>(it); }
+                    else          { for (int e = it + rem; it < e; ++it) m.template iter<true, false>(it); }
+                }
+                if (it < it_hi) {
+                    m.W0 = m.ld(oc_sslot(it + OC_SRING - 2), m.ci); m.W1 = m.ld(oc_sslot(it + OC_SRING - 1), m.ci); m.W2 = m.ld(oc_sslot(it), m.ci);
+                    m.W3 = m.ld(oc_sslot(it + 1), m.ci);            m.W4 = m.ld(oc_sslot(it + 2), m.ci);
+                }
+                if (OC_STREAM_WIN == 2) {
+                    if (interior) for (; it < it_hi; it += 5) { m.template iter<true, true, kW0>(it); m.template iter<true, true, kW1>(it + 1); m.template iter<true, true, kW2>(it + 2); m.template iter<true, true, kW3>(it + 3); m.template iter<true, true, kW4>(it + 4); }
+                    else          for (; it < it_hi; it += 5) { m.template iter<true, false, kW0>(it); m.template iter<true, false, kW1>(it + 1); m.template iter<true, false, kW2>(it + 2); m.template iter<true, false, kW3>(it + 3); m.template iter<true, false, kW4>(it + 4); }
+                } else {
+                    if (interior) for (; it < it_hi; ++it) m.template iter<true, true, kW0>(it);
+                    else          for (; it < it_hi; ++it) m.template iter<true, false, kW0>(it);
+                }
+            } else {
+                if (interior) for (; it < it_hi; ++it) m.template iter<true, true>(it);
+                else          for (; it < it_hi; ++it) m.template iter<true, false>(it);
+            }
 #ifdef __CUDA_ARCH__
             if ((c.dbg & 8) && i == 0) oc_timeline_mark(c, 3);
 #endif

@@ -16,6 +16,7 @@ extern "C" const void* oc_stream_fn_fast(int WC, int occ)
         case 0: case 6: return (const void*)&oc_k_stream<OcInstMath, 64, 6>;
 #ifdef OC_ALL_VARIANTS          // the other register caps measured in DESIGN.md 4.2 (equal or slower; not part of the default build)
         case 4: return (const void*)&oc_k_stream<OcInstMath, 64, 4>;
+        case 5: return (const void*)&oc_k_stream<OcInstMath, 64, 5>;
         case 8: return (const void*)&oc_k_stream<OcInstMath, 64, 8>;
 #endif
         default: return nullptr;

@@ -171,7 +171,7 @@ def test_stream_fast_mode_does_not_depend_on_the_tiling():
     nx, ny = 37, 30
     x0, xl0 = helpers.developed_state(nx, ny, 1700)
     ref = None
-    for WC, RS in ((64, 0), (16, 5), (8, 3), (32, 15)):
+    for WC, RS in ((64, 0), (16, 5), (8, 3), (32, 15), (16, 8)):     # (steady loop: register window, 5 rows per trip + remainder)
         e = Emu(nx, ny); e.upload(x0, xl0); e.step(12, kernel=STREAM, exact=0, TW=WC, RS=RS)
         got = e.download()
         ref = ref or got
@@ -181,6 +181,15 @@ def test_stream_fast_mode_does_not_depend_on_the_tiling():
         e = Emu(nx, ny); e.upload(x0, xl0); e.step(12, kernel=STREAM2, exact=0, TW=WC, RS=RS)
         got = e.download()
         assert bitwise_equal(got[0], ref[0]) and bitwise_equal(got[1], ref[1]), ("stream2", WC, RS)
+    # long tiles: several trips of the unrolled steady loop and every remainder, against short tiles and oc_k_stream2
+    nx, ny = 20, 66
+    x0, xl0 = helpers.developed_state(nx, ny, 900)
+    ref = None
+    for kern, WC, RS in ((STREAM2, 32, 0), (STREAM, 32, 0), (STREAM, 16, 11), (STREAM, 32, 17), (STREAM, 8, 3), (STREAM, 32, 19 | (1 << 17))):
+        e = Emu(nx, ny); e.upload(x0, xl0); e.step(6, kernel=kern, exact=0, TW=WC, RS=RS)
+        got = e.download()
+        ref = ref or got
+        assert bitwise_equal(got[0], ref[0]) and bitwise_equal(got[1], ref[1]), (kern, WC, RS)
 
 
 @pytest.mark.parametrize("order", [1, 2])
