@@ -57,7 +57,12 @@ typedef enum oc_kernel {
     OC_KERNEL_STREAM = 6,    /* streaming gather over twin tiles: every particle evaluates all of its twelve springs itself
                                 from a shared-memory ring of rows (no force exchange, small per-thread state, many resident
                                 warps); same coverage as OC_KERNEL_TWIN */
-    OC_KERNEL_STREAM2 = 7    /* the same with two adjacent columns per thread: a third of the neighbour loads is shared */
+    OC_KERNEL_STREAM2 = 7,   /* the same with two adjacent columns per thread: a third of the neighbour loads is shared */
+    OC_KERNEL_BANDRES = 8    /* mid-size whole cloths (about 10^3 .. 3*10^5 particles, single cloth): one row band per CTA, at most
+                                one CTA per SM (cooperative launch), state resident in shared memory for all the substeps of
+                                an oc_step call, two boundary rows per band exchanged through global memory per substep.
+                                AUTO between OC_KERNEL_RESIDENT and the marching kernels; falls back to OC_KERNEL_MARCH2
+                                where it does not apply (batches, row bands, Provot pass, bands too tall for shared memory) */
 } oc_kernel;
 
 /* The reference's explicit integrators on this spring net.  "E:" =

@@ -25,6 +25,7 @@ OC_KERNEL_RESIDENT = 4
 OC_KERNEL_TWIN = 5
 OC_KERNEL_STREAM = 6
 OC_KERNEL_STREAM2 = 7
+OC_KERNEL_BANDRES = 8
 
 OC_BAND_ENDPOINT_BYTES = 512
 

@@ -12,6 +12,7 @@
 #include "oc_provot.cuh"
 #include "oc_normals.cuh"
 #include "oc_resident.cuh"
+#include "oc_bandres.cuh"
 #include "oc_march.cuh"
 #include "oc_march2.cuh"
 #include "oc_twin.cuh"
@@ -95,6 +96,9 @@ struct oc_cloth {
         int       rev;                  // this band launches its segments bottom to top (OcPeer2::rev): odd bands of the chain
     } link;
     unsigned* in_flags;          // device: 2 x OC_LINK_STRIPS words released by the neighbours' boundary tiles
+    // oc_k_bandres (mid-size cloths resident in shared memory, one row band per CTA): exchange rows of two parities, one
+    // flag word per band, substeps taken so far (the flags count on from launch to launch); allocated at the first use
+    struct { float4* ex; unsigned* flags; unsigned epoch; int coop; } bres;
     // run-time pin sets (oc_set_pins): bitmap over batch x ny x nx particles + per-row summary; empty = reference default
     std::vector<unsigned>* h_pins;
     std::vector<unsigned char>* h_pin_rows;
@@ -117,6 +121,8 @@ static int free_handle(oc_cloth* c)
     if (c->d_dbg) cudaFree(c->d_dbg);
     if (c->chain.flags) cudaFree(c->chain.flags);
     if (c->in_flags) cudaFree(c->in_flags);
+    if (c->bres.ex) cudaFree(c->bres.ex);
+    if (c->bres.flags) cudaFree(c->bres.flags);
     if (c->d_pins) cudaFree(c->d_pins);
     if (c->d_pin_rows) cudaFree(c->d_pin_rows);
     delete c->h_pins; delete c->h_pin_rows;
@@ -288,7 +294,7 @@ static int validate(const oc_params* p)
     if (!(p->dt > 0.0f) || !(p->mass > 0.0f)) return oc_fail(OC_ERR_INVALID, "dt and mass must be positive");
     if (p->substeps_per_launch < 0 || p->substeps_per_launch > OC_MARCH_MAX_STAGES)
         return oc_fail(OC_ERR_INVALID, "substeps_per_launch must be 0..%d", OC_MARCH_MAX_STAGES);
-    if (p->kernel < OC_KERNEL_AUTO || p->kernel > OC_KERNEL_STREAM2) return oc_fail(OC_ERR_INVALID, "bad kernel id");
+    if (p->kernel < OC_KERNEL_AUTO || p->kernel > OC_KERNEL_BANDRES) return oc_fail(OC_ERR_INVALID, "bad kernel id");
     if (p->integrator < OC_INTEGRATOR_VERLET || p->integrator > OC_INTEGRATOR_SEMI_IMPLICIT) return oc_fail(OC_ERR_INVALID, "bad integrator id %d", p->integrator);
     if (p->provot != 0 && p->provot != 1) return oc_fail(OC_ERR_INVALID, "provot must be 0 or 1");
     if ((p->integrator != OC_INTEGRATOR_VERLET || p->provot) && (p->row_begin != 0 || p->row_end != 0) && (p->row_begin > 0 || p->row_end < p->ny))
@@ -382,6 +388,9 @@ extern "C" int oc_create(oc_cloth** out, const oc_params* p)
     // function attributes are per device: set them at every create, for the device of this handle
     if (rc == 0) rc = (int)cudaFuncSetAttribute((const void*)&oc_k_resident<MathExact>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OcResidentSmem::bytes(OC_RESIDENT_MAX_PARTICLES));
     if (rc == 0) rc = (int)cudaFuncSetAttribute((const void*)&oc_k_resident<MathFast>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OcResidentSmem::bytes(OC_RESIDENT_MAX_PARTICLES));
+    if (rc == 0) rc = (int)cudaFuncSetAttribute((const void*)&oc_k_bandres<MathExact>, cudaFuncAttributeMaxDynamicSharedMemorySize, OC_BANDRES_SMEM_MAX);
+    if (rc == 0) rc = (int)cudaFuncSetAttribute((const void*)&oc_k_bandres<MathFast>, cudaFuncAttributeMaxDynamicSharedMemorySize, OC_BANDRES_SMEM_MAX);
+    if (rc == 0) rc = (int)cudaDeviceGetAttribute(&c->bres.coop, cudaDevAttrCooperativeLaunch, c->dev);
     if (rc != 0) { free_handle(c); return oc_fail(OC_ERR_CUDA, "oc_march_configure failed: %s", cudaGetErrorString((cudaError_t)rc)); }
 #undef OC_CREATE_CUDA
     *out = c;
@@ -759,18 +768,40 @@ extern "C" int oc_reset_pins(oc_cloth* c)
 // step
 // ------------------------------------------------------------------------------------------------
 static bool oc_stream_pays(const oc_cloth* c) { return (long long)c->p.nx * c->rows_own * c->p.batch >= (3LL << 20); }
+// oc_k_bandres: bands and rows of the tallest band for this cloth; false if the kernel does not apply
+static bool bandres_plan(const oc_cloth* c, int* nb, int* rmax)
+{
+    if (c->q.band || c->link.on || c->p.batch != 1 || c->p.integrator != OC_INTEGRATOR_VERLET || c->p.provot || !c->bres.coop) return false;
+    const int V = c->p.ny, U = c->p.nx;
+    if (V < 4) return false;
+    int n = c->sm_count < V / 2 ? c->sm_count : V / 2;
+    if (n > OC_BANDRES_MAX_BANDS) n = OC_BANDRES_MAX_BANDS;
+    // no more bands than give every CTA's threads a particle
+    const int want = (int)(((long long)U * V + OC_BANDRES_THREADS - 1) / OC_BANDRES_THREADS);
+    if (n > want) n = want < 1 ? 1 : want;
+    const int r = (V + n - 1) / n;
+    if (OcBandresSmem::bytes(U, r) > (size_t)OC_BANDRES_SMEM_MAX) return false;
+    *nb = n; *rmax = r;
+    return true;
+}
+
 static int pick_kernel(const oc_cloth* c)
 {
     const bool can_reside = !c->q.band && (long long)c->p.nx * c->p.ny <= OC_RESIDENT_MAX_PARTICLES;
+    int bres_nb = 0, bres_r = 0;
+    const bool can_band = bandres_plan(c, &bres_nb, &bres_r);
     if (c->link.on) return (c->p.kernel == OC_KERNEL_TWIN || c->p.kernel == OC_KERNEL_STREAM || c->p.kernel == OC_KERNEL_STREAM2) ? c->p.kernel : ((c->p.kernel == OC_KERNEL_AUTO && !c->p.exact && oc_stream_pays(c)) ? OC_KERNEL_STREAM : OC_KERNEL_MARCH2);      // linked row bands: the kernels that push their boundary rows
     if (c->p.integrator != OC_INTEGRATOR_VERLET) return OC_KERNEL_GATHER;      // state (X, V): oc_k_gather_xv
-    if (c->p.provot && (c->p.kernel == OC_KERNEL_RESIDENT || c->p.kernel == OC_KERNEL_AUTO)) return OC_KERNEL_MARCH2;   // a pass after EVERY substep
+    if (c->p.provot && (c->p.kernel == OC_KERNEL_RESIDENT || c->p.kernel == OC_KERNEL_BANDRES || c->p.kernel == OC_KERNEL_AUTO)) return OC_KERNEL_MARCH2;   // a pass after EVERY substep
     if (c->p.kernel == OC_KERNEL_RESIDENT) return can_reside ? OC_KERNEL_RESIDENT : OC_KERNEL_MARCH2;   // a cloth that does not fit one CTA's shared memory: the fastest general kernel
+    if (c->p.kernel == OC_KERNEL_BANDRES) return can_band ? OC_KERNEL_BANDRES : OC_KERNEL_MARCH2;       // (batches, row bands, Provot, bands too tall for shared memory)
     if (c->p.kernel != OC_KERNEL_AUTO) return c->p.kernel;
     // small whole cloths (the reference's own 21 x 21): state resident in shared memory, all substeps in one launch.
     // One CTA per cloth: worth it while the CTA's 1024 threads cover the cloth's springs in a few passes (beyond that
     // the gather kernel, which spreads one cloth over many SMs, or the marching kernel is quicker).
     if (can_reside && c->p.substeps_per_launch <= 1 && (long long)c->p.nx * c->p.ny <= 1024) return OC_KERNEL_RESIDENT;
+    // mid-size whole cloths: one row band per SM resident in shared memory, all substeps in one launch (oc_bandres.cuh)
+    if (can_band && c->p.substeps_per_launch <= 1) return OC_KERNEL_BANDRES;
     // one substep per launch: the two-columns-per-thread kernel (fastest); k > 1: the staged one-column kernel
     if (c->p.substeps_per_launch > 1) return OC_KERNEL_MARCH;
     // one substep per launch.  Exact mode: every spring once, two columns per thread (oc_k_march2; the bit-exact arithmetic is
@@ -817,6 +848,28 @@ static int launch_rows(oc_cloth* c, int kern, const OcLaunch& L, int ra, int rb)
         else            oc_k_resident<MathFast><<<c->p.batch, threads, smem, c->stream>>>(c->k, c->buf[L.src_a], c->buf[L.src_b], c->buf[L.dst], c->buf[L.dst_prev], L.S);
         c->launches++;
         OC_CUDA(cudaGetLastError());
+    } else if (kern == OC_KERNEL_BANDRES) {
+        chain_break(c);
+        int nb = 0, rmax = 0;
+        if (!bandres_plan(c, &nb, &rmax)) return oc_fail(OC_ERR_INVALID, "oc_k_bandres does not apply to this cloth");
+        const size_t NG = (size_t)c->p.nx * c->p.ny;
+        if (!c->bres.ex) {
+            OC_CUDA(cudaMalloc(&c->bres.ex, 2 * NG * sizeof(float4)));
+            OC_CUDA(cudaMalloc(&c->bres.flags, OC_BANDRES_MAX_BANDS * sizeof(unsigned)));
+            OC_CUDA(cudaMemsetAsync(c->bres.flags, 0, OC_BANDRES_MAX_BANDS * sizeof(unsigned), c->stream));
+            c->bres.epoch = 0;
+        }
+        const float4* a = c->buf[L.src_a]; const float4* b = c->buf[L.src_b];
+        float4* d0 = c->buf[L.dst]; float4* d1 = c->buf[L.dst_prev];
+        int S = L.S;
+        unsigned epoch = c->bres.epoch;
+        void* args[] = { (void*)&c->k, (void*)&a, (void*)&b, (void*)&d0, (void*)&d1, (void*)&S, (void*)&c->bres.ex, (void*)&c->bres.flags, (void*)&epoch, (void*)&rmax };
+        const void* fn = c->p.exact ? (const void*)&oc_k_bandres<MathExact> : (const void*)&oc_k_bandres<MathFast>;
+        if (c->k.dbg & 16) fprintf(stderr, "[oc] bandres: %d bands of <= %d rows, %zu bytes of shared memory, %d substeps\n", nb, rmax, OcBandresSmem::bytes(c->p.nx, rmax), S);
+        cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(nb), dim3(OC_BANDRES_THREADS), args, OcBandresSmem::bytes(c->p.nx, rmax), c->stream);
+        if (e != cudaSuccess) return oc_fail(OC_ERR_CUDA, "oc_k_bandres launch failed: %s", cudaGetErrorString(e));
+        c->bres.epoch += (unsigned)S;
+        c->launches++;
     } else if (kern == OC_KERNEL_MARCH) {
         chain_break(c);
         int nl = 0;
@@ -905,7 +958,7 @@ static int step_impl(oc_cloth* c, int n, cudaStream_t split_stream, bool want_sp
         c->pipe.step_chunks = (n_call == 1) ? nch : 0;         // a download that follows directly may go chunk by chunk
     }
     while (n > 0) {
-        int kmaxS = (kern == OC_KERNEL_MARCH) ? oc_host_pick_stages(n < kdef ? n : kdef) : (kern == OC_KERNEL_RESIDENT ? OC_RESIDENT_MAX_STEPS : 1);
+        int kmaxS = (kern == OC_KERNEL_MARCH) ? oc_host_pick_stages(n < kdef ? n : kdef) : (kern == OC_KERNEL_RESIDENT ? OC_RESIDENT_MAX_STEPS : (kern == OC_KERNEL_BANDRES ? OC_BANDRES_MAX_STEPS : 1));
         if (c->p.provot || c->q.xv) kmaxS = 1;                    // the Provot pass follows every substep; (X, V) steps are single
         OcLaunch L;
         oc_host_next_launch(c->q, n, kmaxS, L);

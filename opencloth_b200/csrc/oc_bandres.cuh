@@ -1,0 +1,214 @@
+// oc_bandres.cuh — kernel 8: mid-size cloths RESIDENT in the shared memory of MANY SMs (one row band per CTA).
+//
+// Between the cloth that fits one CTA (oc_k_resident, <= 1536 particles) and the cloth that fills the machine with
+// marching tiles (>= 10^6 particles) a step of the marching kernels is pure latency: a 512 x 512 cloth gives every CTA a
+// tile of 8-16 rows behind a 6-row pipeline fill, one launch and one round of tile flags per substep - 21 us per step
+// where the arithmetic needs 3.  Here the cloth is cut into one band of rows per CTA (at most one CTA per SM, launched
+// cooperatively so that all of them are resident), each band keeps its rows - and two halo rows either side - in shared
+// memory for ALL the substeps of an oc_step call, and per substep the bands exchange nothing but their two boundary
+// rows, through a small global buffer and one flag word per band:
+//   P1  every own particle gathers its twelve springs from shared memory (six packed pairs, oc_spring2; the reference's
+//       order, see oc_gather.cuh), IntegrateVerlet, EllipsoidCollision -> X(t+1) into the other position buffer; boundary
+//       rows also go to the exchange buffer of this substep's parity;
+//       barrier; thread 0 releases the band's flag (= epoch + substep);
+//   P2  every own particle: X - X_last and the velocity, in place;
+//       threads 0 / 32 wait for the flags of the bands above / below; barrier; the halo rows' new positions come from
+//       the exchange buffer (ld.cg), their velocities are derived from them like everybody else's; barrier.
+// A band's exchange rows of parity p are overwritten two substeps later, after the band has seen its neighbours' flags of
+// the substep in between - which they release only after they have read parity p.  Arithmetic and order are those of the
+// other kernels: bit-identical to the reference in exact mode.
+// Limits: one whole cloth (no batch, no row band), Verlet, no Provot pass; the tallest band must fit shared memory
+// (oc_bandres_plan: up to ~300 k particles, e.g. 512 x 576).
+#pragma once
+#include "oc_core.cuh"
+#include "oc_march2.cuh"      // oc_flag_wait
+
+#define OC_BANDRES_THREADS 512
+#define OC_BANDRES_MAX_STEPS 4096           /* substeps per launch (bounds the run time of one launch) */
+#define OC_BANDRES_MAX_BANDS 1024
+#define OC_BANDRES_SMEM_MAX (224 * 1024)    /* dynamic shared memory of one CTA (one CTA per SM) */
+
+// shared memory (floats; strides of the TALLEST band so that every CTA has the same layout):
+//   NL = (rmax + 4) * U local particles incl. halo rows, NO = rmax * U own particles
+struct OcBandresSmem {
+    float* base; int NL, NO;
+    OC_HD float* X(int buf, int k) const { return base + (size_t)(3 * buf + k) * NL; }      // positions, two buffers (t / t-1, swapped every substep)
+    OC_HD float* Vv(int k) const { return base + (size_t)(6 + k) * NL; }                    // velocity
+    OC_HD float* D(int k) const { return base + (size_t)9 * NL + (size_t)k * NO; }          // X(t) - X_last(t), own rows
+    OC_HD float* W(int buf) const { return base + (size_t)9 * NL + (size_t)(3 + buf) * NO; } // w of the position buffer (collider flag), own rows
+    static OC_HD size_t bytes(int U, int rmax) { return ((size_t)9 * (rmax + 4) * U + (size_t)5 * rmax * U) * sizeof(float); }
+};
+
+// rows [r0, r1) of band b of nb over V rows: even cut, every band >= 2 rows when nb <= V / 2
+OC_HD void oc_bandres_rows(int V, int nb, int b, int& r0, int& r1)
+{
+    r0 = (int)((long long)b * V / nb); r1 = (int)((long long)(b + 1) * V / nb);
+}
+
+#ifdef __CUDACC__
+// the flag of a neighbour band: a short busy poll first (the neighbour is normally a few hundred cycles away), then the
+// backed-off wait with its time-out and poison word (oc_flag_wait)
+__device__ __forceinline__ bool oc_bandres_wait(const OcConst& c, const unsigned* p, unsigned want)
+{
+    for (int k = 0; k < 4096; ++k) {
+        unsigned v;
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+        if ((int)(v - want) >= 0) return true;
+    }
+    return oc_flag_wait<false>(c, p, want);
+}
+
+template <class M>
+__global__ void __launch_bounds__(OC_BANDRES_THREADS, 1)
+oc_k_bandres(const __grid_constant__ OcConst c, const float4* __restrict__ A, const float4* __restrict__ B,
+             float4* __restrict__ dst, float4* __restrict__ dst_prev, int n_steps,
+             float4* __restrict__ ex, unsigned* __restrict__ flags, unsigned epoch, int rmax)
+{
+    extern __shared__ __align__(16) unsigned char oc_dyn_smem[];
+    const int U = c.U, V = c.V;
+    const int tid = threadIdx.x, T = blockDim.x, b = blockIdx.x, nb = gridDim.x;
+    int r0, r1;
+    oc_bandres_rows(V, nb, b, r0, r1);
+    const int R = r1 - r0;
+    const int jbase = r0 - 2;                                        // global row of local row 0
+    const int h0 = r0 - 2 < 0 ? 0 : r0 - 2, h1 = r1 + 2 > V ? V : r1 + 2;   // rows held locally
+    OcBandresSmem s;
+    s.base = reinterpret_cast<float*>(oc_dyn_smem); s.NL = (rmax + 4) * U; s.NO = rmax * U;
+    const long long goff = -(long long)c.row_lo * U;                 // storage offset of global row 0 (whole cloths: 0)
+    const float ydt = oc_rcp_bf(c.dt);
+    const size_t NG = (size_t)U * V;
+
+    auto velocity = [&](f3 d) {
+        bool bad = false;
+        f3 v = oc_velocity_bf<M>(d, c, ydt, bad);
+        if (M::kExact && bad) v = M::velocity(d, c);
+        return v;
+    };
+
+    // ---- load: X(t) into buffer 0, X(t-1) into buffer 1, derived state --------------------------------------
+    for (int lp = (h0 - jbase) * U + tid; lp < (h1 - jbase) * U; lp += T) {
+        const long long g = goff + (long long)jbase * U + lp;
+        const float4 a = A[g], q = B[g];
+        s.X(0, 0)[lp] = a.x; s.X(0, 1)[lp] = a.y; s.X(0, 2)[lp] = a.z;
+        s.X(1, 0)[lp] = q.x; s.X(1, 1)[lp] = q.y; s.X(1, 2)[lp] = q.z;
+        const f3 d = oc_delta<M>(a, q);
+        const f3 v = velocity(d);
+        s.Vv(0)[lp] = v.x; s.Vv(1)[lp] = v.y; s.Vv(2)[lp] = v.z;
+        const int op = lp - 2 * U;
+        if (op >= 0 && op < R * U) {
+            s.D(0)[op] = d.x; s.D(1)[op] = d.y; s.D(2)[op] = d.z;
+            s.W(0)[op] = a.w; s.W(1)[op] = q.w;
+        }
+    }
+    __syncthreads();
+
+    int cur = 0;
+    for (int step = 1; step <= n_steps; ++step) {
+        const int nxt = cur ^ 1;
+        const float* x0 = s.X(cur, 0); const float* x1 = s.X(cur, 1); const float* x2 = s.X(cur, 2);
+        const float* v0 = s.Vv(0);     const float* v1 = s.Vv(1);     const float* v2 = s.Vv(2);
+        float4* exw = ex + (size_t)(step & 1) * NG;
+        // ---- P1: gather, integrate, collide ------------------------------------------------------------------
+        for (int op = tid; op < R * U; op += T) {
+            const int oj = op / U, i = op - oj * U, j = r0 + oj, lp = op + 2 * U;
+            const f3 xm = make_f3(x0[lp], x1[lp], x2[lp]);
+            const f3 vm = make_f3(v0[lp], v1[lp], v2[lp]);
+            const f3 d  = make_f3(s.D(0)[op], s.D(1)[op], s.D(2)[op]);
+            const bool pinned = oc_pinned(c, 0, i, j);
+            f3 F = oc_base_force<M>(c, vm, pinned);
+            // two springs of the particle at once; a missing partner is a ghost at unit distance moving with the particle
+            // (its force is not added).  `keep`: the pair's forces, for the springs the reference's list holds twice.
+            auto pair = [&](int qa, bool ea, int qb, bool eb, float2 rest, float2 nks, float2 kd, OcPair3* keep) {
+                if (!ea && !eb) return;
+                const int a = ea ? qa : lp, bb = eb ? qb : lp;
+                OcPair3 qx, qv;
+                qx.x = make_float2(ea ? x0[a] : xm.x + 1.0f, eb ? x0[bb] : xm.x + 1.0f);
+                qx.y = make_float2(x1[a], x1[bb]); qx.z = make_float2(x2[a], x2[bb]);
+                qv.x = make_float2(v0[a], v0[bb]); qv.y = make_float2(v1[a], v1[bb]); qv.z = make_float2(v2[a], v2[bb]);
+                bool bad = false;
+                OcPair3 f = oc_spring2<M>(xm, vm, qx, qv, M::kExact ? rest : p_mul(rest, nks), nks, kd, c.one, bad);
+                if (M::kExact && bad) {                                      // rare: IEEE intrinsics
+                    const f3 fa = oc_spring<M>(xm, vm, make_f3(qx.x.x, qx.y.x, qx.z.x), make_f3(qv.x.x, qv.y.x, qv.z.x), rest.x, nks.x, kd.x);
+                    const f3 fb = oc_spring<M>(xm, vm, make_f3(qx.x.y, qx.y.y, qx.z.y), make_f3(qv.x.y, qv.y.y, qv.z.y), rest.y, nks.y, kd.y);
+                    f.x = make_float2(fa.x, fb.x); f.y = make_float2(fa.y, fb.y); f.z = make_float2(fa.z, fb.z);
+                }
+                if (ea) { F.x = M::add(F.x, f.x.x); F.y = M::add(F.y, f.y.x); F.z = M::add(F.z, f.z.x); }
+                if (eb) { F.x = M::add(F.x, f.x.y); F.y = M::add(F.y, f.y.y); F.z = M::add(F.z, f.z.y); }
+                if (keep) *keep = f;
+            };
+            auto shear_rest = [&](int ia, int ib, int jj) {                  // sqrt(dx2[ia] + dz2[jj]), sqrt(dx2[ib] + dz2[jj])
+                bool badr = false;
+                const float sa = M::add(c.dx2[ia], c.dz2[jj]), sb = M::add(c.dx2[ib], c.dz2[jj]);
+                float2 r = oc_sqrt2<M>(make_float2(sa, sb), badr);
+                if (M::kExact && badr) r = make_float2(M::sqrt(sa), M::sqrt(sb));
+                return r;
+            };
+            if (!pinned) {
+                const bool l1 = i - 1 >= 0, r1e = i + 1 < U, l2 = i - 2 >= 0, r2e = i + 2 < U;
+                const bool u1 = j - 1 >= 0, d1 = j + 1 < V, u2 = j - 2 >= 0, d2 = j + 2 < V;
+                const int im1 = l1 ? i - 1 : 0, im2 = l2 ? i - 2 : 0, jm1 = u1 ? j - 1 : 0, jm2 = u2 ? j - 2 : 0;
+                const float2 nS = p_bc(c.nks_struct), kS = p_bc(c.kd_struct), nSh = p_bc(c.nks_shear), kSh = p_bc(c.kd_shear);
+                const float2 nB = p_bc(c.nks_bend), kB = p_bc(c.kd_bend);
+                pair(lp - 1, l1, lp + 1, r1e, make_float2(c.rh1[im1], c.rh1[i]), nS, kS, nullptr);                            //  1  2   V:288-291
+                pair(lp - U, u1, lp + U, d1,  make_float2(c.rv1[jm1], c.rv1[j]), nS, kS, nullptr);                            //  3  4   V:294-297
+                pair(lp - U - 1, l1 && u1, lp - U + 1, r1e && u1, shear_rest(im1, i, jm1), nSh, kSh, nullptr);                //  5  6   V:301-305
+                pair(lp + U - 1, l1 && d1, lp + U + 1, r1e && d1, shear_rest(im1, i, j),   nSh, kSh, nullptr);                //  7  8
+                OcPair3 k;
+                k.x = k.y = k.z = make_float2(0.0f, 0.0f);
+                pair(lp - 2, l2, lp + 2, r2e, make_float2(c.rh2[im2], c.rh2[i]), nB, kB, &k);                                 //  9 10   V:309-314
+                if (i == U - 3 && r2e) { F.x = M::add(F.x, k.x.y); F.y = M::add(F.y, k.y.y); F.z = M::add(F.z, k.z.y); }      // 11      the row's last bend spring twice (V:313)
+                if (i == U - 1 && l2)  { F.x = M::add(F.x, k.x.x); F.y = M::add(F.y, k.y.x); F.z = M::add(F.z, k.z.x); }
+                pair(lp - 2 * U, u2, lp + 2 * U, d2, make_float2(c.rv2[jm2], c.rv2[j]), nB, kB, &k);                          // 12 13   V:315-320
+                if (j == V - 3 && d2) { F.x = M::add(F.x, k.x.y); F.y = M::add(F.y, k.y.y); F.z = M::add(F.z, k.z.y); }       // 14      the column's last bend spring twice (V:319)
+                if (j == V - 1 && u2) { F.x = M::add(F.x, k.x.x); F.y = M::add(F.y, k.y.x); F.z = M::add(F.z, k.z.x); }
+            }
+            bool hit;
+            const f3 n = oc_integrate_collide<M>(c, xm, d, F, &hit);
+            const float w = oc_u2f(hit ? OC_W_HIT : OC_W_PLAIN);
+            s.X(nxt, 0)[lp] = n.x; s.X(nxt, 1)[lp] = n.y; s.X(nxt, 2)[lp] = n.z; s.W(nxt)[op] = w;
+            if ((oj < 2 && b > 0) || (oj >= R - 2 && b + 1 < nb)) __stcg(exw + (size_t)j * U + i, make_float4(n.x, n.y, n.z, w));
+        }
+        __syncthreads();
+        if (tid == 0) {                       // (fence + release by one thread after the barrier: cumulative over the CTA's stores, as in OcDevCtx2::publish)
+            __threadfence();
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(flags + b), "r"(epoch + (unsigned)step) : "memory");
+        }
+        // ---- P2: derived state of the own rows (in place: nobody reads another particle's in this phase) ---------
+        for (int op = tid; op < R * U; op += T) {
+            const int lp = op + 2 * U;
+            f3 d = make_f3(0.0f, 0.0f, 0.0f);
+            if (!oc_hit(s.W(nxt)[op]))
+                d = make_f3(M::sub(s.X(nxt, 0)[lp], x0[lp]), M::sub(s.X(nxt, 1)[lp], x1[lp]), M::sub(s.X(nxt, 2)[lp], x2[lp]));
+            const f3 v = velocity(d);
+            s.D(0)[op] = d.x; s.D(1)[op] = d.y; s.D(2)[op] = d.z;
+            s.Vv(0)[lp] = v.x; s.Vv(1)[lp] = v.y; s.Vv(2)[lp] = v.z;
+        }
+        if (step < n_steps) {
+            // ---- the neighbours' boundary rows of this substep ---------------------------------------------------
+            bool ok = true;
+            if (tid == 0 && b > 0)       ok = oc_bandres_wait(c, flags + b - 1, epoch + (unsigned)step);
+            if (tid == 32 && b + 1 < nb) ok = oc_bandres_wait(c, flags + b + 1, epoch + (unsigned)step);
+            if (!__syncthreads_and(ok)) return;                          // a neighbour never arrived: error word set (oc_flag_wait)
+            const int n_up = (r0 - h0) * U, n_dn = (h1 - r1) * U;
+            for (int e = tid; e < n_up + n_dn; e += T) {
+                const int lp = e < n_up ? (h0 - jbase) * U + e : (r1 - jbase) * U + (e - n_up);
+                const float4 a = __ldcg(exw + ((long long)jbase * U + lp));
+                f3 d = make_f3(0.0f, 0.0f, 0.0f);
+                if (!oc_hit(a.w)) d = make_f3(M::sub(a.x, x0[lp]), M::sub(a.y, x1[lp]), M::sub(a.z, x2[lp]));
+                const f3 v = velocity(d);
+                s.X(nxt, 0)[lp] = a.x; s.X(nxt, 1)[lp] = a.y; s.X(nxt, 2)[lp] = a.z;
+                s.Vv(0)[lp] = v.x; s.Vv(1)[lp] = v.y; s.Vv(2)[lp] = v.z;
+            }
+        }
+        __syncthreads();
+        cur = nxt;
+    }
+    // ---- store: X(t+n) and, for more than one substep, X(t+n-1) --------------------------------------------
+    for (int op = tid; op < R * U; op += T) {
+        const int lp = op + 2 * U;
+        const long long g = goff + (long long)r0 * U + op;
+        dst[g] = make_float4(s.X(cur, 0)[lp], s.X(cur, 1)[lp], s.X(cur, 2)[lp], s.W(cur)[op]);
+        if (n_steps > 1) dst_prev[g] = make_float4(s.X(cur ^ 1, 0)[lp], s.X(cur ^ 1, 1)[lp], s.X(cur ^ 1, 2)[lp], s.W(cur ^ 1)[op]);
+    }
+}
+#endif

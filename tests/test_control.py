@@ -64,7 +64,7 @@ def test_cuda_custom_pins_match_oracle(nx, ny, steps, which):
     x0, xl0 = helpers.developed_state(nx, ny, 200)
     o = Oracle(nx, ny); o.set_state(x0, xl0); o.set_pins(pins); o.step(steps)
     ox, oxl = o.state()
-    for kernel, k in ((m.OC_KERNEL_MARCH2, 1), (m.OC_KERNEL_TWIN, 1), (m.OC_KERNEL_STREAM, 1), (m.OC_KERNEL_MARCH, 2), (m.OC_KERNEL_GATHER, 1), (m.OC_KERNEL_AUTO, 1)):
+    for kernel, k in ((m.OC_KERNEL_MARCH2, 1), (m.OC_KERNEL_TWIN, 1), (m.OC_KERNEL_STREAM, 1), (m.OC_KERNEL_MARCH, 2), (m.OC_KERNEL_GATHER, 1), (m.OC_KERNEL_AUTO, 1), (m.OC_KERNEL_BANDRES, 1)):
         c = m.Cloth(nx, ny, kernel=kernel, substeps_per_launch=k)
         c.upload(x0, xl0)
         c.set_pins(pins)

@@ -31,7 +31,7 @@ def golden(name):
 
 
 def kid(m, kernel):
-    return {"march": m.OC_KERNEL_MARCH, "gather": m.OC_KERNEL_GATHER, "march2": m.OC_KERNEL_MARCH2, "resident": m.OC_KERNEL_RESIDENT, "twin": m.OC_KERNEL_TWIN, "stream": m.OC_KERNEL_STREAM, "stream2": m.OC_KERNEL_STREAM2}[kernel]
+    return {"march": m.OC_KERNEL_MARCH, "gather": m.OC_KERNEL_GATHER, "march2": m.OC_KERNEL_MARCH2, "resident": m.OC_KERNEL_RESIDENT, "twin": m.OC_KERNEL_TWIN, "stream": m.OC_KERNEL_STREAM, "stream2": m.OC_KERNEL_STREAM2, "bandres": m.OC_KERNEL_BANDRES}[kernel]
 
 
 def nbad(a, b):
@@ -42,7 +42,7 @@ def nbad(a, b):
 # golden vectors of the verbatim reference
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("name", ["grid_21x21.npz", "grid_37x23.npz", "grid_64x64.npz", "grid_256x256.npz"])
-@pytest.mark.parametrize("kernel,k", [("march", 1), ("march", 4), ("gather", 1), ("march2", 1), ("resident", 1), ("twin", 1), ("stream", 1), ("stream2", 1)])
+@pytest.mark.parametrize("kernel,k", [("march", 1), ("march", 4), ("gather", 1), ("march2", 1), ("resident", 1), ("twin", 1), ("stream", 1), ("stream2", 1), ("bandres", 1)])
 def test_cuda_matches_reference_golden(name, kernel, k):
     g, meta = golden(name)
     nx, ny = meta["nx"], meta["ny"]
@@ -78,7 +78,7 @@ def test_energy_trajectory_matches_reference():
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("nx,ny,pre,steps", [(3, 3, 0, 300), (4, 7, 0, 300), (21, 21, 1650, 400), (37, 23, 1800, 300),
                                              (100, 61, 1500, 200), (129, 40, 800, 100), (300, 200, 600, 100), (1000, 37, 300, 50)])
-@pytest.mark.parametrize("kernel,k", [("march", 1), ("march", 2), ("march", 8), ("gather", 1), ("march2", 1), ("resident", 1), ("twin", 1), ("stream", 1), ("stream2", 1)])
+@pytest.mark.parametrize("kernel,k", [("march", 1), ("march", 2), ("march", 8), ("gather", 1), ("march2", 1), ("resident", 1), ("twin", 1), ("stream", 1), ("stream2", 1), ("bandres", 1)])
 def test_cuda_matches_oracle_bitwise(nx, ny, pre, steps, kernel, k):
     m = oc()
     x0, xl0 = helpers.developed_state(nx, ny, pre)
@@ -165,6 +165,69 @@ def test_large_grid_matches_oracle_2048():
         x4, xl4 = c.download(stride=4)
         assert bitwise_equal(x4[:, :3], ox) and (x4[:, 3] == 1.0).all()
         c.close()
+
+
+@pytest.mark.parametrize("nx,ny,steps", [(512, 512, 2400), (256, 256, 2400), (513, 301, 900), (100, 1000, 600), (700, 90, 600), (64, 40, 600)])
+def test_bandres_kernel_mid_size_cloths(nx, ny, steps):
+    """Kernel 8 (oc_k_bandres: one row band per CTA resident in shared memory, cooperative launch, two boundary rows
+    per band and substep through global memory): what AUTO picks between the one-CTA resident kernel and the marching
+    kernels.  One launch per oc_step call whatever n; bitwise equal to the gather kernel (plain launches, one thread
+    per particle) over thousands of substeps in odd call patterns - n = 1 writes one buffer, n > 1 two; the flag words
+    count on from launch to launch - across a particle edit, an upload and a change of time step; band heights that do
+    not divide the cloth; no flag wait may time out."""
+    import ctypes
+    m = oc()
+    a = m.Cloth(nx, ny)                                       # AUTO
+    g = m.Cloth(nx, ny, kernel=m.OC_KERNEL_GATHER)
+    l0 = a.launch_count
+    a.step(5); g.step(5)
+    assert a.launch_count - l0 == 1, "AUTO did not pick the band-resident kernel"
+    done = 5
+    plan = [1, 2, 7, 50, 3, 1, 1, 200]
+    i = 0
+    while done < steps:
+        n = min(plan[i % len(plan)] if i < 24 else 400, steps - done)
+        a.step(n); g.step(n); done += n
+        if i % 4 == 1:
+            xa, xla = a.download(); xg, xlg = g.download()
+            assert bitwise_equal(xa, xg) and bitwise_equal(xla, xlg), f"after {done} steps: {nbad(xa, xg)} particles differ"
+        if i == 5:
+            for c in (a, g):
+                c.set_particle((ny // 2) * nx + nx // 3, (0.25, 3.0, -0.5))
+        if i == 9:
+            xa, xla = a.download()
+            a.upload(xa, xla); g.upload(xa, xla)
+        if i == 13:
+            for c in (a, g):
+                c.set_params(dt=1.0 / 90.0)
+        i += 1
+    xa, xla = a.download(); xg, xlg = g.download()
+    assert bitwise_equal(xa, xg) and bitwise_equal(xla, xlg), f"{nbad(xa, xg)} particles differ"
+    out = (ctypes.c_ulonglong * 4)()
+    a._lib.oc_debug_counters(a._h, out)
+    assert (out[2] >> 40) == 0, "a flag wait timed out"
+    a.close(); g.close()
+
+
+def test_bandres_kernel_fast_mode_and_fallbacks():
+    """Tolerance mode of the band-resident kernel against the reference CPU path (north-star bound), and the cases it
+    hands to oc_k_march2: batches, cloths whose bands do not fit shared memory."""
+    m = oc()
+    nx = ny = 256
+    o = Oracle(nx, ny); o.step(100)
+    c = m.Cloth(nx, ny, kernel=m.OC_KERNEL_BANDRES, exact=0)
+    c.step(100)
+    err = np.abs(c.download()[0].astype(np.float64) - o.state()[0].astype(np.float64)).max()
+    assert err <= 1e-5 * EXTENT, err
+    c.close()
+    for kw in (dict(nx=64, ny=48, batch=3), dict(nx=1024, ny=1024, batch=1)):
+        b = m.Cloth(kw["nx"], kw["ny"], batch=kw["batch"], kernel=m.OC_KERNEL_BANDRES)
+        gk = m.Cloth(kw["nx"], kw["ny"], batch=kw["batch"], kernel=m.OC_KERNEL_GATHER)
+        l0 = b.launch_count
+        b.step(3); gk.step(3)
+        assert b.launch_count - l0 == 3                    # one launch per substep: the marching kernel
+        assert bitwise_equal(b.download()[0], gk.download()[0])
+        b.close(); gk.close()
 
 
 @pytest.mark.parametrize("nx,ny,steps,kernel", [(2048, 2048, 3000, "march2"), (4096, 1200, 600, "march2"), (1100, 5000, 600, "march2"),

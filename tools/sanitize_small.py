@@ -9,7 +9,7 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import opencloth_b200 as oc  # noqa: E402
 
-for kernel, k in ((1, 1), (2, 1), (2, 4), (3, 1), (4, 1), (5, 1), (6, 1), (7, 1)):
+for kernel, k in ((1, 1), (2, 1), (2, 4), (3, 1), (4, 1), (5, 1), (6, 1), (7, 1), (8, 1)):
     for exact in (1, 0):
         for nx, ny, batch in ((150, 70, 1), (37, 23, 3), (260, 40, 1), (21, 21, 2)):
             c = oc.Cloth(nx, ny, batch=batch, kernel=kernel, exact=exact, substeps_per_launch=k)
