@@ -511,6 +511,22 @@ def run_ours(args):
             bc.close()
             line["batch_config5"] = {"workload": "512 independent 128x128 cloths (one GPU's share of BASELINE config 5; no communication)",
                                      "value": 512 * 128 * 128 * n_c / (c_ms * 1e-3), "unit": UNIT, "steps": n_c, "mode": args.mode}
+        if world == 1 and args.workload == "cloth" and not args.no_batch:
+            # BASELINE config 2 (256 x 256, the parity configuration) and 512 x 512: mid-size cloths are served by the
+            # band-resident kernel (oc_k_bandres: state in shared memory, ALL the substeps of the call in one launch)
+            mid = {}
+            for side in (256, 512):
+                mc = oc.Cloth(side, side, device=local, exact=exact)
+                mc.step(W)
+                n_m = 1000
+                l0 = mc.launch_count
+                m_ms = mc.step_timed(n_m)
+                mid[f"{side}x{side}"] = {"value": side * side * n_m / (m_ms * 1e-3), "unit": UNIT, "steps": n_m, "ms_per_1000_steps": m_ms * 1000.0 / n_m,
+                                         "launches": mc.launch_count - l0}
+                mc.close()
+            mid["mode"] = args.mode
+            mid["kernel"] = "oc_k_bandres (AUTO for one whole cloth of about 10^3 .. 3*10^5 particles)"
+            line["mid_size"] = mid
         if world == 1 and not args.no_cpu_baseline:
             base, _ = cpu_reference(nx, 3, 1, budget_s=15.0)
             line["cpu_baseline"] = base
