@@ -98,7 +98,7 @@ struct oc_cloth {
     unsigned* in_flags;          // device: 2 x OC_LINK_STRIPS words released by the neighbours' boundary tiles
     // oc_k_bandres (mid-size cloths resident in shared memory, one row band per CTA): exchange rows of two parities, one
     // flag word per band, substeps taken so far (the flags count on from launch to launch); allocated at the first use
-    struct { float4* ex; unsigned* flags; unsigned epoch; int coop; } bres;
+    struct { void* ex; unsigned* flags; unsigned epoch; int coop; } bres;
     // run-time pin sets (oc_set_pins): bitmap over batch x ny x nx particles + per-row summary; empty = reference default
     std::vector<unsigned>* h_pins;
     std::vector<unsigned char>* h_pin_rows;
@@ -854,7 +854,9 @@ static int launch_rows(oc_cloth* c, int kern, const OcLaunch& L, int ra, int rb)
         if (!bandres_plan(c, &nb, &rmax)) return oc_fail(OC_ERR_INVALID, "oc_k_bandres does not apply to this cloth");
         const size_t NG = (size_t)c->p.nx * c->p.ny;
         if (!c->bres.ex) {
-            OC_CUDA(cudaMalloc(&c->bres.ex, 2 * NG * sizeof(float4)));
+            OC_CUDA(cudaMalloc(&c->bres.ex, OC_BANDRES_EX_BYTES(NG)));
+            OC_CUDA(cudaMemsetAsync(c->bres.ex, 0, OC_BANDRES_EX_BYTES(NG), c->stream));      // tag 0: nothing sent yet
+            c->bres.epoch = 0;
             OC_CUDA(cudaMalloc(&c->bres.flags, OC_BANDRES_MAX_BANDS * sizeof(unsigned)));
             OC_CUDA(cudaMemsetAsync(c->bres.flags, 0, OC_BANDRES_MAX_BANDS * sizeof(unsigned), c->stream));
             c->bres.epoch = 0;

@@ -9,13 +9,18 @@
 // rows, through a small global buffer and one flag word per band:
 //   P1  every own particle gathers its twelve springs from shared memory (six packed pairs, oc_spring2; the reference's
 //       order, see oc_gather.cuh), IntegrateVerlet, EllipsoidCollision -> X(t+1) into the other position buffer; boundary
-//       rows also go to the exchange buffer of this substep's parity;
-//       barrier; thread 0 releases the band's flag (= epoch + substep);
+//       rows also go to the exchange buffer of this substep's parity; barrier;
 //   P2  every own particle: X - X_last and the velocity, in place;
-//       threads 0 / 32 wait for the flags of the bands above / below; barrier; the halo rows' new positions come from
-//       the exchange buffer (ld.cg), their velocities are derived from them like everybody else's; barrier.
-// A band's exchange rows of parity p are overwritten two substeps later, after the band has seen its neighbours' flags of
-// the substep in between - which they release only after they have read parity p.  Arithmetic and order are those of the
+//       the halo rows' new positions come from the exchange buffer, their velocities are derived from them like everybody
+//       else's; barrier.
+// The exchange (OC_BANDRES_LL, default): every coordinate travels as ONE 64-bit word {float, tag = epoch + substep} - a scalar
+// 64-bit store is single-copy atomic, so a word whose tag matches carries its data; the collider flag rides in the top
+// bit of z's tag.  The reader polls the words it needs: one store and one load through L2 per substep, no fence, no flag
+// round trip (the "LL" protocol of collective libraries).  OC_BANDRES_LL=0: float4 rows (st.cg), fence, one flag word per
+// band released by thread 0, acquired by threads 0 / 32 of the neighbours, then ld.cg - two L2 round trips more
+// (256^2: 6.2 us per substep instead of the tagged words' figure in DESIGN.md 4.4).
+// A band's exchange rows of parity p are overwritten two substeps later, after the band has received its neighbours' rows of
+// the substep in between - which they send only after they have read parity p.  Arithmetic and order are those of the
 // other kernels: bit-identical to the reference in exact mode.
 // Limits: one whole cloth (no batch, no row band), Verlet, no Provot pass; the tallest band must fit shared memory
 // (oc_bandres_plan: up to ~300 k particles, e.g. 512 x 576).
@@ -26,6 +31,11 @@
 #define OC_BANDRES_THREADS 512
 #define OC_BANDRES_MAX_STEPS 4096           /* substeps per launch (bounds the run time of one launch) */
 #define OC_BANDRES_MAX_BANDS 1024
+#ifndef OC_BANDRES_LL
+#define OC_BANDRES_LL 1
+#endif
+// bytes of the exchange buffer for a cloth of n particles (two parities; LL: three 64-bit words per particle)
+#define OC_BANDRES_EX_BYTES(n) ((size_t)(n) * (OC_BANDRES_LL ? 48 : 32))
 #define OC_BANDRES_SMEM_MAX (224 * 1024)    /* dynamic shared memory of one CTA (one CTA per SM) */
 
 // shared memory (floats; strides of the TALLEST band so that every CTA has the same layout):
@@ -58,11 +68,44 @@ __device__ __forceinline__ bool oc_bandres_wait(const OcConst& c, const unsigned
     return oc_flag_wait<false>(c, p, want);
 }
 
+// tagged 64-bit words: {float bits, tag} in one scalar store / load (single-copy atomic), strong at GPU scope (L2)
+__device__ __forceinline__ void oc_bandres_put(unsigned long long* p, float v, unsigned tag)
+{
+    const unsigned long long w = ((unsigned long long)tag << 32) | (unsigned long long)__float_as_uint(v);
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(w) : "memory");
+}
+// x, y, z of one particle (words p, p + stride, p + 2 stride) once all three carry `tag`; a.w = the collider flag.
+// false: they never came (time-out / poison word, like oc_flag_wait)
+__device__ __forceinline__ bool oc_bandres_get(const OcConst& c, const unsigned long long* p, int stride, unsigned tag, float4& a)
+{
+    unsigned long long w0, w1, w2;
+    unsigned long long t0 = 0;
+    for (unsigned spins = 1;; ++spins) {
+        asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w0) : "l"(p) : "memory");
+        asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w1) : "l"(p + stride) : "memory");
+        asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w2) : "l"(p + 2 * stride) : "memory");
+        if ((unsigned)(w0 >> 32) == tag && (unsigned)(w1 >> 32) == tag && ((unsigned)(w2 >> 32) & 0x7fffffffu) == tag) break;
+        if ((spins & 1023u) != 0u) continue;
+        unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if (t0 == 0) t0 = t;
+        const bool poisoned = (*(volatile unsigned long long*)(c.dbg_cnt + 2) >> 40) != 0ull;
+        if (poisoned || t - t0 > ((c.dbg & 32) ? 50000000ull : 2000000000ull)) {
+            atomicAdd(c.dbg_cnt + 2, 1ull << 40);
+            if (c.err) { *(volatile unsigned*)c.err = 1u; __threadfence_system(); }
+            a = make_float4(0.0f, 0.0f, 0.0f, oc_u2f(OC_W_PLAIN));
+            return false;
+        }
+    }
+    a = make_float4(__uint_as_float((unsigned)w0), __uint_as_float((unsigned)w1), __uint_as_float((unsigned)w2),
+                    oc_u2f(((unsigned)(w2 >> 32) & 0x80000000u) ? OC_W_HIT : OC_W_PLAIN));
+    return true;
+}
+
 template <class M>
 __global__ void __launch_bounds__(OC_BANDRES_THREADS, 1)
 oc_k_bandres(const __grid_constant__ OcConst c, const float4* __restrict__ A, const float4* __restrict__ B,
              float4* __restrict__ dst, float4* __restrict__ dst_prev, int n_steps,
-             float4* __restrict__ ex, unsigned* __restrict__ flags, unsigned epoch, int rmax)
+             void* __restrict__ ex_, unsigned* __restrict__ flags, unsigned epoch, int rmax)
 {
     extern __shared__ __align__(16) unsigned char oc_dyn_smem[];
     const int U = c.U, V = c.V;
@@ -107,7 +150,9 @@ oc_k_bandres(const __grid_constant__ OcConst c, const float4* __restrict__ A, co
         const int nxt = cur ^ 1;
         const float* x0 = s.X(cur, 0); const float* x1 = s.X(cur, 1); const float* x2 = s.X(cur, 2);
         const float* v0 = s.Vv(0);     const float* v1 = s.Vv(1);     const float* v2 = s.Vv(2);
-        float4* exw = ex + (size_t)(step & 1) * NG;
+        float4* exw = reinterpret_cast<float4*>(ex_) + (size_t)(step & 1) * NG;                                  // flag protocol: rows of float4
+        unsigned long long* exl = reinterpret_cast<unsigned long long*>(ex_) + (size_t)(step & 1) * NG * 3;       // tagged words: [row][x, y, z][column]
+        const unsigned tag = (epoch + (unsigned)step) & 0x7fffffffu;
         // ---- P1: gather, integrate, collide ------------------------------------------------------------------
         for (int op = tid; op < R * U; op += T) {
             const int oj = op / U, i = op - oj * U, j = r0 + oj, lp = op + 2 * U;
@@ -166,10 +211,17 @@ oc_k_bandres(const __grid_constant__ OcConst c, const float4* __restrict__ A, co
             const f3 n = oc_integrate_collide<M>(c, xm, d, F, &hit);
             const float w = oc_u2f(hit ? OC_W_HIT : OC_W_PLAIN);
             s.X(nxt, 0)[lp] = n.x; s.X(nxt, 1)[lp] = n.y; s.X(nxt, 2)[lp] = n.z; s.W(nxt)[op] = w;
-            if ((oj < 2 && b > 0) || (oj >= R - 2 && b + 1 < nb)) __stcg(exw + (size_t)j * U + i, make_float4(n.x, n.y, n.z, w));
+            if ((oj < 2 && b > 0) || (oj >= R - 2 && b + 1 < nb)) {
+                if (OC_BANDRES_LL) {
+                    unsigned long long* e = exl + (size_t)j * 3 * U + i;
+                    oc_bandres_put(e, n.x, tag); oc_bandres_put(e + U, n.y, tag); oc_bandres_put(e + 2 * U, n.z, tag | (hit ? 0x80000000u : 0u));
+                } else {
+                    __stcg(exw + (size_t)j * U + i, make_float4(n.x, n.y, n.z, w));
+                }
+            }
         }
         __syncthreads();
-        if (tid == 0) {                       // (fence + release by one thread after the barrier: cumulative over the CTA's stores, as in OcDevCtx2::publish)
+        if (!OC_BANDRES_LL && tid == 0) {     // (fence + release by one thread after the barrier: cumulative over the CTA's stores, as in OcDevCtx2::publish)
             __threadfence();
             asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(flags + b), "r"(epoch + (unsigned)step) : "memory");
         }
@@ -183,16 +235,24 @@ oc_k_bandres(const __grid_constant__ OcConst c, const float4* __restrict__ A, co
             s.D(0)[op] = d.x; s.D(1)[op] = d.y; s.D(2)[op] = d.z;
             s.Vv(0)[lp] = v.x; s.Vv(1)[lp] = v.y; s.Vv(2)[lp] = v.z;
         }
+        bool ok = true;
         if (step < n_steps) {
             // ---- the neighbours' boundary rows of this substep ---------------------------------------------------
-            bool ok = true;
-            if (tid == 0 && b > 0)       ok = oc_bandres_wait(c, flags + b - 1, epoch + (unsigned)step);
-            if (tid == 32 && b + 1 < nb) ok = oc_bandres_wait(c, flags + b + 1, epoch + (unsigned)step);
-            if (!__syncthreads_and(ok)) return;                          // a neighbour never arrived: error word set (oc_flag_wait)
+            if (!OC_BANDRES_LL) {
+                if (tid == 0 && b > 0)       ok = oc_bandres_wait(c, flags + b - 1, epoch + (unsigned)step);
+                if (tid == 32 && b + 1 < nb) ok = oc_bandres_wait(c, flags + b + 1, epoch + (unsigned)step);
+                if (!__syncthreads_and(ok)) return;                      // a neighbour never arrived: error word set (oc_flag_wait)
+            }
             const int n_up = (r0 - h0) * U, n_dn = (h1 - r1) * U;
             for (int e = tid; e < n_up + n_dn; e += T) {
                 const int lp = e < n_up ? (h0 - jbase) * U + e : (r1 - jbase) * U + (e - n_up);
-                const float4 a = __ldcg(exw + ((long long)jbase * U + lp));
+                float4 a;
+                if (OC_BANDRES_LL) {
+                    const int lj = lp / U, i = lp - lj * U;
+                    ok &= oc_bandres_get(c, exl + ((long long)(jbase + lj) * 3 * U + i), U, tag, a);
+                } else {
+                    a = __ldcg(exw + ((long long)jbase * U + lp));
+                }
                 f3 d = make_f3(0.0f, 0.0f, 0.0f);
                 if (!oc_hit(a.w)) d = make_f3(M::sub(a.x, x0[lp]), M::sub(a.y, x1[lp]), M::sub(a.z, x2[lp]));
                 const f3 v = velocity(d);
@@ -200,6 +260,8 @@ oc_k_bandres(const __grid_constant__ OcConst c, const float4* __restrict__ A, co
                 s.Vv(0)[lp] = v.x; s.Vv(1)[lp] = v.y; s.Vv(2)[lp] = v.z;
             }
         }
+        if (OC_BANDRES_LL) { if (!__syncthreads_and(ok)) return; }       // a neighbour's rows never arrived: error word set (oc_bandres_get)
+        else
         __syncthreads();
         cur = nxt;
     }
