@@ -388,8 +388,8 @@ extern "C" int oc_create(oc_cloth** out, const oc_params* p)
     // function attributes are per device: set them at every create, for the device of this handle
     if (rc == 0) rc = (int)cudaFuncSetAttribute((const void*)&oc_k_resident<MathExact>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OcResidentSmem::bytes(OC_RESIDENT_MAX_PARTICLES));
     if (rc == 0) rc = (int)cudaFuncSetAttribute((const void*)&oc_k_resident<MathFast>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OcResidentSmem::bytes(OC_RESIDENT_MAX_PARTICLES));
-    if (rc == 0) rc = (int)cudaFuncSetAttribute((const void*)&oc_k_bandres<MathExact>, cudaFuncAttributeMaxDynamicSharedMemorySize, OC_BANDRES_SMEM_MAX);
-    if (rc == 0) rc = (int)cudaFuncSetAttribute((const void*)&oc_k_bandres<MathFast>, cudaFuncAttributeMaxDynamicSharedMemorySize, OC_BANDRES_SMEM_MAX);
+    if (rc == 0) rc = (int)cudaFuncSetAttribute((const void*)&oc_k_bandres<MathExact, OC_BANDRES_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, OC_BANDRES_SMEM_MAX);
+    if (rc == 0) rc = (int)cudaFuncSetAttribute((const void*)&oc_k_bandres<MathFast, OC_BANDRES_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, OC_BANDRES_SMEM_MAX);
     if (rc == 0) rc = (int)cudaDeviceGetAttribute(&c->bres.coop, cudaDevAttrCooperativeLaunch, c->dev);
     if (rc != 0) { free_handle(c); return oc_fail(OC_ERR_CUDA, "oc_march_configure failed: %s", cudaGetErrorString((cudaError_t)rc)); }
 #undef OC_CREATE_CUDA
@@ -866,9 +866,12 @@ static int launch_rows(oc_cloth* c, int kern, const OcLaunch& L, int ra, int rb)
         int S = L.S;
         unsigned epoch = c->bres.epoch;
         void* args[] = { (void*)&c->k, (void*)&a, (void*)&b, (void*)&d0, (void*)&d1, (void*)&S, (void*)&c->bres.ex, (void*)&c->bres.flags, (void*)&epoch, (void*)&rmax };
-        const void* fn = c->p.exact ? (const void*)&oc_k_bandres<MathExact> : (const void*)&oc_k_bandres<MathFast>;
+        // (768 threads per CTA - 24 warps at 80 registers, three instead of four rounds of particles at 512^2 - measured equal
+        // within +-5 %, profiles/r2/bandres_threads.log: the gather is bound by its instruction count, not by the rounds)
+        const int threads = OC_BANDRES_THREADS;
+        const void* fn = c->p.exact ? (const void*)&oc_k_bandres<MathExact, OC_BANDRES_THREADS> : (const void*)&oc_k_bandres<MathFast, OC_BANDRES_THREADS>;
         if (c->k.dbg & 16) fprintf(stderr, "[oc] bandres: %d bands of <= %d rows, %zu bytes of shared memory, %d substeps\n", nb, rmax, OcBandresSmem::bytes(c->p.nx, rmax), S);
-        cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(nb), dim3(OC_BANDRES_THREADS), args, OcBandresSmem::bytes(c->p.nx, rmax), c->stream);
+        cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(nb), dim3(threads), args, OcBandresSmem::bytes(c->p.nx, rmax), c->stream);
         if (e != cudaSuccess) return oc_fail(OC_ERR_CUDA, "oc_k_bandres launch failed: %s", cudaGetErrorString(e));
         c->bres.epoch += (unsigned)S;
         c->launches++;

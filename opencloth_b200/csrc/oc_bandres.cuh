@@ -101,8 +101,8 @@ __device__ __forceinline__ bool oc_bandres_get(const OcConst& c, const unsigned 
     return true;
 }
 
-template <class M>
-__global__ void __launch_bounds__(OC_BANDRES_THREADS, 1)
+template <class M, int TT>
+__global__ void __launch_bounds__(TT, 1)
 oc_k_bandres(const __grid_constant__ OcConst c, const float4* __restrict__ A, const float4* __restrict__ B,
              float4* __restrict__ dst, float4* __restrict__ dst_prev, int n_steps,
              void* __restrict__ ex_, unsigned* __restrict__ flags, unsigned epoch, int rmax)
