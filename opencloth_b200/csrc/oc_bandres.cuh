@@ -38,15 +38,16 @@
 #define OC_BANDRES_EX_BYTES(n) ((size_t)(n) * (OC_BANDRES_LL ? 48 : 32))
 #define OC_BANDRES_SMEM_MAX (224 * 1024)    /* dynamic shared memory of one CTA (one CTA per SM) */
 
-// shared memory (floats; strides of the TALLEST band so that every CTA has the same layout):
-//   NL = (rmax + 4) * U local particles incl. halo rows, NO = rmax * U own particles
+// shared memory (strides of the TALLEST band so that every CTA has the same layout): NL = (rmax + 4) * U local particles
+// incl. halo rows, NO = rmax * U own particles.  Positions and velocities are float4 records - one LDS.128 and one address
+// per neighbour and quantity instead of three scalar loads from three arrays (the gather is bound by its instruction
+// count); w of a position is the collider flag, as in global memory.
 struct OcBandresSmem {
-    float* base; int NL, NO;
-    OC_HD float* X(int buf, int k) const { return base + (size_t)(3 * buf + k) * NL; }      // positions, two buffers (t / t-1, swapped every substep)
-    OC_HD float* Vv(int k) const { return base + (size_t)(6 + k) * NL; }                    // velocity
-    OC_HD float* D(int k) const { return base + (size_t)9 * NL + (size_t)k * NO; }          // X(t) - X_last(t), own rows
-    OC_HD float* W(int buf) const { return base + (size_t)9 * NL + (size_t)(3 + buf) * NO; } // w of the position buffer (collider flag), own rows
-    static OC_HD size_t bytes(int U, int rmax) { return ((size_t)9 * (rmax + 4) * U + (size_t)5 * rmax * U) * sizeof(float); }
+    unsigned char* base; int NL, NO;
+    OC_HD float4* X(int buf) const { return reinterpret_cast<float4*>(base) + (size_t)buf * NL; }     // positions, two buffers (t / t-1, swapped every substep)
+    OC_HD float4* Vv() const { return reinterpret_cast<float4*>(base) + (size_t)2 * NL; }              // velocity (w unused)
+    OC_HD float* D(int k) const { return reinterpret_cast<float*>(base + (size_t)48 * NL) + (size_t)k * NO; }   // X(t) - X_last(t), own rows
+    static OC_HD size_t bytes(int U, int rmax) { return (size_t)48 * (rmax + 4) * U + (size_t)12 * rmax * U; }
 };
 
 // rows [r0, r1) of band b of nb over V rows: even cut, every band >= 2 rows when nb <= V / 2
@@ -116,7 +117,7 @@ oc_k_bandres(const __grid_constant__ OcConst c, const float4* __restrict__ A, co
     const int jbase = r0 - 2;                                        // global row of local row 0
     const int h0 = r0 - 2 < 0 ? 0 : r0 - 2, h1 = r1 + 2 > V ? V : r1 + 2;   // rows held locally
     OcBandresSmem s;
-    s.base = reinterpret_cast<float*>(oc_dyn_smem); s.NL = (rmax + 4) * U; s.NO = rmax * U;
+    s.base = oc_dyn_smem; s.NL = (rmax + 4) * U; s.NO = rmax * U;
     const long long goff = -(long long)c.row_lo * U;                 // storage offset of global row 0 (whole cloths: 0)
     const float ydt = oc_rcp_bf(c.dt);
     const size_t NG = (size_t)U * V;
@@ -132,32 +133,28 @@ oc_k_bandres(const __grid_constant__ OcConst c, const float4* __restrict__ A, co
     for (int lp = (h0 - jbase) * U + tid; lp < (h1 - jbase) * U; lp += T) {
         const long long g = goff + (long long)jbase * U + lp;
         const float4 a = A[g], q = B[g];
-        s.X(0, 0)[lp] = a.x; s.X(0, 1)[lp] = a.y; s.X(0, 2)[lp] = a.z;
-        s.X(1, 0)[lp] = q.x; s.X(1, 1)[lp] = q.y; s.X(1, 2)[lp] = q.z;
+        s.X(0)[lp] = a; s.X(1)[lp] = q;
         const f3 d = oc_delta<M>(a, q);
         const f3 v = velocity(d);
-        s.Vv(0)[lp] = v.x; s.Vv(1)[lp] = v.y; s.Vv(2)[lp] = v.z;
+        s.Vv()[lp] = make_float4(v.x, v.y, v.z, 0.0f);
         const int op = lp - 2 * U;
-        if (op >= 0 && op < R * U) {
-            s.D(0)[op] = d.x; s.D(1)[op] = d.y; s.D(2)[op] = d.z;
-            s.W(0)[op] = a.w; s.W(1)[op] = q.w;
-        }
+        if (op >= 0 && op < R * U) { s.D(0)[op] = d.x; s.D(1)[op] = d.y; s.D(2)[op] = d.z; }
     }
     __syncthreads();
 
     int cur = 0;
     for (int step = 1; step <= n_steps; ++step) {
         const int nxt = cur ^ 1;
-        const float* x0 = s.X(cur, 0); const float* x1 = s.X(cur, 1); const float* x2 = s.X(cur, 2);
-        const float* v0 = s.Vv(0);     const float* v1 = s.Vv(1);     const float* v2 = s.Vv(2);
+        const float4* xc = s.X(cur); float4* xn = s.X(nxt); float4* vv = s.Vv();
         float4* exw = reinterpret_cast<float4*>(ex_) + (size_t)(step & 1) * NG;                                  // flag protocol: rows of float4
         unsigned long long* exl = reinterpret_cast<unsigned long long*>(ex_) + (size_t)(step & 1) * NG * 3;       // tagged words: [row][x, y, z][column]
         const unsigned tag = (epoch + (unsigned)step) & 0x7fffffffu;
         // ---- P1: gather, integrate, collide ------------------------------------------------------------------
         for (int op = tid; op < R * U; op += T) {
             const int oj = op / U, i = op - oj * U, j = r0 + oj, lp = op + 2 * U;
-            const f3 xm = make_f3(x0[lp], x1[lp], x2[lp]);
-            const f3 vm = make_f3(v0[lp], v1[lp], v2[lp]);
+            const float4 xm4 = xc[lp], vm4 = vv[lp];
+            const f3 xm = make_f3(xm4.x, xm4.y, xm4.z);
+            const f3 vm = make_f3(vm4.x, vm4.y, vm4.z);
             const f3 d  = make_f3(s.D(0)[op], s.D(1)[op], s.D(2)[op]);
             const bool pinned = oc_pinned(c, 0, i, j);
             f3 F = oc_base_force<M>(c, vm, pinned);
@@ -166,10 +163,11 @@ oc_k_bandres(const __grid_constant__ OcConst c, const float4* __restrict__ A, co
             auto pair = [&](int qa, bool ea, int qb, bool eb, float2 rest, float2 nks, float2 kd, OcPair3* keep) {
                 if (!ea && !eb) return;
                 const int a = ea ? qa : lp, bb = eb ? qb : lp;
+                const float4 xa = xc[a], xb = xc[bb], va = vv[a], vb = vv[bb];
                 OcPair3 qx, qv;
-                qx.x = make_float2(ea ? x0[a] : xm.x + 1.0f, eb ? x0[bb] : xm.x + 1.0f);
-                qx.y = make_float2(x1[a], x1[bb]); qx.z = make_float2(x2[a], x2[bb]);
-                qv.x = make_float2(v0[a], v0[bb]); qv.y = make_float2(v1[a], v1[bb]); qv.z = make_float2(v2[a], v2[bb]);
+                qx.x = make_float2(ea ? xa.x : xm.x + 1.0f, eb ? xb.x : xm.x + 1.0f);
+                qx.y = make_float2(xa.y, xb.y); qx.z = make_float2(xa.z, xb.z);
+                qv.x = make_float2(va.x, vb.x); qv.y = make_float2(va.y, vb.y); qv.z = make_float2(va.z, vb.z);
                 bool bad = false;
                 OcPair3 f = oc_spring2<M>(xm, vm, qx, qv, M::kExact ? rest : p_mul(rest, nks), nks, kd, c.one, bad);
                 if (M::kExact && bad) {                                      // rare: IEEE intrinsics
@@ -210,7 +208,7 @@ oc_k_bandres(const __grid_constant__ OcConst c, const float4* __restrict__ A, co
             bool hit;
             const f3 n = oc_integrate_collide<M>(c, xm, d, F, &hit);
             const float w = oc_u2f(hit ? OC_W_HIT : OC_W_PLAIN);
-            s.X(nxt, 0)[lp] = n.x; s.X(nxt, 1)[lp] = n.y; s.X(nxt, 2)[lp] = n.z; s.W(nxt)[op] = w;
+            xn[lp] = make_float4(n.x, n.y, n.z, w);
             if ((oj < 2 && b > 0) || (oj >= R - 2 && b + 1 < nb)) {
                 if (OC_BANDRES_LL) {
                     unsigned long long* e = exl + (size_t)j * 3 * U + i;
@@ -228,12 +226,12 @@ oc_k_bandres(const __grid_constant__ OcConst c, const float4* __restrict__ A, co
         // ---- P2: derived state of the own rows (in place: nobody reads another particle's in this phase) ---------
         for (int op = tid; op < R * U; op += T) {
             const int lp = op + 2 * U;
+            const float4 nw = xn[lp], ol = xc[lp];
             f3 d = make_f3(0.0f, 0.0f, 0.0f);
-            if (!oc_hit(s.W(nxt)[op]))
-                d = make_f3(M::sub(s.X(nxt, 0)[lp], x0[lp]), M::sub(s.X(nxt, 1)[lp], x1[lp]), M::sub(s.X(nxt, 2)[lp], x2[lp]));
+            if (!oc_hit(nw.w)) d = make_f3(M::sub(nw.x, ol.x), M::sub(nw.y, ol.y), M::sub(nw.z, ol.z));
             const f3 v = velocity(d);
             s.D(0)[op] = d.x; s.D(1)[op] = d.y; s.D(2)[op] = d.z;
-            s.Vv(0)[lp] = v.x; s.Vv(1)[lp] = v.y; s.Vv(2)[lp] = v.z;
+            vv[lp] = make_float4(v.x, v.y, v.z, 0.0f);
         }
         bool ok = true;
         if (step < n_steps) {
@@ -253,11 +251,12 @@ oc_k_bandres(const __grid_constant__ OcConst c, const float4* __restrict__ A, co
                 } else {
                     a = __ldcg(exw + ((long long)jbase * U + lp));
                 }
+                const float4 ol = xc[lp];
                 f3 d = make_f3(0.0f, 0.0f, 0.0f);
-                if (!oc_hit(a.w)) d = make_f3(M::sub(a.x, x0[lp]), M::sub(a.y, x1[lp]), M::sub(a.z, x2[lp]));
+                if (!oc_hit(a.w)) d = make_f3(M::sub(a.x, ol.x), M::sub(a.y, ol.y), M::sub(a.z, ol.z));
                 const f3 v = velocity(d);
-                s.X(nxt, 0)[lp] = a.x; s.X(nxt, 1)[lp] = a.y; s.X(nxt, 2)[lp] = a.z;
-                s.Vv(0)[lp] = v.x; s.Vv(1)[lp] = v.y; s.Vv(2)[lp] = v.z;
+                xn[lp] = a;
+                vv[lp] = make_float4(v.x, v.y, v.z, 0.0f);
             }
         }
         if (OC_BANDRES_LL) { if (!__syncthreads_and(ok)) return; }       // a neighbour's rows never arrived: error word set (oc_bandres_get)
@@ -269,8 +268,8 @@ oc_k_bandres(const __grid_constant__ OcConst c, const float4* __restrict__ A, co
     for (int op = tid; op < R * U; op += T) {
         const int lp = op + 2 * U;
         const long long g = goff + (long long)r0 * U + op;
-        dst[g] = make_float4(s.X(cur, 0)[lp], s.X(cur, 1)[lp], s.X(cur, 2)[lp], s.W(cur)[op]);
-        if (n_steps > 1) dst_prev[g] = make_float4(s.X(cur ^ 1, 0)[lp], s.X(cur ^ 1, 1)[lp], s.X(cur ^ 1, 2)[lp], s.W(cur ^ 1)[op]);
+        dst[g] = s.X(cur)[lp];
+        if (n_steps > 1) dst_prev[g] = s.X(cur ^ 1)[lp];
     }
 }
 #endif
