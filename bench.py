@@ -25,6 +25,8 @@ Arithmetic mode (--mode): `fast` (default) is north_star's tolerance mode — FM
 the reference CPU path to <= 1e-5 of the cloth extent after 100 steps and 1e-3 after 1000 (tests/test_parity_gpu.py,
 incl. at this bench's 2048^2) — and runs the streaming gather kernel oc_k_stream; `exact` is bit-identical to the
 reference CPU path (oc_k_march2).  Every N = 1 line reports the other mode as `other_mode`.
+Every N = 1 line also carries `scaling_base` (8192^2 on this GPU), `batch_config5` (512 x 128^2 cloths) and `mid_size`
+(256^2 = BASELINE config 2 and 512^2: 1000 steps in one launch of the band-resident kernel oc_k_bandres).
 """
 import argparse
 import hashlib
