@@ -772,17 +772,7 @@ static bool oc_stream_pays(const oc_cloth* c) { return (long long)c->p.nx * c->r
 static bool bandres_plan(const oc_cloth* c, int* nb, int* rmax)
 {
     if (c->q.band || c->link.on || c->p.batch != 1 || c->p.integrator != OC_INTEGRATOR_VERLET || c->p.provot || !c->bres.coop) return false;
-    const int V = c->p.ny, U = c->p.nx;
-    if (V < 4) return false;
-    int n = c->sm_count < V / 2 ? c->sm_count : V / 2;
-    if (n > OC_BANDRES_MAX_BANDS) n = OC_BANDRES_MAX_BANDS;
-    // no more bands than give every CTA's threads a particle
-    const int want = (int)(((long long)U * V + OC_BANDRES_THREADS - 1) / OC_BANDRES_THREADS);
-    if (n > want) n = want < 1 ? 1 : want;
-    const int r = (V + n - 1) / n;
-    if (OcBandresSmem::bytes(U, r) > (size_t)OC_BANDRES_SMEM_MAX) return false;
-    *nb = n; *rmax = r;
-    return true;
+    return oc_bandres_plan(c->p.nx, c->p.ny, c->sm_count, nb, rmax);
 }
 
 static int pick_kernel(const oc_cloth* c)

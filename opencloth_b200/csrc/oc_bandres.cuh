@@ -56,6 +56,22 @@ OC_HD void oc_bandres_rows(int V, int nb, int b, int& r0, int& r1)
     r0 = (int)((long long)b * V / nb); r1 = (int)((long long)(b + 1) * V / nb);
 }
 
+// Bands and rows of the tallest band for a U x V cloth on a device of sm_count SMs; false if the state of the tallest band
+// does not fit the shared memory of one SM.  At most one band per SM, every band at least two rows (the stencil reaches two
+// rows: a band's halo then comes from its two neighbours only), no more bands than give every CTA's threads a particle.
+OC_HD bool oc_bandres_plan(int U, int V, int sm_count, int* nb, int* rmax)
+{
+    if (U < 1 || V < 4 || sm_count < 1) return false;
+    int n = sm_count < V / 2 ? sm_count : V / 2;
+    if (n > OC_BANDRES_MAX_BANDS) n = OC_BANDRES_MAX_BANDS;
+    const long long want = ((long long)U * V + OC_BANDRES_THREADS - 1) / OC_BANDRES_THREADS;
+    if (n > want) n = want < 1 ? 1 : (int)want;
+    const int r = (V + n - 1) / n;
+    if (OcBandresSmem::bytes(U, r) > (size_t)OC_BANDRES_SMEM_MAX) return false;
+    *nb = n; *rmax = r;
+    return true;
+}
+
 #ifdef __CUDACC__
 // the flag of a neighbour band: a short busy poll first (the neighbour is normally a few hundred cycles away), then the
 // backed-off wait with its time-out and poison word (oc_flag_wait)

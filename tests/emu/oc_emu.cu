@@ -41,6 +41,7 @@
 #include "../../opencloth_b200/csrc/oc_stream2.cuh"
 #if EMU_HAS(0)
 #include "../../opencloth_b200/csrc/oc_resident.cuh"      // (holds non-template kernels: one part only)
+#include "../../opencloth_b200/csrc/oc_bandres.cuh"       // (host side only: the band plan; the kernel needs concurrently running CTAs)
 #endif
 
 #include <ucontext.h>
@@ -728,6 +729,14 @@ int emu_bounding_sphere(void* h, float out[4])
 int emu_halo_refreshed(void* h) { ((EmuCloth*)h)->q.fresh = 0; return 0; }
 int emu_halo_budget(void* h) { EmuCloth* e = (EmuCloth*)h; return e->q.band ? e->q.kmax - e->q.fresh : 0x7fffffff; }
 
+// oc_k_bandres: the host-side plan (bands, rows of the tallest band, shared memory) and the row cut
+int emu_bandres_plan(int U, int V, int sm_count, int* nb, int* rmax, unsigned long long* smem)
+{
+    if (!oc_bandres_plan(U, V, sm_count, nb, rmax)) return 0;
+    *smem = (unsigned long long)OcBandresSmem::bytes(U, *rmax);
+    return 1;
+}
+void emu_bandres_rows(int V, int nb, int b, int* r0, int* r1) { oc_bandres_rows(V, nb, b, *r0, *r1); }
 } // extern "C"
 
 #endif      // EMU_HAS(0)

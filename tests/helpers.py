@@ -338,6 +338,8 @@ def emu_lib():
         L.emu_band_link.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int]
         L.emu_bounding_sphere.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         L.emu_check_tiling.argtypes = [ctypes.c_int] * 10
+        L.emu_bandres_plan.argtypes = [ctypes.c_int] * 3 + [ctypes.POINTER(ctypes.c_int)] * 2 + [ctypes.POINTER(ctypes.c_ulonglong)]
+        L.emu_bandres_rows.argtypes = [ctypes.c_int] * 3 + [ctypes.POINTER(ctypes.c_int)] * 2
         _emu = L
     return _emu
 

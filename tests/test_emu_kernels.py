@@ -418,3 +418,32 @@ def test_tile_dependencies_cover_every_producer():
         assert rc >= 0, f"violation {rc}: strips {nstrips}, prev [{pra},{prb}) {prs}|{prs_e}, now [{ra},{rb}) {rs}|{rs_e}"
         chained += rc == 0
     assert chained > 1000
+
+
+def test_bandres_plan_cuts_every_cloth_into_bands_that_fit():
+    """Host logic of kernel 8 (oc_k_bandres; the kernel itself needs concurrently running CTAs and is covered on the GPU):
+    at most one band per SM, the bands tile the rows exactly, every band has at least two rows - so that a band's two halo
+    rows come from its direct neighbours - and at most `rmax` rows, the tallest band's state fits one SM's shared memory,
+    and a cloth whose bands would not fit is refused (it goes to the marching kernel)."""
+    import ctypes
+    L = helpers.emu_lib()
+    nb, rmax, smem = ctypes.c_int(), ctypes.c_int(), ctypes.c_ulonglong()
+    fits = {}
+    for U, V in ((21, 21), (64, 48), (37, 23), (100, 61), (256, 256), (300, 200), (513, 301), (100, 1000), (700, 90), (512, 512),
+                 (512, 576), (512, 640), (1024, 1024), (2048, 2048), (4096, 16), (8, 4), (5, 3)):
+        ok = L.emu_bandres_plan(U, V, 148, ctypes.byref(nb), ctypes.byref(rmax), ctypes.byref(smem))
+        fits[(U, V)] = bool(ok)
+        if not ok:
+            continue
+        n = nb.value
+        assert 1 <= n <= 148 and n <= max(1, V // 2) and smem.value <= 224 * 1024
+        assert n == 1 or (n - 1) * 512 < U * V                      # no band without a particle per thread (but at least one band)
+        prev = 0
+        for b in range(n):
+            r0, r1 = ctypes.c_int(), ctypes.c_int()
+            L.emu_bandres_rows(V, n, b, ctypes.byref(r0), ctypes.byref(r1))
+            assert r0.value == prev and (n == 1 or r1.value - r0.value >= 2) and r1.value - r0.value <= rmax.value
+            prev = r1.value
+        assert prev == V
+    assert fits[(256, 256)] and fits[(512, 512)] and fits[(512, 576)] and fits[(100, 1000)] and fits[(64, 48)]
+    assert not fits[(1024, 1024)] and not fits[(2048, 2048)] and not fits[(4096, 16)] and not fits[(5, 3)]
