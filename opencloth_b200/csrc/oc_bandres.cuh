@@ -118,22 +118,25 @@ __device__ __forceinline__ bool oc_bandres_get(const OcConst& c, const unsigned 
     return true;
 }
 
-template <class M, int TT>
-__global__ void __launch_bounds__(TT, 1)
-oc_k_bandres(const __grid_constant__ OcConst c, const float4* __restrict__ A, const float4* __restrict__ B,
-             float4* __restrict__ dst, float4* __restrict__ dst_prev, int n_steps,
-             void* __restrict__ ex_, unsigned* __restrict__ flags, unsigned epoch, int rmax)
+#endif      // __CUDACC__
+
+// The kernel body over an execution context (the device's OcBandresCtx below; tests/emu/oc_emu.cu runs the same body on
+// the CPU with every CTA's threads as fibers, so that the exchange protocol is checked without a GPU):
+//   tid, nthreads, band (CTA index), nbands, smem, sync, sync_and, put / get (the tagged 64-bit words)
+template <class M, class Ctx>
+OC_HD void oc_bandres_body(Ctx& ctx, const OcConst& c, const float4* __restrict__ A, const float4* __restrict__ B,
+                           float4* __restrict__ dst, float4* __restrict__ dst_prev, int n_steps,
+                           void* __restrict__ ex_, unsigned* __restrict__ flags, unsigned epoch, int rmax)
 {
-    extern __shared__ __align__(16) unsigned char oc_dyn_smem[];
     const int U = c.U, V = c.V;
-    const int tid = threadIdx.x, T = blockDim.x, b = blockIdx.x, nb = gridDim.x;
+    const int tid = ctx.tid(), T = ctx.nthreads(), b = ctx.band(), nb = ctx.nbands();
     int r0, r1;
     oc_bandres_rows(V, nb, b, r0, r1);
     const int R = r1 - r0;
     const int jbase = r0 - 2;                                        // global row of local row 0
     const int h0 = r0 - 2 < 0 ? 0 : r0 - 2, h1 = r1 + 2 > V ? V : r1 + 2;   // rows held locally
     OcBandresSmem s;
-    s.base = oc_dyn_smem; s.NL = (rmax + 4) * U; s.NO = rmax * U;
+    s.base = ctx.smem(); s.NL = (rmax + 4) * U; s.NO = rmax * U;
     const long long goff = -(long long)c.row_lo * U;                 // storage offset of global row 0 (whole cloths: 0)
     const float ydt = oc_rcp_bf(c.dt);
     const size_t NG = (size_t)U * V;
@@ -156,13 +159,14 @@ oc_k_bandres(const __grid_constant__ OcConst c, const float4* __restrict__ A, co
         const int op = lp - 2 * U;
         if (op >= 0 && op < R * U) { s.D(0)[op] = d.x; s.D(1)[op] = d.y; s.D(2)[op] = d.z; }
     }
-    __syncthreads();
+    ctx.sync();
 
     int cur = 0;
     for (int step = 1; step <= n_steps; ++step) {
         const int nxt = cur ^ 1;
         const float4* xc = s.X(cur); float4* xn = s.X(nxt); float4* vv = s.Vv();
         float4* exw = reinterpret_cast<float4*>(ex_) + (size_t)(step & 1) * NG;                                  // flag protocol: rows of float4
+        (void)exw; (void)flags;
         unsigned long long* exl = reinterpret_cast<unsigned long long*>(ex_) + (size_t)(step & 1) * NG * 3;       // tagged words: [row][x, y, z][column]
         const unsigned tag = (epoch + (unsigned)step) & 0x7fffffffu;
         // ---- P1: gather, integrate, collide ------------------------------------------------------------------
@@ -226,19 +230,21 @@ oc_k_bandres(const __grid_constant__ OcConst c, const float4* __restrict__ A, co
             const float w = oc_u2f(hit ? OC_W_HIT : OC_W_PLAIN);
             xn[lp] = make_float4(n.x, n.y, n.z, w);
             if ((oj < 2 && b > 0) || (oj >= R - 2 && b + 1 < nb)) {
-                if (OC_BANDRES_LL) {
-                    unsigned long long* e = exl + (size_t)j * 3 * U + i;
-                    oc_bandres_put(e, n.x, tag); oc_bandres_put(e + U, n.y, tag); oc_bandres_put(e + 2 * U, n.z, tag | (hit ? 0x80000000u : 0u));
-                } else {
-                    __stcg(exw + (size_t)j * U + i, make_float4(n.x, n.y, n.z, w));
-                }
+#if OC_BANDRES_LL
+                unsigned long long* e = exl + (size_t)j * 3 * U + i;
+                ctx.put(e, n.x, tag); ctx.put(e + U, n.y, tag); ctx.put(e + 2 * U, n.z, tag | (hit ? 0x80000000u : 0u));
+#else
+                __stcg(exw + (size_t)j * U + i, make_float4(n.x, n.y, n.z, w));
+#endif
             }
         }
-        __syncthreads();
-        if (!OC_BANDRES_LL && tid == 0) {     // (fence + release by one thread after the barrier: cumulative over the CTA's stores, as in OcDevCtx2::publish)
+        ctx.sync();
+#if !OC_BANDRES_LL
+        if (tid == 0) {                       // (fence + release by one thread after the barrier: cumulative over the CTA's stores, as in OcDevCtx2::publish)
             __threadfence();
             asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(flags + b), "r"(epoch + (unsigned)step) : "memory");
         }
+#endif
         // ---- P2: derived state of the own rows (in place: nobody reads another particle's in this phase) ---------
         for (int op = tid; op < R * U; op += T) {
             const int lp = op + 2 * U;
@@ -252,21 +258,21 @@ oc_k_bandres(const __grid_constant__ OcConst c, const float4* __restrict__ A, co
         bool ok = true;
         if (step < n_steps) {
             // ---- the neighbours' boundary rows of this substep ---------------------------------------------------
-            if (!OC_BANDRES_LL) {
-                if (tid == 0 && b > 0)       ok = oc_bandres_wait(c, flags + b - 1, epoch + (unsigned)step);
-                if (tid == 32 && b + 1 < nb) ok = oc_bandres_wait(c, flags + b + 1, epoch + (unsigned)step);
-                if (!__syncthreads_and(ok)) return;                      // a neighbour never arrived: error word set (oc_flag_wait)
-            }
+#if !OC_BANDRES_LL
+            if (tid == 0 && b > 0)       ok = oc_bandres_wait(c, flags + b - 1, epoch + (unsigned)step);
+            if (tid == 32 && b + 1 < nb) ok = oc_bandres_wait(c, flags + b + 1, epoch + (unsigned)step);
+            if (!ctx.sync_and(ok)) return;                               // a neighbour never arrived: error word set (oc_flag_wait)
+#endif
             const int n_up = (r0 - h0) * U, n_dn = (h1 - r1) * U;
             for (int e = tid; e < n_up + n_dn; e += T) {
                 const int lp = e < n_up ? (h0 - jbase) * U + e : (r1 - jbase) * U + (e - n_up);
                 float4 a;
-                if (OC_BANDRES_LL) {
-                    const int lj = lp / U, i = lp - lj * U;
-                    ok &= oc_bandres_get(c, exl + ((long long)(jbase + lj) * 3 * U + i), U, tag, a);
-                } else {
-                    a = __ldcg(exw + ((long long)jbase * U + lp));
-                }
+#if OC_BANDRES_LL
+                const int lj = lp / U, i = lp - lj * U;
+                ok &= ctx.get(c, exl + ((long long)(jbase + lj) * 3 * U + i), U, tag, a);
+#else
+                a = __ldcg(exw + ((long long)jbase * U + lp));
+#endif
                 const float4 ol = xc[lp];
                 f3 d = make_f3(0.0f, 0.0f, 0.0f);
                 if (!oc_hit(a.w)) d = make_f3(M::sub(a.x, ol.x), M::sub(a.y, ol.y), M::sub(a.z, ol.z));
@@ -275,9 +281,7 @@ oc_k_bandres(const __grid_constant__ OcConst c, const float4* __restrict__ A, co
                 vv[lp] = make_float4(v.x, v.y, v.z, 0.0f);
             }
         }
-        if (OC_BANDRES_LL) { if (!__syncthreads_and(ok)) return; }       // a neighbour's rows never arrived: error word set (oc_bandres_get)
-        else
-        __syncthreads();
+        if (!ctx.sync_and(ok)) return;                                   // a neighbour's rows never arrived: error word set (oc_bandres_get)
         cur = nxt;
     }
     // ---- store: X(t+n) and, for more than one substep, X(t+n-1) --------------------------------------------
@@ -287,5 +291,28 @@ oc_k_bandres(const __grid_constant__ OcConst c, const float4* __restrict__ A, co
         dst[g] = s.X(cur)[lp];
         if (n_steps > 1) dst_prev[g] = s.X(cur ^ 1)[lp];
     }
+}
+
+#ifdef __CUDACC__
+struct OcBandresCtx {
+    __device__ __forceinline__ int tid() const { return threadIdx.x; }
+    __device__ __forceinline__ int nthreads() const { return blockDim.x; }
+    __device__ __forceinline__ int band() const { return blockIdx.x; }
+    __device__ __forceinline__ int nbands() const { return gridDim.x; }
+    __device__ __forceinline__ void sync() const { __syncthreads(); }
+    __device__ __forceinline__ bool sync_and(bool ok) const { return __syncthreads_and(ok) != 0; }
+    __device__ __forceinline__ unsigned char* smem() const { extern __shared__ __align__(16) unsigned char oc_dyn_smem[]; return oc_dyn_smem; }
+    __device__ __forceinline__ void put(unsigned long long* p, float v, unsigned tag) const { oc_bandres_put(p, v, tag); }
+    __device__ __forceinline__ bool get(const OcConst& c, const unsigned long long* p, int stride, unsigned tag, float4& a) const { return oc_bandres_get(c, p, stride, tag, a); }
+};
+
+template <class M, int TT>
+__global__ void __launch_bounds__(TT, 1)
+oc_k_bandres(const __grid_constant__ OcConst c, const float4* __restrict__ A, const float4* __restrict__ B,
+             float4* __restrict__ dst, float4* __restrict__ dst_prev, int n_steps,
+             void* __restrict__ ex_, unsigned* __restrict__ flags, unsigned epoch, int rmax)
+{
+    OcBandresCtx ctx;
+    oc_bandres_body<M, OcBandresCtx>(ctx, c, A, B, dst, dst_prev, n_steps, ex_, flags, epoch, rmax);
 }
 #endif

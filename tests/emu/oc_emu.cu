@@ -439,6 +439,157 @@ static int emu_provot(EmuCloth* e, int threads)
     return rc;
 }
 
+
+#if EMU_HAS(0)
+// ------------------------------------------------------------------------------------------------
+// kernel 8 (oc_k_bandres): ALL the CTAs of the grid run concurrently - their threads are fibers of one scheduler - because
+// the bands wait for each other's boundary rows inside the launch.  A thread is READY, AT a CTA BARRIER (released when all
+// the live threads of its CTA are there), POLLING (a tagged word has not arrived: resumed in the next round) or DONE.
+// ------------------------------------------------------------------------------------------------
+struct EmuGrid;
+struct EmuGridCtx {
+    int tid_, nthreads_, band_, nbands_;
+    unsigned char* smem_;
+    EmuGrid* g; int fib;
+    int tid() const { return tid_; }
+    int nthreads() const { return nthreads_; }
+    int band() const { return band_; }
+    int nbands() const { return nbands_; }
+    unsigned char* smem() const { return smem_; }
+    void sync();
+    bool sync_and(bool ok);
+    void put(unsigned long long* p, float v, unsigned tag) const { *(volatile unsigned long long*)p = ((unsigned long long)tag << 32) | (unsigned long long)oc_f2u(v); }
+    bool get(const OcConst&, const unsigned long long* p, int stride, unsigned tag, float4& a);
+};
+struct EmuGrid {
+    ucontext_t sched;
+    std::vector<ucontext_t> fib;
+    std::vector<char*> stacks;
+    std::vector<int> state;                 // 0 ready, 1 at barrier, 2 polling, 3 done
+    std::vector<long> nsync;
+    std::vector<EmuGridCtx> ctx;
+    std::vector<int> vote;                  // per thread: its argument of the current sync_and
+    std::function<void(EmuGridCtx&)> body;
+    int cur; long polls;
+};
+static EmuGrid* g_grid = nullptr;
+void EmuGridCtx::sync() { g->state[fib] = 1; g->nsync[fib]++; swapcontext(&g->fib[fib], &g->sched); }
+bool EmuGridCtx::sync_and(bool ok)
+{
+    g->vote[fib] = ok ? 1 : 0;
+    sync();
+    bool r = true;
+    for (int t = 0; t < nthreads_; ++t) r = r && g->vote[band_ * nthreads_ + t] != 0;
+    sync();                                 // (everybody has read the votes before anybody casts the next one)
+    return r;
+}
+bool EmuGridCtx::get(const OcConst&, const unsigned long long* p, int stride, unsigned tag, float4& a)
+{
+    for (;;) {
+        const unsigned long long w0 = *(volatile const unsigned long long*)p, w1 = *(volatile const unsigned long long*)(p + stride), w2 = *(volatile const unsigned long long*)(p + 2 * stride);
+        if ((unsigned)(w0 >> 32) == tag && (unsigned)(w1 >> 32) == tag && ((unsigned)(w2 >> 32) & 0x7fffffffu) == tag) {
+            a = make_float4(oc_u2f((unsigned)w0), oc_u2f((unsigned)w1), oc_u2f((unsigned)w2), oc_u2f(((unsigned)(w2 >> 32) & 0x80000000u) ? OC_W_HIT : OC_W_PLAIN));
+            return true;
+        }
+        if (++g->polls > 50000000L) { a = make_float4(0.f, 0.f, 0.f, oc_u2f(OC_W_PLAIN)); return false; }      // a protocol bug: never arrives
+        g->state[fib] = 2;
+        swapcontext(&g->fib[fib], &g->sched);
+    }
+}
+static void grid_fiber_main()
+{
+    EmuGrid* g = g_grid;
+    const int f = g->cur;
+    g->body(g->ctx[f]);
+    g->state[f] = 3;
+    swapcontext(&g->fib[f], &g->sched);
+}
+// returns 0, -1 (barrier counts disagree inside a CTA / threads left a CTA whose others wait at a barrier), -5 (no progress)
+static int run_grid(int nctas, int nthreads, size_t smem_bytes, const std::function<void(EmuGridCtx&)>& body)
+{
+    static EmuGrid grid;
+    EmuGrid* g = &grid;
+    g_grid = g;
+    g->body = body;
+    const int nf = nctas * nthreads;
+    if ((int)g->stacks.size() < nf) {
+        const size_t old = g->stacks.size();
+        g->stacks.resize(nf);
+        for (size_t t = old; t < (size_t)nf; ++t) g->stacks[t] = (char*)malloc(kStack);
+    }
+    g->fib.resize(nf); g->state.assign(nf, 0); g->nsync.assign(nf, 0); g->ctx.resize(nf); g->vote.assign(nf, 1); g->polls = 0;
+    std::vector<unsigned char*> smem(nctas);
+    for (int b = 0; b < nctas; ++b) {
+        smem[b] = (unsigned char*)aligned_alloc(128, (smem_bytes + 127) / 128 * 128 + 128);
+        memset(smem[b], 0xCD, smem_bytes);
+        for (int t = 0; t < nthreads; ++t) {
+            const int f = b * nthreads + t;
+            EmuGridCtx& x = g->ctx[f];
+            x.tid_ = t; x.nthreads_ = nthreads; x.band_ = b; x.nbands_ = nctas; x.smem_ = smem[b]; x.g = g; x.fib = f;
+            getcontext(&g->fib[f]);
+            g->fib[f].uc_stack.ss_sp = g->stacks[f];
+            g->fib[f].uc_stack.ss_size = kStack;
+            g->fib[f].uc_link = &g->sched;
+            makecontext(&g->fib[f], grid_fiber_main, 0);
+        }
+    }
+    int rc = 0;
+    long rounds = 0;
+    for (;;) {
+        int alive = 0;
+        for (int bb = 0; bb < nctas; ++bb) {
+            const int b = g_order == 1 ? nctas - 1 - bb : bb;
+            for (int u = 0; u < nthreads; ++u) {
+                const int t = g_order == 0 ? u : (g_order == 1 ? nthreads - 1 - u : (int)(((unsigned)u * 7u + (unsigned)rounds * 3u) % (unsigned)nthreads));
+                const int f = b * nthreads + t;
+                if (g->state[f] == 3 || g->state[f] == 1) continue;
+                g->state[f] = 0;
+                g->cur = f;
+                swapcontext(&g->sched, &g->fib[f]);
+            }
+            // barrier of this CTA: released when every live thread is at it
+            int at = 0, live = 0, done = 0;
+            for (int t = 0; t < nthreads; ++t) { const int st = g->state[b * nthreads + t]; at += st == 1; live += st != 3; done += st == 3; }
+            if (live > 0 && at == live) {
+                if (done > 0) rc = -1;
+                long ns = -1;
+                for (int t = 0; t < nthreads; ++t) if (g->state[b * nthreads + t] == 1) { const long v = g->nsync[b * nthreads + t]; if (ns < 0) ns = v; else if (v != ns) rc = -1; }
+                for (int t = 0; t < nthreads; ++t) if (g->state[b * nthreads + t] == 1) g->state[b * nthreads + t] = 0;
+            }
+            alive += live;
+        }
+        if (alive == 0) break;
+        if (++rounds > 20000000L) { rc = -5; break; }
+    }
+    for (int b = 0; b < nctas; ++b) free(smem[b]);
+    return rc;
+}
+
+// kernel 8: TW = threads per CTA, RS = "SMs" the plan may use (bands <= RS); all the substeps of the launch in one grid
+template <class M>
+static int emu_bandres(EmuCloth* e, const OcLaunch& L, int TW, int RS)
+{
+    const OcConst& k = e->k;
+    if (e->q.band || k.batch != 1 || e->p.provot || e->q.xv) return -2;
+    int nb = 0, rmax = 0;
+    if (!oc_bandres_plan(k.U, k.V, RS > 0 ? RS : 6, &nb, &rmax)) return -2;
+    const size_t NG = (size_t)k.U * k.V;
+    static std::vector<unsigned long long> ex;
+    static unsigned epoch = 0;
+    if (ex.size() != NG * 6) { ex.assign(NG * 6, 0ull); epoch = 0; }
+    const float4* A = e->buf[L.src_a].data();
+    const float4* B = e->buf[L.src_b].data();
+    float4* d0 = e->buf[L.dst].data();
+    float4* d1 = e->buf[L.dst_prev].data();
+    const unsigned ep = epoch;
+    const int rc = run_grid(nb, TW > 0 ? TW : 32, OcBandresSmem::bytes(k.U, rmax), [&](EmuGridCtx& ctx) {
+        oc_bandres_body<M, EmuGridCtx>(ctx, k, A, B, d0, d1, L.S, ex.data(), nullptr, ep, rmax);
+    });
+    epoch += (unsigned)L.S;
+    return rc;
+}
+#endif
+
 extern "C" {
 
 void* emu_create(const oc_params* p)
@@ -531,11 +682,16 @@ int emu_step(void* h, int n, int kernel, int exact, int k, int TW, int RS)
         int kk = 1;
         if (kernel == 2) { int w = n < k ? n : k; kk = (TW == 16 && w <= 3) ? w : oc_host_pick_stages(w); }
         if (kernel == 4) kk = OC_RESIDENT_MAX_STEPS;
+        if (kernel == 8) kk = OC_BANDRES_MAX_STEPS;
         if (e->p.provot || e->q.xv) kk = 1;
         oc_host_next_launch(e->q, n, kk, L);
         if (kernel == 4) {
             int r = exact ? emu_resident<MathExact>(e, L, TW) : emu_resident<MathFast>(e, L, TW);
             if (r == -2) return -2;
+            rc |= r;
+        } else if (kernel == 8) {
+            int r = exact ? emu_bandres<MathExact>(e, L, TW, RS) : emu_bandres<MathFast>(e, L, TW, RS);
+            if (r == -2 || r == -5) return r;
             rc |= r;
         } else if (kernel == 7) {
             int r = emu_disp_stream2(e, L, exact, TW, RS);

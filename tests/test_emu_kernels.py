@@ -447,3 +447,44 @@ def test_bandres_plan_cuts_every_cloth_into_bands_that_fit():
         assert prev == V
     assert fits[(256, 256)] and fits[(512, 512)] and fits[(512, 576)] and fits[(100, 1000)] and fits[(64, 48)]
     assert not fits[(1024, 1024)] and not fits[(2048, 2048)] and not fits[(4096, 16)] and not fits[(5, 3)]
+
+
+BANDRES = 8
+
+
+@pytest.mark.parametrize("nx,ny,pre,calls,T,sms", [(37, 23, 1900, (1, 2, 5, 1, 9), 32, 6), (64, 48, 1700, (7, 1, 12), 64, 5), (20, 66, 900, (3, 4, 1, 1, 6), 32, 8),
+                                                   (21, 21, 1800, (25,), 32, 3), (5, 4, 3, (30,), 32, 2), (70, 9, 400, (4, 4), 32, 4)])
+def test_bandres_kernel_body_and_exchange(nx, ny, pre, calls, T, sms):
+    """Kernel 8 (oc_k_bandres) on the CPU: all the CTAs of the launch run concurrently as fibers of one scheduler, so the
+    bands really wait for each other's tagged boundary words inside the launch.  Bitwise against the oracle over several
+    oc_step calls (the tags count on from launch to launch; n = 1 writes one buffer, n > 1 two), band heights that do
+    not divide the cloth, a single band, cloths as narrow as the stencil."""
+    x0, xl0 = helpers.developed_state(nx, ny, pre)
+    o = Oracle(nx, ny); o.set_state(x0, xl0)
+    e = Emu(nx, ny); e.upload(x0, xl0)
+    for n in calls:
+        e.step(n, kernel=BANDRES, exact=1, TW=T, RS=sms)
+        o.step(n)
+        x, xl = e.download()
+        ox, oxl = o.state()
+        assert bitwise_equal(x, ox) and bitwise_equal(xl, oxl), (nx, ny, n)
+
+
+@pytest.mark.parametrize("order", [1, 2])
+def test_bandres_is_independent_of_thread_and_cta_schedule(order):
+    """No race inside a phase and none in the exchange protocol: CTAs and threads resumed in reverse / pseudo-random order."""
+    L = helpers.emu_lib()
+    x0, xl0 = helpers.developed_state(40, 33, 1700)
+    ref = Emu(40, 33); ref.upload(x0, xl0); ref.step(14, kernel=BANDRES, exact=1, TW=32, RS=6)
+    rx, rxl = ref.download()
+    L.emu_set_order(order)
+    try:
+        e = Emu(40, 33); e.upload(x0, xl0); e.step(14, kernel=BANDRES, exact=1, TW=32, RS=6)
+        x, xl = e.download()
+    finally:
+        L.emu_set_order(0)
+    assert bitwise_equal(x, rx) and bitwise_equal(xl, rxl)
+    # tolerance mode: the same bits whatever the number of bands (one arithmetic path)
+    a = Emu(40, 33); a.upload(x0, xl0); a.step(10, kernel=BANDRES, exact=0, TW=32, RS=6)
+    b = Emu(40, 33); b.upload(x0, xl0); b.step(10, kernel=BANDRES, exact=0, TW=32, RS=2)
+    assert bitwise_equal(a.download()[0], b.download()[0])
