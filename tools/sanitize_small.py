@@ -9,7 +9,10 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import opencloth_b200 as oc  # noqa: E402
 
+only = [int(t) for t in os.environ.get("OC_SAN_KERNELS", "").split(",") if t]      # e.g. OC_SAN_KERNELS=8: that kernel only
 for kernel, k in ((1, 1), (2, 1), (2, 4), (3, 1), (4, 1), (5, 1), (6, 1), (7, 1), (8, 1)):
+    if only and kernel not in only:
+        continue
     for exact in (1, 0):
         for nx, ny, batch in ((150, 70, 1), (37, 23, 3), (260, 40, 1), (21, 21, 2)):
             c = oc.Cloth(nx, ny, batch=batch, kernel=kernel, exact=exact, substeps_per_launch=k)
@@ -18,6 +21,8 @@ for kernel, k in ((1, 1), (2, 1), (2, 4), (3, 1), (4, 1), (5, 1), (6, 1), (7, 1)
             assert np.isfinite(x).all()
             c.close()
             print("ok", kernel, k, exact, nx, ny, batch, flush=True)
+if only:
+    sys.exit(0)
 # row bands in one process (halo exchange copies, band launches)
 import ctypes  # noqa: E402
 from opencloth_b200 import _abi  # noqa: E402
