@@ -494,6 +494,18 @@ def run_ours(args):
             other.close()
             line["other_mode"] = {"mode": "fast" if exact else "exact", "value": o_val, "unit": UNIT, "steps": n_o,
                                   "roofline_frac": o_val * ALG_BYTES_PER_UPDATE / 1e9 / peak}
+        if world == 1 and K < 500 and args.workload == "cloth":
+            # a short timed region carries the fill of the launch chain's first step and the drain of its last one (about one
+            # tile lifetime, ~60-90 us, 7 % of 20 steps at 2048^2): the same workload, same mode, over 2000 steps for comparison
+            ss = oc.Cloth(nx, ny, device=local, exact=exact, substeps_per_launch=args.k)
+            ss.step(W)
+            n_s = 2000
+            s_ms = ss.step_timed(n_s)
+            ss.close()
+            s_val = particles_total * n_s / (s_ms * 1e-3)
+            line["steady_state"] = {"value": s_val, "unit": UNIT, "steps": n_s, "ms_per_step": s_ms / n_s, "mode": args.mode,
+                                    "roofline_frac": s_val * ALG_BYTES_PER_UPDATE / 1e9 / peak,
+                                    "note": "same workload and mode over 2000 steps (CUDA events inside oc_step_timed); `value` above is the K-step figure"}
         if world == 1 and args.workload == "cloth" and nx != 8192:
             # N > 1 runs split the 8192^2 cloth of BASELINE config 4 (strong scaling): its 1-GPU rate, measured here, is
             # the base a parallel efficiency has to be computed against (not this line's 2048^2 value)
